@@ -1,0 +1,54 @@
+"""Seeded, well-conditioned parity fixtures (weights + inputs) shared by tests, smoke and golden generation.
+
+TEST INFRASTRUCTURE ONLY.  Default random init is a degenerate parity fixture (SURVEY.md
+section 0 item 10: every LV probability within 2e-2 of 0.5), so the fixtures *calibrate* the
+seeded random weights the way training would have: every BatchNorm's running statistics are
+set to the statistics of the activations it sees on a synthetic clip, then the segmentation
+head is scaled so the logit difference has a chosen spread and the motion head so the flow
+spans a chosen number of pixels.  Same recipe on both sides of every comparison.
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+import clasfv_b200.synthetic as synthetic
+from oracle import model_ref
+
+CAL_SHAPE = (32, 112, 112)    # (T, H, W) of the calibration clip: the production clip shape
+
+
+def clip_from_video(video, start=0, length=32):
+    return torch.from_numpy(np.ascontiguousarray(video[:, start:start + length])).unsqueeze(0)
+
+
+@functools.lru_cache(maxsize=4)
+def _calibrated(seed, logit_std, flow_px):
+    sd = synthetic.random_state_dict(seed)
+    t, h, w = CAL_SHAPE
+    x = clip_from_video(synthetic.synthetic_echo_video(t, h, w, seed=seed + 1000), 0, t)
+    model_ref.forward(sd, x, calibrate=True)
+    feat = model_ref.decoder_features(sd, x)
+    seg = F.conv3d(feat, sd["segmentation_head.weight"], sd["segmentation_head.bias"])
+    diff = seg[:, 1] - seg[:, 0]
+    sd["segmentation_head.weight"] = sd["segmentation_head.weight"] * (logit_std / float(diff.std()))
+    seg = F.conv3d(feat, sd["segmentation_head.weight"], None)
+    sd["segmentation_head.bias"] = torch.stack([(seg[:, 1] - seg[:, 0]).mean() / 2, -(seg[:, 1] - seg[:, 0]).mean() / 2]).float()
+    mot = F.conv3d(feat, sd["motion_head.weight"], None)
+    # flow in pixels = tanh(m) * W/2 at the 112-wide production size
+    sd["motion_head.weight"] = sd["motion_head.weight"] * ((flow_px / 56.0) / float(mot.std()))
+    sd["motion_head.bias"] = torch.zeros(4)
+    return {k: v.clone() for k, v in sd.items()}
+
+
+def calibrated_state_dict(seed=0, logit_std=3.0, flow_px=3.0, prefix=""):
+    return {prefix + k: v.clone() for k, v in _calibrated(seed, float(logit_std), float(flow_px)).items()}
+
+
+def synthetic_clip(num_frames=32, height=112, width=112, seed=0, batch=1):
+    vids = [clip_from_video(synthetic.synthetic_echo_video(num_frames, height, width, seed=seed + i), 0, num_frames)
+            for i in range(batch)]
+    return torch.cat(vids, 0)

@@ -1,0 +1,141 @@
+"""The oracle restatements against golden vectors produced by the UNMODIFIED reference
+(oracle/make_golden.py).  Runs on CPU; this is what pins the oracle on the GPU box, where
+/root/reference does not exist."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import clasfv_b200.synthetic as synthetic
+from oracle import fixtures, fuse_ref, model_ref
+from oracle.make_golden import stub_model
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_known_answers_of_the_architecture():
+    # every reference notebook prints "R2+1D MotionNet has 31575731 parameters."
+    spec = synthetic.state_dict_spec()
+    assert len(spec) == 242
+    n_params = sum(int(np.prod(s)) for _k, s, kind in spec if kind in ("conv", "bn_weight", "bn_bias", "bias", "fc"))
+    assert n_params == 31575731
+    mids = [synthetic.midplanes(i, p) for _n, i, p, _s in synthetic.TRUNK_LAYERS]
+    mids2 = [synthetic.midplanes(p, p) for _n, _i, p, _s in synthetic.TRUNK_LAYERS]
+    assert mids == [144, 230, 460, 921] and mids2 == [144, 288, 576, 1152]
+
+
+def test_model_restatement_matches_reference_class(golden_dir):
+    g = _load(golden_dir, "model_forward.npz")
+    sd = fixtures.calibrated_state_dict(0)
+    l1 = sum(float(v.double().abs().sum()) for v in sd.values())
+    assert abs(l1 - float(g["weights_l1norm"])) / float(g["weights_l1norm"]) < 1e-5, "weight recipe drifted"
+    assert int(g["param_count"]) == 31575731
+    for tag in ("a", "b"):
+        seg, mot = model_ref.forward(sd, torch.from_numpy(g[f"x_{tag}"]))
+        assert seg.shape == g[f"seg_{tag}"].shape and mot.shape == g[f"motion_{tag}"].shape
+        # tolerance: recalibration on another CPU may move BN statistics by ~1e-6 relative
+        np.testing.assert_allclose(seg.numpy(), g[f"seg_{tag}"], atol=2e-4, rtol=1e-4)
+        np.testing.assert_allclose(mot.numpy(), g[f"motion_{tag}"], atol=2e-5, rtol=1e-4)
+        assert float(mot.abs().max()) < 1.0
+
+
+def test_model_restatement_full_size_clip(golden_dir):
+    g = _load(golden_dir, "model_forward.npz")
+    sd = fixtures.calibrated_state_dict(0)
+    seg, mot = model_ref.forward(sd, fixtures.synthetic_clip(32, 112, 112, seed=13))
+    assert tuple(seg.shape) == (1, 2, 32, 112, 112) and tuple(mot.shape) == (1, 4, 32, 112, 112)
+    np.testing.assert_allclose(seg.numpy()[:, :, ::4, ::8, ::8], g["seg_full_sub"], atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(mot.numpy()[:, :, ::4, ::8, ::8], g["motion_full_sub"], atol=2e-5, rtol=1e-4)
+
+
+def test_warp_primitive(golden_dir):
+    g = _load(golden_dir, "warp.npz")
+    src, flow = torch.from_numpy(g["src"]), torch.from_numpy(g["flow"])
+    grid = fuse_ref.generate_2dmotion_field(src, flow)
+    np.testing.assert_array_equal(grid.numpy(), g["grid"])
+    np.testing.assert_array_equal(fuse_ref.warp(src, flow).numpy(), g["warped"])
+    # zero flow is NOT the identity: x_src = j*W/(W-1) - 0.5, clamped
+    cols = g["zero_flow_cols"]
+    j = np.arange(112)
+    expect = np.clip(j * 112 / 111 - 0.5, 0, 111)
+    np.testing.assert_allclose(cols, expect, atol=2e-4)
+
+
+@pytest.mark.parametrize("length", [75, 48, 64, 80])
+def test_divide_to_consecutive_clips(golden_dir, length):
+    g = _load(golden_dir, "divide_clips.npz")
+    video = synthetic.synthetic_echo_video(length, 112, 112, seed=20 + length)
+    clips = fuse_ref.divide_to_consecutive_clips(video, interpolate_last=True)
+    assert list(clips.shape) == list(g[f"shape_{length}"]) and str(clips.dtype) == str(g[f"dtype_{length}"])
+    np.testing.assert_array_equal(clips[:, :, :, ::16, ::16], g[f"sub_{length}"])
+    assert abs(clips.sum() - float(g[f"sum_{length}"])) < 1e-6 * abs(float(g[f"sum_{length}"]))
+
+
+def test_clip_count_table_half_to_even():
+    # 48->2, 80->2, 112->4, 176->6, 175->5
+    for length, n in ((48, 2), (80, 2), (112, 4), (176, 6), (175, 5), (128, 4), (200, 6)):
+        assert fuse_ref.num_consecutive_clips(length) == n
+    plans = {(128, 1): 4, (200, 32): 185, (200, 5): 30, (175, 32): 159, (2000, 32): 1984}
+    for (t, f), total in plans.items():
+        shifts = fuse_ref.plan_shifts(t, 1, f)
+        assert sum(fuse_ref.num_consecutive_clips(t - s) for s in shifts) == total
+
+
+def test_temporal_resample_formula_matches_interpolate():
+    rng = np.random.default_rng(0)
+    for l_in, l_out in ((75, 64), (48, 64), (64, 75), (199, 192), (33, 32)):
+        x = rng.random((2, l_in, 5, 7)).astype(np.float32)
+        a = fuse_ref.temporal_resample(x, l_out)
+        b = fuse_ref.temporal_resample_formula(x, l_out)
+        np.testing.assert_allclose(a, b, atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize("tag", ["f5", "f1", "f12"])
+def test_fusion_control_flow(golden_dir, tag):
+    g = _load(golden_dir, "fusion_flow.npz")
+    length, f, step, seed = [int(v) for v in g[f"args_{tag}"]]
+    video = synthetic.synthetic_echo_video(length, 112, 112, seed=seed)
+    fused = fuse_ref.segment_a_video_with_fusion(video, stub_model, interpolate_last=True, step=step, num_clips=f)
+    assert list(fused.shape) == list(g[f"shape_{tag}"]) and str(fused.dtype) == str(g[f"dtype_{tag}"])
+    ref_bits = np.unpackbits(g[f"bits_{tag}"])[:fused.size].reshape(fused.shape)
+    np.testing.assert_array_equal(fused, ref_bits)
+    assert 0.02 < fused.mean() < 0.9          # the fixture is not degenerate
+
+
+def test_host_helpers(golden_dir):
+    g = _load(golden_dir, "host_helpers.npz")
+    np.testing.assert_array_equal(fuse_ref.zeroone_normalizer(g["v"].copy()), g["norm"])
+
+
+def test_fusion_error_behaviour():
+    video = synthetic.synthetic_echo_video(40, 16, 16, seed=1)
+    # T=40, f=10: num_clips clamps to (40-32)//1 = 8 (fuse_utils.py:38-39)
+    assert fuse_ref.plan_shifts(40, 1, 10) == list(range(8))
+    # T<32: "Video is too short", one shift (fuse_utils.py:40-42)
+    assert fuse_ref.plan_shifts(20, 1, 10) == [0]
+    # 32 <= T < 32+step ... num_clips == 0 -> IndexError at fuse_utils.py:82
+    with pytest.raises(IndexError):
+        fuse_ref.segment_a_video_with_fusion(video[:, :32], stub_model, step=1, num_clips=10)
+
+
+def test_warp_fuse_oracle_properties():
+    g = torch.Generator().manual_seed(0)
+    n, h, w = 5, 16, 24
+    logits = torch.randn(n, 2, 32, h, w, generator=g)
+    prob = torch.softmax(logits, 1)
+    motion = torch.tanh(0.05 * torch.randn(n, 4, 32, h, w, generator=g))
+    starts = list(range(n))
+    acc, cnt, mask = fuse_ref.warp_fuse(prob, motion, starts, 32 + n - 1)
+    # bilinear weights sum to one: the two class sums add up to the vote count
+    np.testing.assert_allclose((acc[:, 0] + acc[:, 1]).numpy(), cnt.view(-1, 1, 1).expand(-1, h, w).numpy(), atol=1e-4)
+    assert int(cnt[0]) == 2 and int(cnt.max()) == 3 * n       # frame 0: direct + one backward hop
+    # linearity in prob
+    acc2, _, _ = fuse_ref.warp_fuse(2 * prob, motion, starts, 32 + n - 1)
+    np.testing.assert_allclose(acc2.numpy(), 2 * acc.numpy(), rtol=1e-6, atol=1e-6)
+    # edge hops add exactly the two unsupervised flows per clip
+    _, cnt_e, _ = fuse_ref.warp_fuse(prob, motion, starts, 32 + n + 3, edge_hops=True)
+    _, cnt_s, _ = fuse_ref.warp_fuse(prob, motion, starts, 32 + n + 3, edge_hops=False)
+    assert int(cnt_e.sum() - cnt_s.sum()) == 2 * n - 1          # clip 0's backward hop from t=0 lands on frame -1: dropped

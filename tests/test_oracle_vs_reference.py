@@ -1,0 +1,52 @@
+"""Live pin of the oracle against the reference checkout (build container only; skipped on
+the GPU box, where /root/reference does not exist)."""
+import numpy as np
+import pytest
+import torch
+
+import clasfv_b200.synthetic as synthetic
+from oracle import fixtures, fuse_ref, model_ref, ref_import
+from oracle.make_golden import stub_model
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_import.import_reference()
+
+
+def test_state_dict_spec_matches_reference(ref):
+    sd = ref.R2plus1D_18_MotionNet(pretrained=False).state_dict()
+    spec = synthetic.state_dict_spec()
+    assert [k for k, _s, _k in spec] == list(sd.keys())
+    for k, shape, _kind in spec:
+        assert tuple(sd[k].shape) == tuple(shape)
+
+
+def test_forward_bit_identical_to_reference_class(ref):
+    sd = synthetic.random_state_dict(3)
+    net = ref.R2plus1D_18_MotionNet(pretrained=False)
+    net.load_state_dict(sd)
+    net.eval()
+    x = torch.rand(2, 3, 16, 32, 48, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        seg, mot = net(x)
+    seg2, mot2 = model_ref.forward(sd, x)
+    assert torch.equal(seg, seg2) and torch.equal(mot, mot2)
+
+
+def test_fusion_matches_reference_function(ref):
+    video = synthetic.synthetic_echo_video(80, 112, 112, seed=77)
+    a = ref.fuse_utils.segment_a_video_with_fusion(video, stub_model, interpolate_last=True, step=1, num_clips=7)
+    b = fuse_ref.segment_a_video_with_fusion(video, stub_model, interpolate_last=True, step=1, num_clips=7)
+    assert a.dtype == b.dtype and np.array_equal(a, b)
+
+
+def test_warp_matches_reference_function(ref):
+    g = torch.Generator().manual_seed(9)
+    src = torch.rand(1, 2, 20, 28, generator=g)
+    flow = torch.tanh(0.2 * torch.randn(1, 2, 20, 28, generator=g))
+    with ref_import.cuda_is_noop():
+        grid = ref.transform_utils.generate_2dmotion_field(src, flow)
+    assert torch.equal(grid, fuse_ref.generate_2dmotion_field(src, flow))
