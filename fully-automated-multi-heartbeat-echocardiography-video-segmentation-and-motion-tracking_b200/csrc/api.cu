@@ -1,0 +1,614 @@
+// api.cu - the C ABI of libclasfv_b200.so (include/clasfv_b200.h): handle lifetime, weight folding and
+// packing, the layer schedule of the network, and thin argument-checking wrappers over the kernels.
+#include "internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace clasfv {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+constexpr float BN_EPS = 1e-5f;
+constexpr int DEC = 64;                 // decoder width
+constexpr int STEM_MID = 45, STEM_MID_PAD = 64;
+
+struct HostTensor { std::vector<int64_t> shape; std::vector<float> data; };
+
+struct PackedConv {
+  int cin = 0, cout = 0, cin_pad = 0, cout_pad = 0;
+  int kt = 1, kh = 1, kw = 1, st = 1, sh = 1, sw = 1, pt = 0, ph = 0, pw = 0;
+  void* w = nullptr;          // device [tap][cout_pad][cin_pad], fp32 or bf16
+  float* bias = nullptr;      // device [cout_pad] or nullptr
+};
+
+struct Block { PackedConv s1, t1, s2, t2, down; bool has_down = false; };
+
+// Small host->device tables (clip offsets, fusion plans) go through a ring of pinned slots so that
+// back-to-back asynchronous calls never overwrite a slot whose copy is still in flight.
+struct TableRing {
+  static constexpr int SLOTS = 8;
+  static constexpr size_t SLOT_BYTES = 1 << 20;
+  char* host = nullptr; char* dev = nullptr; cudaEvent_t ev[SLOTS]; bool used[SLOTS]; int next = 0;
+  int init() {
+    CLASFV_CUDA(cudaMallocHost(&host, SLOTS * SLOT_BYTES));
+    CLASFV_CUDA(cudaMalloc(&dev, SLOTS * SLOT_BYTES));
+    for (int i = 0; i < SLOTS; ++i) { CLASFV_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); used[i] = false; }
+    return CLASFV_OK;
+  }
+  void destroy() {
+    if (host) cudaFreeHost(host);
+    if (dev) cudaFree(dev);
+    if (host) for (int i = 0; i < SLOTS; ++i) cudaEventDestroy(ev[i]);
+    host = dev = nullptr;
+  }
+  // stage `bytes` (already laid out by fill(host_slot)) and return the device address
+  template <typename Fill>
+  int upload(size_t bytes, cudaStream_t stream, Fill fill, void** dev_ptr) {
+    if (bytes > SLOT_BYTES) { set_error("table of %zu bytes exceeds the staging slot", bytes); return CLASFV_EINVAL; }
+    const int s = next; next = (next + 1) % SLOTS;
+    if (used[s]) CLASFV_CUDA(cudaEventSynchronize(ev[s]));
+    fill(host + (size_t)s * SLOT_BYTES);
+    CLASFV_CUDA(cudaMemcpyAsync(dev + (size_t)s * SLOT_BYTES, host + (size_t)s * SLOT_BYTES, bytes, cudaMemcpyHostToDevice, stream));
+    CLASFV_CUDA(cudaEventRecord(ev[s], stream));
+    used[s] = true;
+    *dev_ptr = dev + (size_t)s * SLOT_BYTES;
+    return CLASFV_OK;
+  }
+};
+
+}  // namespace
+}  // namespace clasfv
+
+using namespace clasfv;
+
+struct clasfv_handle {
+  int device = 0, num_sms = 0;
+  std::map<std::string, HostTensor> tensors;
+  bool finalized = false;
+  int precision = CLASFV_F32;
+  bool force_simt = false;
+  std::vector<void*> dev_allocs;       // packed weights
+  // packed network
+  float* stem_w = nullptr; float* stem_b = nullptr;
+  PackedConv stem_t;
+  Block blocks[4][2];
+  PackedConv lateral[5];
+  float *b1 = nullptr, *w2 = nullptr, *b2 = nullptr, *wh = nullptr, *bh = nullptr;
+  // workspace
+  void* ws = nullptr; size_t ws_bytes = 0;
+  TableRing ring;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+const HostTensor* find_tensor(const clasfv_handle* h, const std::string& key) {
+  auto it = h->tensors.find(key);
+  return it == h->tensors.end() ? nullptr : &it->second;
+}
+
+int need(const clasfv_handle* h, const std::string& key, std::vector<int64_t> shape, const HostTensor** out) {
+  const HostTensor* t = find_tensor(h, key);
+  if (!t) { set_error("finalize: state_dict tensor '%s' was never set", key.c_str()); return CLASFV_ESTATE; }
+  if (t->shape != shape) { set_error("finalize: tensor '%s' has the wrong shape", key.c_str()); return CLASFV_EINVAL; }
+  *out = t;
+  return CLASFV_OK;
+}
+
+// BatchNorm (inference) as y = x*scale + shift
+int bn_affine(const clasfv_handle* h, const std::string& key, int c, std::vector<float>* scale, std::vector<float>* shift) {
+  const HostTensor *g, *b, *m, *v;
+  int rc;
+  if ((rc = need(h, key + ".weight", {c}, &g))) return rc;
+  if ((rc = need(h, key + ".bias", {c}, &b))) return rc;
+  if ((rc = need(h, key + ".running_mean", {c}, &m))) return rc;
+  if ((rc = need(h, key + ".running_var", {c}, &v))) return rc;
+  scale->resize(c); shift->resize(c);
+  for (int i = 0; i < c; ++i) {
+    const float s = g->data[i] / std::sqrt(v->data[i] + BN_EPS);
+    (*scale)[i] = s; (*shift)[i] = b->data[i] - m->data[i] * s;
+  }
+  return CLASFV_OK;
+}
+
+int dev_upload(clasfv_handle* h, const void* src, size_t bytes, void** out) {
+  void* d = nullptr;
+  CLASFV_CUDA(cudaMalloc(&d, bytes));
+  h->dev_allocs.push_back(d);
+  CLASFV_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+  *out = d;
+  return CLASFV_OK;
+}
+
+// Pack (Cout,Cin,kt,kh,kw) fp32 -> [tap][cout_pad][cin_pad] with an optional per-output-channel scale,
+// zero-filled padding, in fp32 or bf16; upload.
+int pack_weight(clasfv_handle* h, const float* w, int cout, int cin, int cin_off, int cin_total, int taps, const float* scale,
+                int cout_pad, int cin_pad, int dtype, void** out) {
+  const size_t n = (size_t)taps * cout_pad * cin_pad;
+  std::vector<float> packed(n, 0.f);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int tap = 0; tap < taps; ++tap) {
+        const float v = w[((size_t)co * cin_total + cin_off + ci) * taps + tap] * (scale ? scale[co] : 1.f);
+        packed[((size_t)tap * cout_pad + co) * cin_pad + ci] = v;
+      }
+  if (dtype == CLASFV_F32) return dev_upload(h, packed.data(), n * sizeof(float), out);
+  std::vector<__nv_bfloat16> pb(n);
+  for (size_t i = 0; i < n; ++i) pb[i] = __float2bfloat16_rn(packed[i]);
+  return dev_upload(h, pb.data(), n * sizeof(__nv_bfloat16), out);
+}
+
+int pack_conv_bn(clasfv_handle* h, const std::string& conv_key, const std::string& bn_key, int cin, int cout, int kt, int kh, int kw,
+                 int st, int sh, int sw, int pt, int ph, int pw, int cin_pad, int cout_pad, PackedConv* pc) {
+  const HostTensor* w;
+  int rc;
+  if ((rc = need(h, conv_key + ".weight", {cout, cin, kt, kh, kw}, &w))) return rc;
+  std::vector<float> scale, shift;
+  if ((rc = bn_affine(h, bn_key, cout, &scale, &shift))) return rc;
+  pc->cin = cin; pc->cout = cout; pc->cin_pad = cin_pad; pc->cout_pad = cout_pad;
+  pc->kt = kt; pc->kh = kh; pc->kw = kw; pc->st = st; pc->sh = sh; pc->sw = sw; pc->pt = pt; pc->ph = ph; pc->pw = pw;
+  if ((rc = pack_weight(h, w->data.data(), cout, cin, 0, cin, kt * kh * kw, scale.data(), cout_pad, cin_pad, h->precision, &pc->w))) return rc;
+  std::vector<float> bias(cout_pad, 0.f);
+  for (int i = 0; i < cout; ++i) bias[i] = shift[i];
+  return dev_upload(h, bias.data(), bias.size() * sizeof(float), reinterpret_cast<void**>(&pc->bias));
+}
+
+void free_packed(clasfv_handle* h) {
+  for (void* p : h->dev_allocs) cudaFree(p);
+  h->dev_allocs.clear();
+  h->finalized = false;
+}
+
+inline int midplanes(int inplanes, int planes) { return (inplanes * planes * 27) / (inplanes * 9 + 3 * planes); }
+
+int ensure_workspace(clasfv_handle* h, size_t bytes) {
+  if (bytes <= h->ws_bytes) return CLASFV_OK;
+  if (h->ws) { CLASFV_CUDA(cudaDeviceSynchronize()); CLASFV_CUDA(cudaFree(h->ws)); h->ws = nullptr; h->ws_bytes = 0; }
+  cudaError_t e = cudaMalloc(&h->ws, bytes);
+  if (e != cudaSuccess) { set_error("workspace allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return CLASFV_ENOMEM; }
+  h->ws_bytes = bytes;
+  return CLASFV_OK;
+}
+
+ConvArgs make_conv(const PackedConv& pc, int n, int ti, int hi, int wi, const void* in, void* out, const void* residual, int relu,
+                   int act_dtype, int out_f32) {
+  ConvArgs a;
+  ConvShape& s = a.s;
+  s.n = n; s.ti = ti; s.hi = hi; s.wi = wi; s.cin = pc.cin_pad; s.cout = pc.cout_pad;
+  s.kt = pc.kt; s.kh = pc.kh; s.kw = pc.kw; s.st = pc.st; s.sh = pc.sh; s.sw = pc.sw; s.pt = pc.pt; s.ph = pc.ph; s.pw = pc.pw;
+  s.to = (ti + 2 * pc.pt - pc.kt) / pc.st + 1; s.ho = (hi + 2 * pc.ph - pc.kh) / pc.sh + 1; s.wo = (wi + 2 * pc.pw - pc.kw) / pc.sw + 1;
+  a.in = in; a.weight = pc.w; a.bias = pc.bias; a.residual = residual; a.out = out;
+  a.act_dtype = act_dtype; a.out_f32 = out_f32; a.relu = relu;
+  return a;
+}
+
+int run_conv(clasfv_handle* h, const ConvArgs& a, cudaStream_t stream) {
+  if (a.act_dtype == CLASFV_BF16 && !h->force_simt) return launch_conv_umma(a, h->num_sms, stream);
+  return launch_conv_simt(a, stream);
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+int clasfv_abi_version(void) { return CLASFV_ABI_VERSION; }
+const char* clasfv_last_error(void) { return g_error; }
+
+int clasfv_create(int device, clasfv_handle** out) {
+  if (!out) { set_error("clasfv_create: out is NULL"); return CLASFV_EINVAL; }
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    set_error("clasfv_create: no CUDA device available - this library has no CPU path");
+    return CLASFV_EUNSUPPORTED;
+  }
+  CLASFV_REQUIRE(device >= 0 && device < count, "clasfv_create: device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  CLASFV_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("clasfv_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return CLASFV_EUNSUPPORTED;
+  }
+  DeviceGuard guard(device);
+  clasfv_handle* h = new clasfv_handle();
+  h->device = device; h->num_sms = prop.multiProcessorCount;
+  const char* env = getenv("CLASFV_FORCE_SIMT");
+  h->force_simt = env && env[0] == '1';
+  int rc = h->ring.init();
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return CLASFV_OK;
+}
+
+void clasfv_destroy(clasfv_handle* h) {
+  if (!h) return;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  free_packed(h);
+  if (h->ws) cudaFree(h->ws);
+  h->ring.destroy();
+  delete h;
+}
+
+int clasfv_set_tensor(clasfv_handle* h, const char* key, const float* data_host, const int64_t* shape, int ndim) {
+  CLASFV_REQUIRE(h && key && data_host && (shape || ndim == 0) && ndim >= 0 && ndim <= 8, "clasfv_set_tensor: bad argument");
+  std::string k(key);
+  if (k.rfind("module.", 0) == 0) k = k.substr(7);
+  HostTensor t;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) { CLASFV_REQUIRE(shape[i] >= 0, "clasfv_set_tensor: negative extent"); t.shape.push_back(shape[i]); n *= shape[i]; }
+  t.data.assign(data_host, data_host + n);
+  h->tensors[k] = std::move(t);
+  h->finalized = false;
+  return CLASFV_OK;
+}
+
+int clasfv_finalize(clasfv_handle* h, int precision) {
+  CLASFV_REQUIRE(h, "clasfv_finalize: handle is NULL");
+  CLASFV_REQUIRE(precision == CLASFV_F32 || precision == CLASFV_BF16, "clasfv_finalize: unknown precision %d", precision);
+  DeviceGuard guard(h->device);
+  CLASFV_CUDA(cudaDeviceSynchronize());
+  free_packed(h);
+  h->precision = precision;
+  int rc;
+  const std::string p = "r2plus1d_model.";
+  // ---- stem: 1x7x7 conv + BN folded, fp32 [147][48]; channels padded to 64 in the activation
+  {
+    const HostTensor* w;
+    if ((rc = need(h, p + "stem.0.weight", {STEM_MID, 3, 1, 7, 7}, &w))) return rc;
+    std::vector<float> scale, shift;
+    if ((rc = bn_affine(h, p + "stem.1", STEM_MID, &scale, &shift))) return rc;
+    std::vector<float> pw(147 * 48, 0.f), pb(48, 0.f);
+    for (int co = 0; co < STEM_MID; ++co) {
+      for (int tap = 0; tap < 147; ++tap) pw[(size_t)tap * 48 + co] = w->data[(size_t)co * 147 + tap] * scale[co];
+      pb[co] = shift[co];
+    }
+    if ((rc = dev_upload(h, pw.data(), pw.size() * 4, reinterpret_cast<void**>(&h->stem_w)))) return rc;
+    if ((rc = dev_upload(h, pb.data(), pb.size() * 4, reinterpret_cast<void**>(&h->stem_b)))) return rc;
+    if ((rc = pack_conv_bn(h, p + "stem.3", p + "stem.4", STEM_MID, 64, 3, 1, 1, 1, 1, 1, 1, 0, 0, STEM_MID_PAD, 64, &h->stem_t))) return rc;
+  }
+  // ---- residual layers
+  const int planes_of[4] = {64, 128, 256, 512};
+  int inplanes = 64;
+  for (int l = 0; l < 4; ++l) {
+    const int planes = planes_of[l], stride = l == 0 ? 1 : 2;
+    for (int b = 0; b < 2; ++b) {
+      const int cin = b == 0 ? inplanes : planes, s = b == 0 ? stride : 1;
+      const int mid = midplanes(cin, planes), mid_pad = mid == 230 ? 240 : mid == 460 ? 480 : mid == 921 ? 960 : round_up(mid, 16);
+      const std::string k = p + "layer" + std::to_string(l + 1) + "." + std::to_string(b);
+      Block& blk = h->blocks[l][b];
+      if ((rc = pack_conv_bn(h, k + ".conv1.0.0", k + ".conv1.0.1", cin, mid, 1, 3, 3, 1, s, s, 0, 1, 1, cin, mid_pad, &blk.s1))) return rc;
+      if ((rc = pack_conv_bn(h, k + ".conv1.0.3", k + ".conv1.1", mid, planes, 3, 1, 1, s, 1, 1, 1, 0, 0, mid_pad, planes, &blk.t1))) return rc;
+      if ((rc = pack_conv_bn(h, k + ".conv2.0.0", k + ".conv2.0.1", planes, mid, 1, 3, 3, 1, 1, 1, 0, 1, 1, planes, mid_pad, &blk.s2))) return rc;
+      if ((rc = pack_conv_bn(h, k + ".conv2.0.3", k + ".conv2.1", mid, planes, 3, 1, 1, 1, 1, 1, 1, 0, 0, mid_pad, planes, &blk.t2))) return rc;
+      blk.has_down = (b == 0 && stride != 1);
+      if (blk.has_down &&
+          (rc = pack_conv_bn(h, k + ".downsample.0", k + ".downsample.1", cin, planes, 1, 1, 1, s, s, s, 0, 0, 0, cin, planes, &blk.down))) return rc;
+    }
+    inplanes = planes;
+  }
+  // ---- decoder: comb_1 (+BN1) split into five lateral 1x1x1 projections; comb_2 (+BN2); heads
+  {
+    const HostTensor *w1, *bb1, *w2, *bb2, *ws, *bs, *wm, *bm;
+    if ((rc = need(h, "comb_1_layer.weight", {DEC, 1024, 1, 1, 1}, &w1))) return rc;
+    if ((rc = need(h, "comb_1_layer.bias", {DEC}, &bb1))) return rc;
+    if ((rc = need(h, "comb_2_layer.weight", {DEC, DEC, 1, 1, 1}, &w2))) return rc;
+    if ((rc = need(h, "comb_2_layer.bias", {DEC}, &bb2))) return rc;
+    if ((rc = need(h, "segmentation_head.weight", {2, DEC, 1, 1, 1}, &ws))) return rc;
+    if ((rc = need(h, "segmentation_head.bias", {2}, &bs))) return rc;
+    if ((rc = need(h, "motion_head.weight", {4, DEC, 1, 1, 1}, &wm))) return rc;
+    if ((rc = need(h, "motion_head.bias", {4}, &bm))) return rc;
+    std::vector<float> s1, t1, s2, t2;
+    if ((rc = bn_affine(h, "comb_batch_norm_1", DEC, &s1, &t1))) return rc;
+    if ((rc = bn_affine(h, "comb_batch_norm_2", DEC, &s2, &t2))) return rc;
+    const int widths[5] = {64, 64, 128, 256, 512};
+    int off = 0;
+    for (int i = 0; i < 5; ++i) {
+      PackedConv& pc = h->lateral[i];
+      pc = PackedConv();
+      pc.cin = pc.cin_pad = widths[i]; pc.cout = pc.cout_pad = DEC;
+      if ((rc = pack_weight(h, w1->data.data(), DEC, widths[i], off, 1024, 1, s1.data(), DEC, widths[i], h->precision, &pc.w))) return rc;
+      off += widths[i];
+    }
+    std::vector<float> b1(DEC), w2p(DEC * DEC), b2(DEC), wh(6 * DEC), bh(6);
+    for (int j = 0; j < DEC; ++j) {
+      b1[j] = s1[j] * bb1->data[j] + t1[j];
+      b2[j] = s2[j] * bb2->data[j] + t2[j];
+      for (int k = 0; k < DEC; ++k) w2p[j * DEC + k] = w2->data[j * DEC + k] * s2[j];
+    }
+    for (int k = 0; k < DEC; ++k) {
+      wh[0 * DEC + k] = ws->data[k]; wh[1 * DEC + k] = ws->data[DEC + k];
+      for (int q = 0; q < 4; ++q) wh[(2 + q) * DEC + k] = wm->data[q * DEC + k];
+    }
+    bh[0] = bs->data[0]; bh[1] = bs->data[1];
+    for (int q = 0; q < 4; ++q) bh[2 + q] = bm->data[q];
+    if ((rc = dev_upload(h, b1.data(), b1.size() * 4, reinterpret_cast<void**>(&h->b1)))) return rc;
+    if ((rc = dev_upload(h, w2p.data(), w2p.size() * 4, reinterpret_cast<void**>(&h->w2)))) return rc;
+    if ((rc = dev_upload(h, b2.data(), b2.size() * 4, reinterpret_cast<void**>(&h->b2)))) return rc;
+    if ((rc = dev_upload(h, wh.data(), wh.size() * 4, reinterpret_cast<void**>(&h->wh)))) return rc;
+    if ((rc = dev_upload(h, bh.data(), bh.size() * 4, reinterpret_cast<void**>(&h->bh)))) return rc;
+  }
+  h->finalized = true;
+  return CLASFV_OK;
+}
+
+int64_t clasfv_workspace_bytes(const clasfv_handle* h) { return h ? (int64_t)h->ws_bytes : 0; }
+
+int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_offset_host, int64_t channel_stride,
+                   int n, int t, int height, int width, int out_kind, int out_dtype,
+                   void* seg_dev, void* motion_dev, void* stream_v) {
+  CLASFV_REQUIRE(h, "clasfv_forward: handle is NULL");
+  if (!h->finalized) { set_error("clasfv_forward: call clasfv_finalize first"); return CLASFV_ESTATE; }
+  CLASFV_REQUIRE(x_dev && seg_dev && motion_dev, "clasfv_forward: null buffer");
+  CLASFV_REQUIRE(n >= 1 && t >= 8 && t % 8 == 0 && height >= 16 && height % 16 == 0 && width >= 16 && width % 16 == 0,
+                 "clasfv_forward: need N >= 1, T %% 8 == 0, H %% 16 == 0, W %% 16 == 0 (got N=%d T=%d H=%d W=%d)", n, t, height, width);
+  CLASFV_REQUIRE(out_kind == CLASFV_OUT_LOGITS || out_kind == CLASFV_OUT_PROB, "clasfv_forward: bad out_kind");
+  CLASFV_REQUIRE(out_dtype == CLASFV_F32 || out_dtype == CLASFV_BF16, "clasfv_forward: bad out_dtype");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int act = h->precision;
+  const size_t es = act == CLASFV_F32 ? 4 : 2;
+  const int64_t thw = (int64_t)t * height * width;
+  if (!clip_offset_host) {
+    CLASFV_REQUIRE(channel_stride == 0 || channel_stride == thw, "clasfv_forward: dense input needs channel_stride == T*H*W");
+    channel_stride = thw;
+  }
+  // ---- geometry of the four resolutions
+  const int T[5] = {t, t, t / 2, t / 4, t / 8};
+  const int H[5] = {height / 2, height / 2, height / 4, height / 8, height / 16};
+  const int W[5] = {width / 2, width / 2, width / 4, width / 8, width / 16};
+  const int C[5] = {64, 64, 128, 256, 512};
+  int64_t P[5];
+  for (int i = 0; i < 5; ++i) P[i] = (int64_t)n * T[i] * H[i] * W[i];
+  // ---- workspace carve-up (256-byte aligned regions)
+  size_t total = 0;
+  auto region = [&](size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; };
+  int64_t mid_elems = 0;
+  for (int l = 0; l < 4; ++l)
+    for (int b = 0; b < 2; ++b) {
+      const Block& blk = h->blocks[l][b];
+      // s1 output lives at the block input's temporal extent and the block output's spatial extent
+      const int64_t e1 = (int64_t)n * (b == 0 ? T[l] : T[l + 1]) * H[l + 1] * W[l + 1] * blk.s1.cout_pad;
+      const int64_t e2 = P[l + 1] * blk.s2.cout_pad;
+      mid_elems = std::max(mid_elems, std::max(e1, e2));
+    }
+  const size_t o_s0 = region(P[0] * STEM_MID_PAD * es);
+  size_t o_f[5];
+  for (int i = 0; i < 5; ++i) o_f[i] = region(P[i] * C[i] * es);
+  const size_t o_mid = region(mid_elems * es);
+  const size_t o_ta = region(P[1] * 64 * es);
+  const size_t o_x1 = region(P[1] * 64 * es);
+  const size_t o_ds = region(P[2] * 128 * es);
+  size_t o_g[4];
+  for (int i = 0; i < 4; ++i) o_g[i] = region(P[i + 1] * DEC * sizeof(float));
+  int rc;
+  if ((rc = ensure_workspace(h, total))) return rc;
+  char* ws = static_cast<char*>(h->ws);
+  // ---- clip offsets
+  void* offs_dev = nullptr;
+  rc = h->ring.upload((size_t)n * sizeof(int64_t), stream, [&](char* dst) {
+    int64_t* o = reinterpret_cast<int64_t*>(dst);
+    for (int i = 0; i < n; ++i) o[i] = clip_offset_host ? clip_offset_host[i] : (int64_t)i * 3 * thw;
+  }, &offs_dev);
+  if (rc) return rc;
+  // ---- stem
+  StemArgs sa;
+  sa.x = x_dev; sa.clip_offset = static_cast<const int64_t*>(offs_dev); sa.channel_stride = channel_stride;
+  sa.n = n; sa.t = t; sa.h = height; sa.w = width; sa.weight = h->stem_w; sa.bias = h->stem_b; sa.out = ws + o_s0; sa.out_channels = STEM_MID_PAD; sa.out_dtype = act;
+  if ((rc = launch_stem(sa, stream))) return rc;
+  if ((rc = run_conv(h, make_conv(h->stem_t, n, T[0], H[0], W[0], ws + o_s0, ws + o_f[0], nullptr, 1, act, 0), stream))) return rc;
+  // ---- residual layers
+  for (int l = 0; l < 4; ++l) {
+    const void* in = ws + o_f[l];
+    int ti = T[l], hi = H[l], wi = W[l];
+    for (int b = 0; b < 2; ++b) {
+      const Block& blk = h->blocks[l][b];
+      void* out = b == 0 ? (void*)(ws + o_x1) : (void*)(ws + o_f[l + 1]);
+      ConvArgs c1 = make_conv(blk.s1, n, ti, hi, wi, in, ws + o_mid, nullptr, 1, act, 0);
+      if ((rc = run_conv(h, c1, stream))) return rc;
+      ConvArgs c2 = make_conv(blk.t1, n, c1.s.to, c1.s.ho, c1.s.wo, ws + o_mid, ws + o_ta, nullptr, 1, act, 0);
+      if ((rc = run_conv(h, c2, stream))) return rc;
+      ConvArgs c3 = make_conv(blk.s2, n, c2.s.to, c2.s.ho, c2.s.wo, ws + o_ta, ws + o_mid, nullptr, 1, act, 0);
+      if ((rc = run_conv(h, c3, stream))) return rc;
+      const void* res = in;
+      if (blk.has_down) {
+        if ((rc = run_conv(h, make_conv(blk.down, n, ti, hi, wi, in, ws + o_ds, nullptr, 0, act, 0), stream))) return rc;
+        res = ws + o_ds;
+      }
+      ConvArgs c4 = make_conv(blk.t2, n, c3.s.to, c3.s.ho, c3.s.wo, ws + o_mid, out, res, 1, act, 0);
+      if ((rc = run_conv(h, c4, stream))) return rc;
+      in = out; ti = c4.s.to; hi = c4.s.ho; wi = c4.s.wo;
+    }
+  }
+  // ---- decoder: lateral projections at native resolution (fp32 out), stem + layer1 share one map
+  if ((rc = run_conv(h, make_conv(h->lateral[0], n, T[0], H[0], W[0], ws + o_f[0], ws + o_g[0], nullptr, 0, act, 1), stream))) return rc;
+  if ((rc = run_conv(h, make_conv(h->lateral[1], n, T[1], H[1], W[1], ws + o_f[1], ws + o_g[0], ws + o_g[0], 0, act, 1), stream))) return rc;
+  for (int i = 2; i < 5; ++i)
+    if ((rc = run_conv(h, make_conv(h->lateral[i], n, T[i], H[i], W[i], ws + o_f[i], ws + o_g[i - 1], nullptr, 0, act, 1), stream))) return rc;
+  HeadArgs ha;
+  for (int i = 0; i < 4; ++i) { ha.g[i] = reinterpret_cast<const float*>(ws + o_g[i]); ha.tl[i] = T[i + 1]; ha.hl[i] = H[i + 1]; ha.wl[i] = W[i + 1]; }
+  ha.n = n; ha.t = t; ha.h = height; ha.w = width;
+  ha.b1 = h->b1; ha.w2 = h->w2; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;
+  ha.seg = seg_dev; ha.motion = motion_dev; ha.out_dtype = out_dtype; ha.out_kind = out_kind;
+  return launch_head(ha, stream);
+}
+
+int clasfv_warp(const float* src_dev, const float* flow_dev, float* out_dev, int n, int c, int height, int width, void* stream) {
+  CLASFV_REQUIRE(src_dev && flow_dev && out_dev && n >= 1 && c >= 1 && height >= 1 && width >= 1, "clasfv_warp: bad argument");
+  return launch_warp(src_dev, flow_dev, out_dev, n, c, height, width, static_cast<cudaStream_t>(stream));
+}
+
+int clasfv_motion_field(const float* flow_dev, float* grid_dev, int n, int height, int width, void* stream) {
+  CLASFV_REQUIRE(flow_dev && grid_dev && n >= 1 && height >= 1 && width >= 1, "clasfv_motion_field: bad argument");
+  return launch_motion_field(flow_dev, grid_dev, n, height, width, static_cast<cudaStream_t>(stream));
+}
+
+int clasfv_warp_fuse(clasfv_handle* h, const void* prob_dev, const void* motion_dev, int dtype,
+                     const int32_t* clip_start_host, int n_clips, int clip_len, int t_out, int height, int width,
+                     int edge_hops, int accumulate, float* acc_dev, int32_t* cnt_dev, uint8_t* mask_dev,
+                     int32_t* area_dev, void* stream_v) {
+  CLASFV_REQUIRE(h && prob_dev && motion_dev && clip_start_host && acc_dev, "clasfv_warp_fuse: null argument");
+  CLASFV_REQUIRE(dtype == CLASFV_F32 || dtype == CLASFV_BF16, "clasfv_warp_fuse: bad dtype");
+  CLASFV_REQUIRE(n_clips >= 1 && clip_len >= 1 && t_out >= 1 && height >= 1 && width >= 1, "clasfv_warp_fuse: bad extent");
+  for (int c = 1; c < n_clips; ++c) CLASFV_REQUIRE(clip_start_host[c] >= clip_start_host[c - 1], "clasfv_warp_fuse: clip starts must ascend");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  void* tab = nullptr;
+  const size_t bytes = sizeof(int32_t) * ((size_t)n_clips + 2 * (size_t)t_out);
+  int rc = h->ring.upload(bytes, stream, [&](char* dst) {
+    int32_t* starts = reinterpret_cast<int32_t*>(dst);
+    int32_t* lo = starts + n_clips;
+    int32_t* hi = lo + t_out;
+    memcpy(starts, clip_start_host, sizeof(int32_t) * n_clips);
+    // candidate clips of frame g: start in [g - clip_len, g + 1] (direct, forward hop, backward hop, edge hops)
+    int a = 0, b = 0;
+    for (int g = 0; g < t_out; ++g) {
+      while (a < n_clips && clip_start_host[a] < g - clip_len) ++a;
+      while (b < n_clips && clip_start_host[b] <= g + 1) ++b;
+      lo[g] = a; hi[g] = b;
+    }
+  }, &tab);
+  if (rc) return rc;
+  WarpFuseArgs a;
+  a.prob = prob_dev; a.motion = motion_dev; a.dtype = dtype;
+  a.clip_start = static_cast<const int32_t*>(tab); a.frame_lo = a.clip_start + n_clips; a.frame_hi = a.frame_lo + t_out;
+  a.n_clips = n_clips; a.clip_len = clip_len; a.t_out = t_out; a.h = height; a.w = width; a.edge_hops = edge_hops; a.accumulate = accumulate;
+  a.acc = acc_dev; a.cnt = cnt_dev; a.mask = mask_dev; a.area = area_dev;
+  return launch_warp_fuse(a, stream);
+}
+
+static int upload_shift_table(clasfv_handle* h, int n_shifts, const int32_t* start, const int32_t* len, const int32_t* nclips,
+                              const int32_t* base, int total_clips, cudaStream_t stream, ShiftTable* tab, const int32_t** clip_shift) {
+  void* dev = nullptr;
+  const size_t bytes = sizeof(int32_t) * (4 * (size_t)n_shifts + (size_t)total_clips);
+  int rc = h->ring.upload(bytes, stream, [&](char* dst) {
+    int32_t* p = reinterpret_cast<int32_t*>(dst);
+    for (int k = 0; k < n_shifts; ++k) {
+      p[k] = start ? start[k] : 0; p[n_shifts + k] = len[k]; p[2 * n_shifts + k] = nclips[k]; p[3 * n_shifts + k] = base[k];
+      for (int q = 0; q < nclips[k] && base[k] + q < total_clips; ++q) p[4 * n_shifts + base[k] + q] = k;
+    }
+  }, &dev);
+  if (rc) return rc;
+  const int32_t* p = static_cast<const int32_t*>(dev);
+  tab->start = p; tab->len = p + n_shifts; tab->nclips = p + 2 * n_shifts; tab->clip_base = p + 3 * n_shifts;
+  if (clip_shift) *clip_shift = p + 4 * n_shifts;
+  return CLASFV_OK;
+}
+
+int clasfv_build_shift_clips(clasfv_handle* h, const float* video_dev, int t, int height, int width, int clip_len,
+                             int n_shifts, const int32_t* shift_start_host, const int32_t* shift_len_host,
+                             const int32_t* shift_nclips_host, const int32_t* shift_clip_base_host,
+                             float* clips_dev, void* stream_v) {
+  CLASFV_REQUIRE(h && video_dev && clips_dev && shift_start_host && shift_len_host && shift_nclips_host && shift_clip_base_host,
+                 "clasfv_build_shift_clips: null argument");
+  CLASFV_REQUIRE(n_shifts >= 1 && clip_len >= 1 && t >= 1 && ((int64_t)height * width) % 4 == 0, "clasfv_build_shift_clips: bad extent (H*W must be a multiple of 4)");
+  int total = 0;
+  for (int k = 0; k < n_shifts; ++k) {
+    CLASFV_REQUIRE(shift_start_host[k] >= 0 && shift_len_host[k] >= 1 && shift_start_host[k] + shift_len_host[k] <= t && shift_nclips_host[k] >= 0,
+                   "clasfv_build_shift_clips: shift %d out of range", k);
+    CLASFV_REQUIRE(shift_clip_base_host[k] == total, "clasfv_build_shift_clips: clip bases must be the running sum of clip counts");
+    // without a resample the clips are plain slices and must fit (the reference truncates when it rounds down)
+    CLASFV_REQUIRE(shift_nclips_host[k] * clip_len == shift_len_host[k] || shift_len_host[k] % clip_len != 0,
+                   "clasfv_build_shift_clips: inconsistent clip count for shift %d", k);
+    total += shift_nclips_host[k];
+  }
+  if (total == 0) return CLASFV_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  ShiftTable tab; const int32_t* clip_shift = nullptr;
+  int rc = upload_shift_table(h, n_shifts, shift_start_host, shift_len_host, shift_nclips_host, shift_clip_base_host, total, stream, &tab, &clip_shift);
+  if (rc) return rc;
+  return launch_build_shift_clips(video_dev, t, height, width, clip_len, n_shifts, total, clip_shift, tab, clips_dev, stream);
+}
+
+int clasfv_fuse_shift_votes(clasfv_handle* h, const void* prob_dev, int dtype, int t, int height, int width,
+                            int clip_len, int step, int n_shifts, const int32_t* shift_len_host,
+                            const int32_t* shift_nclips_host, const int32_t* shift_clip_base_host,
+                            uint8_t* mask_dev, int32_t* area_dev, void* stream_v) {
+  CLASFV_REQUIRE(h && prob_dev && mask_dev && shift_len_host && shift_nclips_host && shift_clip_base_host, "clasfv_fuse_shift_votes: null argument");
+  CLASFV_REQUIRE(dtype == CLASFV_F32 || dtype == CLASFV_BF16, "clasfv_fuse_shift_votes: bad dtype");
+  CLASFV_REQUIRE(n_shifts >= 1 && step >= 1 && clip_len >= 1 && t >= 1, "clasfv_fuse_shift_votes: bad extent");
+  CLASFV_REQUIRE(shift_nclips_host[0] >= 1, "clasfv_fuse_shift_votes: shift 0 has no clip (the reference raises IndexError)");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  int total = 0;
+  for (int k = 0; k < n_shifts; ++k) total += shift_nclips_host[k];
+  ShiftTable tab;
+  int rc = upload_shift_table(h, n_shifts, nullptr, shift_len_host, shift_nclips_host, shift_clip_base_host, total, stream, &tab, nullptr);
+  if (rc) return rc;
+  return launch_fuse_shift_votes(prob_dev, dtype, t, height, width, clip_len, step, n_shifts, tab, mask_dev, area_dev, stream);
+}
+
+int clasfv_temporal_resample(const float* in_dev, float* out_dev, int channels, int l_in, int l_out, int64_t hw, void* stream) {
+  CLASFV_REQUIRE(in_dev && out_dev && channels >= 1 && l_in >= 1 && l_out >= 1 && hw >= 1, "clasfv_temporal_resample: bad argument");
+  return launch_temporal_resample(in_dev, out_dev, channels, l_in, l_out, hw, static_cast<cudaStream_t>(stream));
+}
+
+int clasfv_conv3d(clasfv_handle* h, const void* x_dev, int dtype, int n, int t, int height, int width, int cin,
+                  const float* w_host, const float* scale_host, const float* shift_host, int cout,
+                  int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
+                  const void* residual_dev, int relu, int engine, int out_f32, void* out_dev, void* stream_v) {
+  CLASFV_REQUIRE(h && x_dev && w_host && out_dev, "clasfv_conv3d: null argument");
+  CLASFV_REQUIRE(dtype == CLASFV_F32 || dtype == CLASFV_BF16, "clasfv_conv3d: bad dtype");
+  CLASFV_REQUIRE(cin % 16 == 0 && cout % 16 == 0, "clasfv_conv3d: channel counts must be multiples of 16");
+  CLASFV_REQUIRE(engine == 0 || (engine == 1 && dtype == CLASFV_BF16), "clasfv_conv3d: the tcgen05 engine needs bf16");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int taps = kt * kh * kw;
+  // pack on the host, upload to a temporary that is freed after the stream drains (test surface: simplicity over speed)
+  const size_t nw = (size_t)taps * cout * cin;
+  std::vector<float> packed(nw);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int tap = 0; tap < taps; ++tap)
+        packed[((size_t)tap * cout + co) * cin + ci] = w_host[((size_t)co * cin + ci) * taps + tap] * (scale_host ? scale_host[co] : 1.f);
+  void* w_dev = nullptr; float* b_dev = nullptr;
+  if (dtype == CLASFV_F32) {
+    CLASFV_CUDA(cudaMalloc(&w_dev, nw * 4));
+    CLASFV_CUDA(cudaMemcpy(w_dev, packed.data(), nw * 4, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<__nv_bfloat16> pb(nw);
+    for (size_t i = 0; i < nw; ++i) pb[i] = __float2bfloat16_rn(packed[i]);
+    CLASFV_CUDA(cudaMalloc(&w_dev, nw * 2));
+    CLASFV_CUDA(cudaMemcpy(w_dev, pb.data(), nw * 2, cudaMemcpyHostToDevice));
+  }
+  if (shift_host) {
+    CLASFV_CUDA(cudaMalloc(&b_dev, (size_t)cout * 4));
+    CLASFV_CUDA(cudaMemcpy(b_dev, shift_host, (size_t)cout * 4, cudaMemcpyHostToDevice));
+  }
+  PackedConv pc;
+  pc.cin = pc.cin_pad = cin; pc.cout = pc.cout_pad = cout;
+  pc.kt = kt; pc.kh = kh; pc.kw = kw; pc.st = st; pc.sh = sh; pc.sw = sw; pc.pt = pt; pc.ph = ph; pc.pw = pw;
+  pc.w = w_dev; pc.bias = b_dev;
+  ConvArgs a = make_conv(pc, n, t, height, width, x_dev, out_dev, residual_dev, relu, dtype, out_f32);
+  int rc = engine == 1 ? launch_conv_umma(a, h->num_sms, stream) : launch_conv_simt(a, stream);
+  cudaError_t e = cudaStreamSynchronize(stream);
+  cudaFree(w_dev);
+  if (b_dev) cudaFree(b_dev);
+  if (rc) return rc;
+  if (e != cudaSuccess) { set_error("clasfv_conv3d: kernel failed: %s", cudaGetErrorString(e)); return CLASFV_ECUDA; }
+  return CLASFV_OK;
+}
+
+}  // extern "C"

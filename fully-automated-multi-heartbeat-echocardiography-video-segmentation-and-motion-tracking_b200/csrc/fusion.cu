@@ -1,0 +1,288 @@
+// fusion.cu - bandwidth-bound kernels either side of the network: the warp primitive, the
+// warp-and-fuse operator (F2), and the reference-exact shifted-pass fusion (F1).
+//
+// Reference semantics reproduced here (paths relative to the reference checkout):
+//   generate_2dmotion_field          src/transform_utils.py:14-34   base grid linspace(-1,1,S) (an
+//       align_corners=True grid) consumed by grid_sample(align_corners=False, bilinear, border):
+//       zero flow is NOT the identity, x_src = j*W/(W-1) - 1/2.
+//   divide_to_consecutive_clips      src/fuse_utils.py:16-33        temporal resample, align_corners=False
+//   segment_a_video_with_fusion      src/fuse_utils.py:70-98        resample back, argmax, per-frame vote
+#include "internal.h"
+
+namespace clasfv {
+namespace {
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(__ldg(p));
+}
+
+// torch.linspace(-1, 1, steps)[idx] in fp32 (symmetric evaluation, as ATen does)
+__device__ __forceinline__ float linspace_pm1(int idx, int steps) {
+  if (steps <= 1) return -1.f;
+  const float step = 2.f / (float)(steps - 1);
+  return idx < steps / 2 ? -1.f + step * (float)idx : 1.f - step * (float)(steps - idx - 1);
+}
+
+struct Bilinear {
+  int x0, y0;                 // north-west corner
+  float nw, ne, sw, se;       // weights; out-of-range corners carry weight of an in-range clamp below
+  bool x1ok, y1ok;
+};
+
+// grid_sample(align_corners=False, padding_mode="border", mode="bilinear") source location for
+// output pixel (i, j) displaced by the normalised flow (fx, fy).
+__device__ __forceinline__ Bilinear bilinear_setup(int i, int j, float fx, float fy, int h, int w) {
+  const float gx = linspace_pm1(j, w) + fx, gy = linspace_pm1(i, h) + fy;
+  float ix = ((gx + 1.f) * (float)w - 1.f) * 0.5f;
+  float iy = ((gy + 1.f) * (float)h - 1.f) * 0.5f;
+  ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
+  iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  Bilinear b;
+  b.x0 = (int)fx0; b.y0 = (int)fy0;
+  const float x1 = fx0 + 1.f, y1 = fy0 + 1.f;
+  b.nw = (x1 - ix) * (y1 - iy);
+  b.ne = (ix - fx0) * (y1 - iy);
+  b.sw = (x1 - ix) * (iy - fy0);
+  b.se = (ix - fx0) * (iy - fy0);
+  b.x1ok = b.x0 + 1 < w; b.y1ok = b.y0 + 1 < h;
+  return b;
+}
+
+template <typename T>
+__device__ __forceinline__ float bilinear_fetch(const T* __restrict__ plane, const Bilinear& b, int w) {
+  const T* p = plane + (int64_t)b.y0 * w + b.x0;
+  float v = ldf<T>(p) * b.nw;
+  if (b.x1ok) v += ldf<T>(p + 1) * b.ne;
+  if (b.y1ok) v += ldf<T>(p + w) * b.sw;
+  if (b.x1ok && b.y1ok) v += ldf<T>(p + w + 1) * b.se;
+  return v;
+}
+
+__global__ void warp_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ out,
+                            int c, int h, int w) {
+  const int n = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= h * w) return;
+  const int i = pix / w, j = pix % w;
+  const int64_t hw = (int64_t)h * w;
+  const float fx = __ldg(flow + (int64_t)n * 2 * hw + pix), fy = __ldg(flow + ((int64_t)n * 2 + 1) * hw + pix);
+  const Bilinear b = bilinear_setup(i, j, fx, fy, h, w);
+  for (int k = 0; k < c; ++k) out[((int64_t)n * c + k) * hw + pix] = bilinear_fetch<float>(src + ((int64_t)n * c + k) * hw, b, w);
+}
+
+__global__ void motion_field_kernel(const float* __restrict__ flow, float* __restrict__ grid, int h, int w) {
+  const int n = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= h * w) return;
+  const int i = pix / w, j = pix % w;
+  const int64_t hw = (int64_t)h * w;
+  float2 g;
+  g.x = linspace_pm1(j, w) + __ldg(flow + (int64_t)n * 2 * hw + pix);
+  g.y = linspace_pm1(i, h) + __ldg(flow + ((int64_t)n * 2 + 1) * hw + pix);
+  reinterpret_cast<float2*>(grid)[(int64_t)n * hw + pix] = g;
+}
+
+// ------------------------------------------------------------------------------------------- F2
+constexpr int WF_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArgs a) {
+  const int g = blockIdx.y;
+  const int pix = blockIdx.x * WF_THREADS + threadIdx.x;
+  const int hw = a.h * a.w;
+  const bool valid = pix < hw;
+  const int i = valid ? pix / a.w : 0, j = valid ? pix % a.w : 0;
+  const int L = a.clip_len;
+  const T* __restrict__ prob = static_cast<const T*>(a.prob);
+  const T* __restrict__ mot = static_cast<const T*>(a.motion);
+  float* acc = a.acc + (int64_t)g * 2 * hw;
+  float a0 = 0.f, a1 = 0.f;
+  if (a.accumulate && valid) { a0 = acc[pix]; a1 = acc[hw + pix]; }
+  int votes = 0;
+  const int lo = __ldg(a.frame_lo + g), hi = __ldg(a.frame_hi + g);
+  for (int c = lo; c < hi; ++c) {
+    const int t = g - __ldg(a.clip_start + c);
+    const T* pc = prob + (int64_t)c * 2 * L * hw;
+    const T* mc = mot + (int64_t)c * 4 * L * hw;
+    if (t >= 0 && t < L) {                                   // direct vote
+      ++votes;
+      if (valid) { a0 += ldf<T>(pc + (int64_t)t * hw + pix); a1 += ldf<T>(pc + (int64_t)(L + t) * hw + pix); }
+    }
+    int ts = t - 1;                                          // forward hop: frame ts -> ts + 1 == t
+    if (ts >= 0 && ts < L && (a.edge_hops || ts + 1 < L)) {
+      ++votes;
+      if (valid) {
+        const float fx = ldf<T>(mc + (int64_t)ts * hw + pix), fy = ldf<T>(mc + (int64_t)(L + ts) * hw + pix);
+        const Bilinear b = bilinear_setup(i, j, fx, fy, a.h, a.w);
+        a0 += bilinear_fetch<T>(pc + (int64_t)ts * hw, b, a.w);
+        a1 += bilinear_fetch<T>(pc + (int64_t)(L + ts) * hw, b, a.w);
+      }
+    }
+    ts = t + 1;                                              // backward hop: frame ts -> ts - 1 == t
+    if (ts >= 0 && ts < L && (a.edge_hops || ts >= 1)) {
+      ++votes;
+      if (valid) {
+        const float fx = ldf<T>(mc + (int64_t)(2 * L + ts) * hw + pix), fy = ldf<T>(mc + (int64_t)(3 * L + ts) * hw + pix);
+        const Bilinear b = bilinear_setup(i, j, fx, fy, a.h, a.w);
+        a0 += bilinear_fetch<T>(pc + (int64_t)ts * hw, b, a.w);
+        a1 += bilinear_fetch<T>(pc + (int64_t)(L + ts) * hw, b, a.w);
+      }
+    }
+  }
+  const bool lv = valid && (a1 > a0);
+  if (valid) {
+    acc[pix] = a0; acc[hw + pix] = a1;
+    if (a.mask) a.mask[(int64_t)g * hw + pix] = lv ? 1 : 0;
+  }
+  if (a.area) {
+    const int cnt = __syncthreads_count(lv);
+    if (threadIdx.x == 0 && cnt) atomicAdd(a.area + g, cnt);
+  }
+  if (a.cnt && blockIdx.x == 0 && threadIdx.x == 0) a.cnt[g] = (a.accumulate ? a.cnt[g] : 0) + votes;
+}
+
+// ------------------------------------------------------------------------------------------- F1
+struct Lerp { int i0, i1; float l0, l1; };
+// PyTorch linear resample, align_corners=False: src = max(scale*(dst+0.5)-0.5, 0)
+__device__ __forceinline__ Lerp lerp_tap(int dst, int in_size, int out_size) {
+  Lerp r;
+  const float scale = (float)in_size / (float)out_size;
+  const float src = fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.f);
+  r.i0 = min((int)src, in_size - 1);
+  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+  r.l1 = fminf(fmaxf(src - (float)r.i0, 0.f), 1.f);
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+__global__ void build_shift_clips_kernel(const float* __restrict__ video, int t_video, int64_t hw4, int clip_len,
+                                         const int32_t* __restrict__ clip_shift, ShiftTable tab,
+                                         float* __restrict__ clips) {
+  const int clip = blockIdx.z, tt = blockIdx.y;
+  const int64_t p4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p4 >= hw4) return;
+  const int k = __ldg(clip_shift + clip);
+  const int start = __ldg(tab.start + k), len = __ldg(tab.len + k), lr = clip_len * __ldg(tab.nclips + k);
+  const int f = (clip - __ldg(tab.clip_base + k)) * clip_len + tt;
+  Lerp r;
+  if (lr == len) { r.i0 = r.i1 = f; r.l0 = 1.f; r.l1 = 0.f; }
+  else r = lerp_tap(f, len, lr);
+  const float4* v = reinterpret_cast<const float4*>(video);
+  float4* o = reinterpret_cast<float4*>(clips);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float4 x0 = __ldg(v + ((int64_t)c * t_video + start + r.i0) * hw4 + p4);
+    float4 y = x0;
+    if (lr != len) {
+      const float4 x1 = __ldg(v + ((int64_t)c * t_video + start + r.i1) * hw4 + p4);
+      y.x = r.l0 * x0.x + r.l1 * x1.x; y.y = r.l0 * x0.y + r.l1 * x1.y;
+      y.z = r.l0 * x0.z + r.l1 * x1.z; y.w = r.l0 * x0.w + r.l1 * x1.w;
+    }
+    o[(((int64_t)clip * 3 + c) * clip_len + tt) * hw4 + p4] = y;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fuse_shift_votes_kernel(const T* __restrict__ prob, int t_video, int hw, int clip_len,
+                                                               int step, int n_shifts, ShiftTable tab,
+                                                               uint8_t* __restrict__ mask, int32_t* __restrict__ area) {
+  const int i = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = pix < hw;
+  int ones = 0, voters = 0;
+  const int kmax = i == 0 ? 1 : min(i, n_shifts);
+  for (int k = 0; k < kmax; ++k) {
+    const int j = i - k * step;
+    if (j < 0) break;
+    const int len = __ldg(tab.len + k), lr = clip_len * __ldg(tab.nclips + k), cb = __ldg(tab.clip_base + k);
+    if (j >= (lr == len ? lr : len)) continue;   // the reference raises IndexError here; the host rejects such plans
+    ++voters;
+    if (!valid) continue;
+    float p0, p1;
+    if (lr == len) {
+      const T* pc = prob + ((int64_t)(cb + j / clip_len) * 2 * clip_len + j % clip_len) * hw + pix;
+      p0 = ldf<T>(pc); p1 = ldf<T>(pc + (int64_t)clip_len * hw);
+    } else {
+      const Lerp r = lerp_tap(j, lr, len);
+      const T* pa = prob + ((int64_t)(cb + r.i0 / clip_len) * 2 * clip_len + r.i0 % clip_len) * hw + pix;
+      const T* pb = prob + ((int64_t)(cb + r.i1 / clip_len) * 2 * clip_len + r.i1 % clip_len) * hw + pix;
+      p0 = r.l0 * ldf<T>(pa) + r.l1 * ldf<T>(pb);
+      p1 = r.l0 * ldf<T>(pa + (int64_t)clip_len * hw) + r.l1 * ldf<T>(pb + (int64_t)clip_len * hw);
+    }
+    ones += p1 > p0 ? 1 : 0;
+  }
+  const bool lv = valid && (2 * ones > voters);
+  if (valid) mask[(int64_t)i * hw + pix] = lv ? 1 : 0;
+  if (area) {
+    const int cnt = __syncthreads_count(lv);
+    if (threadIdx.x == 0 && cnt) atomicAdd(area + i, cnt);
+  }
+}
+
+__global__ void temporal_resample_kernel(const float* __restrict__ in, float* __restrict__ out, int l_in, int l_out, int64_t hw) {
+  const int d = blockIdx.y, c = blockIdx.z;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= hw) return;
+  const Lerp r = lerp_tap(d, l_in, l_out);
+  const float* base = in + (int64_t)c * l_in * hw;
+  out[((int64_t)c * l_out + d) * hw + p] = r.l0 * __ldg(base + (int64_t)r.i0 * hw + p) + r.l1 * __ldg(base + (int64_t)r.i1 * hw + p);
+}
+
+}  // namespace
+
+int launch_warp(const float* src, const float* flow, float* out, int n, int c, int h, int w, cudaStream_t s) {
+  dim3 grid((unsigned)cdiv((int64_t)h * w, 256), (unsigned)n);
+  warp_kernel<<<grid, 256, 0, s>>>(src, flow, out, c, h, w);
+  CLASFV_CUDA(cudaGetLastError());
+  return CLASFV_OK;
+}
+
+int launch_motion_field(const float* flow, float* grid_out, int n, int h, int w, cudaStream_t s) {
+  dim3 grid((unsigned)cdiv((int64_t)h * w, 256), (unsigned)n);
+  motion_field_kernel<<<grid, 256, 0, s>>>(flow, grid_out, h, w);
+  CLASFV_CUDA(cudaGetLastError());
+  return CLASFV_OK;
+}
+
+int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
+  if (a.area) CLASFV_CUDA(cudaMemsetAsync(a.area, 0, sizeof(int32_t) * a.t_out, s));
+  dim3 grid((unsigned)cdiv((int64_t)a.h * a.w, WF_THREADS), (unsigned)a.t_out);
+  if (a.dtype == CLASFV_F32) warp_fuse_kernel<float><<<grid, WF_THREADS, 0, s>>>(a);
+  else warp_fuse_kernel<__nv_bfloat16><<<grid, WF_THREADS, 0, s>>>(a);
+  CLASFV_CUDA(cudaGetLastError());
+  return CLASFV_OK;
+}
+
+int launch_build_shift_clips(const float* video, int t, int h, int w, int clip_len, int n_shifts, int total_clips,
+                             const int32_t* clip_shift, ShiftTable tab, float* clips, cudaStream_t s) {
+  (void)n_shifts;
+  const int64_t hw4 = (int64_t)h * w / 4;
+  dim3 grid((unsigned)cdiv(hw4, 128), (unsigned)clip_len, (unsigned)total_clips);
+  build_shift_clips_kernel<<<grid, 128, 0, s>>>(video, t, hw4, clip_len, clip_shift, tab, clips);
+  CLASFV_CUDA(cudaGetLastError());
+  return CLASFV_OK;
+}
+
+int launch_fuse_shift_votes(const void* prob, int dtype, int t, int h, int w, int clip_len, int step, int n_shifts,
+                            ShiftTable tab, uint8_t* mask, int32_t* area, cudaStream_t s) {
+  if (area) CLASFV_CUDA(cudaMemsetAsync(area, 0, sizeof(int32_t) * t, s));
+  dim3 grid((unsigned)cdiv((int64_t)h * w, 256), (unsigned)t);
+  if (dtype == CLASFV_F32)
+    fuse_shift_votes_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(prob), t, h * w, clip_len, step, n_shifts, tab, mask, area);
+  else
+    fuse_shift_votes_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(prob), t, h * w, clip_len, step, n_shifts, tab, mask, area);
+  CLASFV_CUDA(cudaGetLastError());
+  return CLASFV_OK;
+}
+
+int launch_temporal_resample(const float* in, float* out, int channels, int l_in, int l_out, int64_t hw, cudaStream_t s) {
+  dim3 grid((unsigned)cdiv(hw, 256), (unsigned)l_out, (unsigned)channels);
+  temporal_resample_kernel<<<grid, 256, 0, s>>>(in, out, l_in, l_out, hw);
+  CLASFV_CUDA(cudaGetLastError());
+  return CLASFV_OK;
+}
+
+}  // namespace clasfv

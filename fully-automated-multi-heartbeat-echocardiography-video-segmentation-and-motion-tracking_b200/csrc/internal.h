@@ -1,0 +1,113 @@
+// internal.h - shared declarations between the translation units of libclasfv_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/clasfv_b200.h"
+
+namespace clasfv {
+
+void set_error(const char* fmt, ...);
+
+#define CLASFV_CUDA(expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ::clasfv::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CLASFV_ECUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+#define CLASFV_REQUIRE(cond, ...)                                                                 \
+  do {                                                                                            \
+    if (!(cond)) { ::clasfv::set_error(__VA_ARGS__); return CLASFV_EINVAL; }                      \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// One convolution on channels-last (N,T,H,W,C) activations.
+struct ConvShape {
+  int n, ti, hi, wi, cin;      // cin, cout: stored (padded) channel counts
+  int to, ho, wo, cout;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+};
+
+struct ConvArgs {
+  ConvShape s;
+  const void* in;         // (N,Ti,Hi,Wi,Cin)  element type = act_dtype
+  const void* weight;     // [tap][Cout][Cin]  element type = act_dtype (fp32 or bf16), BN scale folded
+  const float* bias;      // [Cout] fp32 or nullptr
+  const void* residual;   // (N,To,Ho,Wo,Cout) element type = out type, or nullptr
+  void* out;              // (N,To,Ho,Wo,Cout)
+  int act_dtype;          // CLASFV_F32 | CLASFV_BF16: type of in / weight
+  int out_f32;            // 1: out (and residual) are fp32 regardless of act_dtype
+  int relu;
+};
+
+// CUDA-core implicit GEMM (both storage types).  conv_simt.cu
+int launch_conv_simt(const ConvArgs& a, cudaStream_t stream);
+// tcgen05 / TMEM / TMA implicit GEMM, bf16 only.  conv_umma.cu
+int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream);
+int umma_selftest_supported();
+
+// Stem 1x7x7 stride (1,2,2) pad (0,3,3) convolution from the planar fp32 input.  conv_simt.cu
+struct StemArgs {
+  const float* x;              // planar fp32 input
+  const int64_t* clip_offset;  // device [N] element offsets
+  int64_t channel_stride;
+  int n, t, h, w;              // input dims (output is (N,T,H/2,W/2,48))
+  const float* weight;         // [147][48] fp32 (tap-major: (c*7+kh)*7+kw), BN folded, channels 45..47 zero
+  const float* bias;           // [48]
+  void* out;                   // (N,T,H/2,W/2,out_channels); channels 45.. are written as zero
+  int out_channels;
+  int out_dtype;
+};
+int launch_stem(const StemArgs& a, cudaStream_t stream);
+
+// Decoder head: 4-level trilinear (align_corners=True) gather-sum of the laterally projected feature
+// maps + bias + ReLU + 64x64 + ReLU + 6x64 heads + softmax / tanh.  decoder.cu
+struct HeadArgs {
+  const float* g[4];           // (N,Tl,Hl,Wl,64) fp32, levels 1/2 (T/1), 1/4 (T/2), 1/8 (T/4), 1/16 (T/8)
+  int tl[4], hl[4], wl[4];
+  int n, t, h, w;
+  const float* b1;             // [64]   folded comb_1 bias + BN1
+  const float* w2;             // [64][64] folded comb_2 * BN2 scale, row = output channel
+  const float* b2;             // [64]
+  const float* wh;             // [6][64]  rows 0-1 segmentation head, 2-5 motion head
+  const float* bh;             // [6]
+  void* seg; void* motion;     // (N,2,T,H,W), (N,4,T,H,W)
+  int out_dtype;               // CLASFV_F32 | CLASFV_BF16
+  int out_kind;                // CLASFV_OUT_LOGITS | CLASFV_OUT_PROB
+};
+int launch_head(const HeadArgs& a, cudaStream_t stream);
+
+// fusion.cu
+int launch_warp(const float* src, const float* flow, float* out, int n, int c, int h, int w, cudaStream_t s);
+int launch_motion_field(const float* flow, float* grid, int n, int h, int w, cudaStream_t s);
+struct WarpFuseArgs {
+  const void* prob; const void* motion; int dtype;
+  const int32_t* clip_start;   // device [n_clips]
+  const int32_t* frame_lo;     // device [t_out]   first candidate clip for the frame
+  const int32_t* frame_hi;     // device [t_out]   one past the last candidate clip
+  int n_clips, clip_len, t_out, h, w, edge_hops, accumulate;
+  float* acc; int32_t* cnt; uint8_t* mask; int32_t* area;
+};
+int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s);
+struct ShiftTable {            // device arrays [n_shifts]
+  const int32_t* start; const int32_t* len; const int32_t* nclips; const int32_t* clip_base;
+};
+int launch_build_shift_clips(const float* video, int t, int h, int w, int clip_len, int n_shifts, int total_clips,
+                             const int32_t* clip_shift /*device [total_clips]*/, ShiftTable tab, float* clips,
+                             cudaStream_t s);
+int launch_fuse_shift_votes(const void* prob, int dtype, int t, int h, int w, int clip_len, int step, int n_shifts,
+                            ShiftTable tab, uint8_t* mask, int32_t* area, cudaStream_t s);
+int launch_temporal_resample(const float* in, float* out, int channels, int l_in, int l_out, int64_t hw, cudaStream_t s);
+
+}  // namespace clasfv

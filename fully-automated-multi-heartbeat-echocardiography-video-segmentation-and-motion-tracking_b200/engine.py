@@ -1,0 +1,228 @@
+"""Host-side wrapper of one ``clasfv_handle`` (packed network + workspace on one device).
+
+This is plumbing shared by the reference-shaped drop-ins in ``src/``: it moves state_dict tensors
+across the C ABI, and exposes forward / fusion calls on torch CUDA tensors (torch supplies device
+memory and streams only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, OUT_LOGITS, OUT_PROB, ClasfvError, check
+
+
+def precision_code(precision):
+    if precision in (F32, "fp32", "f32", "float32", torch.float32):
+        return F32
+    if precision in (BF16, "bf16", "bfloat16", torch.bfloat16):
+        return BF16
+    raise ClasfvError(f"unknown precision {precision!r}: use 'fp32' or 'bf16'")
+
+
+class Engine:
+    """One packed CLAS-FV network on one CUDA device."""
+
+    def __init__(self, device):
+        self.lib = _lib.lib()
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise ClasfvError(f"clasfv_b200 runs on CUDA devices only (sm_100a); got {dev}. There is no CPU path.")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        h = C.c_void_p()
+        check(self.lib.clasfv_create(self.device.index, C.byref(h)), "clasfv_create")
+        self._h = h
+        self.precision = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.clasfv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict, precision="fp32"):
+        for key, t in state_dict.items():
+            if key.startswith("module."):
+                key = key[7:]
+            if not torch.is_floating_point(t):
+                continue                      # num_batches_tracked
+            a = np.ascontiguousarray(t.detach().to("cpu", torch.float32).numpy())
+            shape = _lib.i64_array(a.shape) if a.ndim else None
+            check(self.lib.clasfv_set_tensor(self._h, key.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim),
+                  f"clasfv_set_tensor({key})")
+        self.finalize(precision)
+
+    def finalize(self, precision):
+        code = precision_code(precision)
+        check(self.lib.clasfv_finalize(self._h, code), "clasfv_finalize")
+        self.precision = code
+
+    # ------------------------------------------------------------------ network
+    def forward(self, x, out_kind=OUT_LOGITS, out_dtype=torch.float32, clip_starts=None, clip_len=None):
+        """x: (N,3,T,H,W) fp32 CUDA tensor, or with ``clip_starts`` a resident video (3,Tv,H,W) whose
+        windows [s, s+clip_len) are the clips (no copy).  Returns (seg, motion)."""
+        _lib.require_cuda(x, "x")
+        if x.dtype != torch.float32:
+            raise ClasfvError("network input must be float32")
+        if clip_starts is None:
+            if x.dim() != 5 or x.shape[1] != 3:
+                raise ClasfvError(f"expected input of shape (N,3,T,H,W), got {tuple(x.shape)}")
+            n, _, t, h, w = x.shape
+            offs, ch_stride = None, 0
+        else:
+            if x.dim() != 4 or x.shape[0] != 3:
+                raise ClasfvError(f"expected a video of shape (3,T,H,W), got {tuple(x.shape)}")
+            _, tv, h, w = x.shape
+            t = int(clip_len)
+            n = len(clip_starts)
+            if n and (min(clip_starts) < 0 or max(clip_starts) + t > tv):
+                raise ClasfvError("clip window outside the video")
+            offs = _lib.i64_array([int(s) * h * w for s in clip_starts])
+            ch_stride = tv * h * w
+        seg = torch.empty((n, 2, t, h, w), dtype=out_dtype, device=x.device)
+        mot = torch.empty((n, 4, t, h, w), dtype=out_dtype, device=x.device)
+        if n == 0:
+            return seg, mot
+        check(self.lib.clasfv_forward(self._h, x.data_ptr(), offs, ch_stride, n, t, h, w, out_kind,
+                                      _lib.torch_dtype_code(out_dtype), seg.data_ptr(), mot.data_ptr(),
+                                      _lib.current_stream_ptr(x.device)), "clasfv_forward")
+        return seg, mot
+
+    def forward_into(self, x, seg, mot, out_kind, clip_starts=None, clip_len=None):
+        """As :meth:`forward`, writing into caller-provided slices of larger (N,2,T,H,W)/(N,4,T,H,W) buffers."""
+        if clip_starts is None:
+            n, _, t, h, w = x.shape
+            offs, ch_stride = None, 0
+        else:
+            _, tv, h, w = x.shape
+            t, n = int(clip_len), len(clip_starts)
+            offs = _lib.i64_array([int(s) * h * w for s in clip_starts])
+            ch_stride = tv * h * w
+        assert seg.is_contiguous() and mot.is_contiguous() and seg.shape[0] == n and mot.shape[0] == n
+        check(self.lib.clasfv_forward(self._h, x.data_ptr(), offs, ch_stride, n, t, h, w, out_kind,
+                                      _lib.torch_dtype_code(seg.dtype), seg.data_ptr(), mot.data_ptr(),
+                                      _lib.current_stream_ptr(x.device)), "clasfv_forward")
+
+    def workspace_bytes(self):
+        return int(self.lib.clasfv_workspace_bytes(self._h))
+
+    # ------------------------------------------------------------------ fusion
+    def warp_fuse(self, prob, motion, clip_starts, num_frames, edge_hops=False, acc=None, accumulate=False,
+                  want_mask=True, want_area=True):
+        """F2 (oracle/fuse_ref.py:warp_fuse). Returns dict(acc, cnt, mask, area)."""
+        _lib.require_cuda(prob, "prob"); _lib.require_cuda(motion, "motion")
+        n, c, clip_len, h, w = prob.shape
+        if c != 2 or tuple(motion.shape) != (n, 4, clip_len, h, w) or motion.dtype != prob.dtype:
+            raise ClasfvError("warp_fuse: prob must be (n,2,L,H,W) and motion (n,4,L,H,W) of the same dtype")
+        if len(clip_starts) != n:
+            raise ClasfvError("warp_fuse: one start per clip")
+        dev = prob.device
+        if acc is None:
+            acc = torch.empty((num_frames, 2, h, w), dtype=torch.float32, device=dev)
+            accumulate = False
+        cnt = torch.zeros((num_frames,), dtype=torch.int32, device=dev) if not accumulate else None
+        cnt = cnt if cnt is not None else torch.zeros((num_frames,), dtype=torch.int32, device=dev)
+        mask = torch.empty((num_frames, h, w), dtype=torch.uint8, device=dev) if want_mask else None
+        area = torch.empty((num_frames,), dtype=torch.int32, device=dev) if want_area else None
+        check(self.lib.clasfv_warp_fuse(self._h, prob.data_ptr(), motion.data_ptr(), _lib.torch_dtype_code(prob.dtype),
+                                        _lib.i32_array(clip_starts), n, clip_len, num_frames, h, w,
+                                        1 if edge_hops else 0, 1 if accumulate else 0, acc.data_ptr(), cnt.data_ptr(),
+                                        mask.data_ptr() if mask is not None else None,
+                                        area.data_ptr() if area is not None else None,
+                                        _lib.current_stream_ptr(dev)), "clasfv_warp_fuse")
+        return {"acc": acc, "cnt": cnt, "mask": mask, "area": area}
+
+    def build_shift_clips(self, video, plan, clip_len=32):
+        """video (3,T,H,W) fp32 CUDA; plan = list of (start, length, nclips). Returns (total,3,clip_len,H,W)."""
+        _lib.require_cuda(video, "video")
+        _, t, h, w = video.shape
+        starts = [p[0] for p in plan]; lens = [p[1] for p in plan]; ncl = [p[2] for p in plan]
+        bases = list(np.cumsum([0] + ncl[:-1]))
+        total = int(sum(ncl))
+        clips = torch.empty((total, 3, clip_len, h, w), dtype=torch.float32, device=video.device)
+        check(self.lib.clasfv_build_shift_clips(self._h, video.data_ptr(), t, h, w, clip_len, len(plan),
+                                                _lib.i32_array(starts), _lib.i32_array(lens), _lib.i32_array(ncl),
+                                                _lib.i32_array(bases), clips.data_ptr(),
+                                                _lib.current_stream_ptr(video.device)), "clasfv_build_shift_clips")
+        return clips
+
+    def fuse_shift_votes(self, prob, plan, num_frames, step=1, want_area=True):
+        """prob (total,2,L,H,W); plan as in build_shift_clips. Returns (mask (T,H,W) uint8, area (T,) int32)."""
+        _lib.require_cuda(prob, "prob")
+        total, _, clip_len, h, w = prob.shape
+        lens = [p[1] for p in plan]; ncl = [p[2] for p in plan]
+        bases = list(np.cumsum([0] + ncl[:-1]))
+        mask = torch.empty((num_frames, h, w), dtype=torch.uint8, device=prob.device)
+        area = torch.empty((num_frames,), dtype=torch.int32, device=prob.device) if want_area else None
+        check(self.lib.clasfv_fuse_shift_votes(self._h, prob.data_ptr(), _lib.torch_dtype_code(prob.dtype), num_frames, h, w,
+                                               clip_len, step, len(plan), _lib.i32_array(lens), _lib.i32_array(ncl),
+                                               _lib.i32_array(bases), mask.data_ptr(),
+                                               area.data_ptr() if area is not None else None,
+                                               _lib.current_stream_ptr(prob.device)), "clasfv_fuse_shift_votes")
+        return mask, area
+
+    # ------------------------------------------------------------------ single layer (tests)
+    def conv3d(self, x, weight, scale=None, shift=None, stride=(1, 1, 1), padding=(0, 0, 0), residual=None, relu=False,
+               engine="umma", out_f32=False):
+        """x channels-last (N,T,H,W,Cin) CUDA (fp32|bf16); weight (Cout,Cin,kt,kh,kw) fp32 host tensor."""
+        _lib.require_cuda(x, "x")
+        n, t, h, w, cin = x.shape
+        cout, _, kt, kh, kw = weight.shape
+        to = (t + 2 * padding[0] - kt) // stride[0] + 1
+        ho = (h + 2 * padding[1] - kh) // stride[1] + 1
+        wo = (w + 2 * padding[2] - kw) // stride[2] + 1
+        out_dtype = torch.float32 if (out_f32 or x.dtype == torch.float32) else torch.bfloat16
+        out = torch.empty((n, to, ho, wo, cout), dtype=out_dtype, device=x.device)
+        wa = np.ascontiguousarray(weight.detach().cpu().float().numpy())
+        sa = np.ascontiguousarray(scale.detach().cpu().float().numpy()) if scale is not None else None
+        ba = np.ascontiguousarray(shift.detach().cpu().float().numpy()) if shift is not None else None
+        check(self.lib.clasfv_conv3d(self._h, x.data_ptr(), _lib.torch_dtype_code(x.dtype), n, t, h, w, cin,
+                                     wa.ctypes.data_as(C.c_void_p), sa.ctypes.data_as(C.c_void_p) if sa is not None else None,
+                                     ba.ctypes.data_as(C.c_void_p) if ba is not None else None, cout, kt, kh, kw,
+                                     stride[0], stride[1], stride[2], padding[0], padding[1], padding[2],
+                                     residual.data_ptr() if residual is not None else None, 1 if relu else 0,
+                                     1 if engine == "umma" else 0, 1 if out_f32 else 0, out.data_ptr(),
+                                     _lib.current_stream_ptr(x.device)), "clasfv_conv3d")
+        return out
+
+
+def warp(src, flow):
+    """W1 + its grid_sample call site on fp32 CUDA tensors: src (N,C,H,W), flow (N,2,H,W)."""
+    _lib.require_cuda(src, "src"); _lib.require_cuda(flow, "flow")
+    if src.dtype != torch.float32 or flow.dtype != torch.float32:
+        raise ClasfvError("warp: float32 tensors only")
+    n, c, h, w = src.shape
+    if tuple(flow.shape) != (n, 2, h, w):
+        raise ClasfvError("warp: flow must be (N,2,H,W)")
+    out = torch.empty_like(src)
+    check(_lib.lib().clasfv_warp(src.data_ptr(), flow.data_ptr(), out.data_ptr(), n, c, h, w,
+                                 _lib.current_stream_ptr(src.device)), "clasfv_warp")
+    return out
+
+
+def motion_field(offset, height, width):
+    _lib.require_cuda(offset, "offset")
+    n = offset.shape[0]
+    grid = torch.empty((n, height, width, 2), dtype=torch.float32, device=offset.device)
+    check(_lib.lib().clasfv_motion_field(offset.data_ptr(), grid.data_ptr(), n, height, width,
+                                         _lib.current_stream_ptr(offset.device)), "clasfv_motion_field")
+    return grid
+
+
+def temporal_resample(x, out_len):
+    """(C,L,H,W) fp32 CUDA -> (C,out_len,H,W), linear, align_corners=False."""
+    _lib.require_cuda(x, "x")
+    c, l, h, w = x.shape
+    out = torch.empty((c, out_len, h, w), dtype=torch.float32, device=x.device)
+    check(_lib.lib().clasfv_temporal_resample(x.data_ptr(), out.data_ptr(), c, l, out_len, h * w,
+                                              _lib.current_stream_ptr(x.device)), "clasfv_temporal_resample")
+    return out

@@ -1,0 +1,236 @@
+"""Drop-in for the reference's ``src/fuse_utils.py`` on libclasfv_b200.
+
+Same three entry points and argument meanings:
+
+* ``divide_to_consecutive_clips(video, clip_length=32, interpolate_last=False)``            (reference :16-33)
+* ``segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num_clips=10,
+                               fuse_method="simple", class_list=[0, 1])``                    (reference :36-102)
+* ``compute_ef_using_putative_clips(fused_segmentations, test_pat_index, return_edes=False)``  (reference :105-147)
+
+What changed underneath: the video is uploaded once, every shifted pass is resampled and cut into
+clips on the device, all clips of all passes go through the network in batches (softmax fused into
+the head kernel), and resample-back + argmax + per-frame voting are one kernel; only the final
+(T,H,W) mask comes back.  H and W are taken from the input (the reference hard-codes 112).
+
+``fuse_method``:
+  "simple" / "itkvoting" / "majority"  reference-exact shifted-pass fusion with per-pixel majority voting
+                (LabelFusion's SIMPLE is unpinned - package not vendored; for binary labels it reduces to
+                 majority voting up to its iterative re-weighting; ties go to background)
+  "warp"        the north-star warp-and-fuse operator: every ``step``-strided 32-frame window of the video,
+                soft votes, each frame also voting on its neighbours along the predicted forward / backward
+                motion fields (specified by oracle/fuse_ref.py:warp_fuse); ``num_clips`` is ignored
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import engine as _engine
+from .._lib import OUT_PROB, ClasfvError
+from .echonet_dataset import EDESpairs
+
+CLIP = 32
+MAJORITY_METHODS = ("simple", "itkvoting", "majority")
+
+_default_engines = {}
+
+
+def _default_engine():
+    if not torch.cuda.is_available():
+        raise ClasfvError("clasfv_b200.fuse_utils needs a CUDA device (sm_100a); there is no CPU path")
+    idx = torch.cuda.current_device()
+    if idx not in _default_engines:
+        _default_engines[idx] = _engine.Engine(torch.device("cuda", idx))
+    return _default_engines[idx]
+
+
+def _unwrap(model):
+    from .model.R2plus1D_18_MotionNet import R2plus1D_18_MotionNet
+    net = model.module if isinstance(model, torch.nn.DataParallel) else model
+    if not isinstance(net, R2plus1D_18_MotionNet):
+        raise TypeError("segment_a_video_with_fusion needs a clasfv_b200 R2plus1D_18_MotionNet "
+                        "(optionally wrapped in nn.DataParallel); got " + type(net).__name__)
+    if net.training:
+        raise ClasfvError("call model.eval() first (inference only)")
+    return net
+
+
+def _num_clips(length, clip_length=CLIP):
+    return int(np.round(length / clip_length))      # half to even, as the reference (:21, :29)
+
+
+def _shift_plan_entry(start, length, clip_length, interpolate_last):
+    """(start, effective length, nclips) of one shifted pass, or raises what the reference raises."""
+    n = _num_clips(length, clip_length)
+    if length % clip_length != 0 and not interpolate_last:
+        if n * clip_length > length:
+            raise ValueError("all the input array dimensions except for the concatenation axis must match exactly "
+                             "(last clip is short; the reference fails in np.concatenate, fuse_utils.py:32)")
+        return (start, n * clip_length, n)          # truncated, no resample
+    if length % clip_length != 0 and n == 0:
+        raise RuntimeError("Input and output sizes should be greater than 0 (video shorter than half a clip)")
+    return (start, length, n)
+
+
+def _to_device_video(video, device):
+    if isinstance(video, torch.Tensor):
+        v = video
+    else:
+        v = torch.from_numpy(np.ascontiguousarray(video))
+    if v.dim() != 4 or v.shape[0] != 3:
+        raise ClasfvError(f"expected a video of shape (3,T,H,W), got {tuple(v.shape)}")
+    return v.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def divide_to_consecutive_clips(video, clip_length=32, interpolate_last=False):
+    """(3, L, H, W) array -> (n, 3, clip_length, H, W) float64 array, n = round(L / clip_length)."""
+    eng = _default_engine()
+    length = video.shape[1]
+    entry = _shift_plan_entry(0, length, clip_length, interpolate_last)
+    if entry[2] == 0:
+        return np.empty((0, 3, clip_length) + tuple(video.shape[2:]), dtype=np.float64)
+    v = _to_device_video(video, eng.device)
+    clips = eng.build_shift_clips(v, [entry], clip_length)
+    return clips.cpu().numpy().astype(np.float64)
+
+
+def plan_shifts(num_frames, step=1, num_clips=10):
+    """The shift distances the reference uses (:38-45), including its clamping and its message."""
+    if num_frames < CLIP + num_clips * step:
+        num_clips = (num_frames - CLIP) // step
+    if num_clips < 0:
+        print("Video is too short")
+        num_clips = 1
+    return list(range(0, num_clips * step, step))
+
+
+def segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num_clips=10,
+                                fuse_method="simple", class_list=[0, 1], batch_clips=16, edge_hops=False,
+                                return_details=False):
+    net = _unwrap(model)
+    eng = net.engine()
+    if list(class_list) != [0, 1]:
+        raise ClasfvError("class_list must be [0, 1] (background, LV)")
+    method = fuse_method.lower()
+    v = _to_device_video(video, eng.device)
+    num_frames, h, w = int(v.shape[1]), int(v.shape[2]), int(v.shape[3])
+    out_dtype = torch.float32 if eng.precision == 0 else torch.bfloat16
+
+    if method == "warp":
+        if num_frames < CLIP:
+            raise ClasfvError("warp fusion needs at least one full 32-frame clip")
+        starts = list(range(0, num_frames - CLIP + 1, step))
+        if starts[-1] != num_frames - CLIP:
+            starts.append(num_frames - CLIP)        # the tail is always covered
+        n = len(starts)
+        prob = torch.empty((n, 2, CLIP, h, w), dtype=out_dtype, device=v.device)
+        mot = torch.empty((n, 4, CLIP, h, w), dtype=out_dtype, device=v.device)
+        for b0 in range(0, n, batch_clips):
+            b1 = min(n, b0 + batch_clips)
+            eng.forward_into(v, prob[b0:b1], mot[b0:b1], OUT_PROB, clip_starts=starts[b0:b1], clip_len=CLIP)
+        res = eng.warp_fuse(prob, mot, starts, num_frames, edge_hops=edge_hops)
+        fused = res["mask"].cpu().numpy().astype(np.int64)
+        if return_details:
+            return fused, {"area": res["area"].cpu().numpy(), "cnt": res["cnt"].cpu().numpy(), "acc": res["acc"],
+                           "clips": n, "prob": prob, "motion": mot, "starts": starts}
+        return fused
+
+    if method == "staple":
+        raise NotImplementedError("STAPLE label fusion (LabelFusion/SimpleITK) is not part of this path")
+    if method not in MAJORITY_METHODS:
+        raise ValueError(f"unknown fuse_method {fuse_method!r}")
+
+    shifts = plan_shifts(num_frames, step, num_clips)
+    if not shifts:
+        raise IndexError("list index out of range")     # reference: all_interpolated_segmentations[0] (:82)
+    plan = [_shift_plan_entry(s, num_frames - s, CLIP, interpolate_last) for s in shifts]
+    if plan[0][2] == 0:
+        raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+    for k, (_s, eff_len, _n) in enumerate(plan):        # frames a shift must provide (reference :87-91)
+        last_needed = (num_frames - 1) - k * step
+        if k < min(num_frames - 1, len(plan)) or k == 0:
+            if last_needed >= eff_len and last_needed >= 0:
+                raise IndexError(f"index {last_needed} is out of bounds for axis 0 with size {eff_len}")
+    clips = eng.build_shift_clips(v, plan, CLIP)
+    total = clips.shape[0]
+    prob = torch.empty((total, 2, CLIP, h, w), dtype=out_dtype, device=v.device)
+    mot = torch.empty((min(batch_clips, total), 4, CLIP, h, w), dtype=out_dtype, device=v.device)
+    for b0 in range(0, total, batch_clips):
+        b1 = min(total, b0 + batch_clips)
+        eng.forward_into(clips[b0:b1], prob[b0:b1], mot[:b1 - b0], OUT_PROB)
+    mask, area = eng.fuse_shift_votes(prob, plan, num_frames, step)
+    fused = mask.cpu().numpy().astype(np.int64)
+    keep = [0] + [i for i in range(1, num_frames) if step - 1 < i]   # reference skips frames 1..step-1 (:85)
+    if len(keep) != num_frames:
+        fused = fused[keep]
+    if return_details:
+        return fused, {"area": area.cpu().numpy()[keep], "clips": total, "plan": plan, "prob": prob}
+    return fused
+
+
+# ------------------------------------------------------------------------------------------- EF (host)
+def _find_boundaries_thick(binary):
+    """skimage.segmentation.find_boundaries(label_img, mode='thick') for a 2-D label image:
+    (grey dilation != grey erosion) with the 4-connected cross."""
+    from scipy import ndimage as ndi
+    img = binary.astype(np.uint8)
+    fp = ndi.generate_binary_structure(2, 1)
+    return ndi.grey_dilation(img, footprint=fp, mode="nearest") != ndi.grey_erosion(img, footprint=fp, mode="nearest")
+
+
+def get2dPucks(abin, apix, npucks=10):
+    """Reference ``src/utils/echo_utils.py:259-334``: long-axis extent (PCA) and ``npucks`` disk radii."""
+    if not np.any(abin):
+        return 1.0, np.zeros((npucks,))
+    x, y = np.where(abin > 0)
+    X = np.stack([x, y]).astype(np.float64) * np.array(apix)[:, None]
+    try:
+        val, vec = np.linalg.eig(np.cov(X, rowvar=True))
+    except Exception:
+        return 0.0, np.zeros((npucks,))
+    order = np.argsort(val)[-1::-1]
+    vec = vec[:, order]
+    if vec[0, 0] < 0:
+        vec[:, 0] = -1.0 * vec[:, 0]
+    if vec[1, 1] < 0:
+        vec[:, 1] = -1.0 * vec[:, 1]
+    mu = np.expand_dims(np.mean(X, axis=1), axis=1)
+    Xb = np.stack(np.where(_find_boundaries_thick(abin))).astype(np.float64) * np.array(apix)[:, None]
+    proj = np.dot((Xb - mu).T, vec)
+    l_min, l_max = np.min(proj, axis=0), np.max(proj, axis=0)
+    length = l_max - l_min
+    part = np.linspace(l_min[0], l_max[0], npucks + 1)
+    radii = []
+    for i in range(len(part) - 1):
+        which = np.logical_and(proj[:, 0] >= part[i], proj[:, 0] < part[i + 1])
+        radii.append(np.median(np.abs(proj[:, 1][which])) if np.any(which) else np.nan)
+    return length[0], np.array(radii)
+
+
+def compute_ef_using_putative_clips(fused_segmentations, test_pat_index, return_edes=False):
+    from scipy.signal import find_peaks
+    size = np.sum(fused_segmentations, axis=(1, 2)).ravel()
+    _05cut, _85cut, _95cut = np.percentile(size, [5, 85, 95])
+    trim_range = _95cut - _05cut
+    systole = find_peaks(-size, distance=20, prominence=(0.50 * trim_range))[0]
+    diastole = find_peaks(size, distance=20, prominence=(0.50 * trim_range))[0]
+    diastole = [x for x in diastole if size[x] >= _85cut]
+    if np.mean(size[:3]) >= _85cut:
+        diastole = [0] + diastole
+    diastole = np.array(diastole)
+    clip_pairs = EDESpairs(diastole, systole)
+    frames = fused_segmentations.reshape((-1,) + tuple(fused_segmentations.shape[-2:]))
+    predicted_efs = []
+    for ed, es in clip_pairs:
+        length_ed, radius_ed = get2dPucks((frames[ed] == 1).astype('int'), (1.0, 1.0))
+        length_es, radius_es = get2dPucks((frames[es] == 1).astype('int'), (1.0, 1.0))
+        edv = np.sum(((np.pi * radius_ed * radius_ed) * length_ed / len(radius_ed)))
+        esv = np.sum(((np.pi * radius_es * radius_es) * length_es / len(radius_es)))
+        ef_predicted = (edv - esv) / edv * 100
+        if ef_predicted < 0:
+            print("Negative EF at patient: " + str(test_pat_index))
+            continue
+        predicted_efs.append(ef_predicted)
+    if return_edes:
+        return predicted_efs, clip_pairs
+    return predicted_efs
