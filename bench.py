@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py - frames/sec segmented + tracked (fusion on) for the CLAS-FV full-video inference path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one whole pass of the hot path over one synthetic video of BASELINE.json configs[1]
+(112x112, 200 frames, bf16): every stride-1 32-frame window (169 clips) through the R(2+1)D-18
+encoder + decoder heads, then warp-and-fuse into one (200,112,112) mask.  With N > 1 every rank
+processes its own video (videos shard across GPUs with no collective: weak scaling).
+
+  value  fused frames/s with the video already resident in HBM (CUDA events, max over ranks)
+  e2e    the same through the public drop-in fuse_utils.segment_a_video_with_fusion(video, model,
+         fuse_method="warp"): pinned host video -> device, host mask back, every step
+  roofline      trunk convolutions (tcgen05 implicit GEMM): algorithmic FLOP/s vs measured bf16 peak
+  roofline_warp_fuse  the fusion kernel: algorithmic bytes/s vs measured HBM copy bandwidth
+  cpu_baseline  the oracle (PyTorch CPU restatement of the reference path) on a bounded sample
+
+--impl reference times that CPU path alone (the reference is PyTorch; /root/reference is not on the
+GPU box, so the oracle's line-by-line restatement of it is what runs).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_VIDEO, H, W, CLIP = 200, 112, 112, 32
+N_CLIPS = T_VIDEO - CLIP + 1                       # 169 stride-1 windows
+# trunk MACs per 32x112x112 clip executed by the tensor-core kernel
+# (encoder 81.038 GMAC minus the 1x7x7 stem conv 0.664 GMAC, which runs on CUDA cores)
+TRUNK_GFLOP_PER_CLIP = 2 * (81.038 - 0.664)
+ENCODER_GFLOP_PER_CLIP = 2 * 81.038
+KERNELS_PER_FORWARD = 43                           # stem + 41 convolutions + head
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "bf16_tflops_burst": float(p["bf16_tflops"]), "source": "MEASURED_PEAKS.json"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nme in enumerate(names):
+                if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
+                    reasons.add(nme)
+        smax = next((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_sample(sample_clips, threads=None):
+    """Oracle = PyTorch-CPU restatement of the reference path, on `sample_clips` stride-1 windows."""
+    import torch
+    from clasfv_b200 import synthetic
+    from oracle import fuse_ref, model_ref
+    if threads:
+        torch.set_num_threads(threads)
+    sd = synthetic.random_state_dict(0)
+    video = synthetic.synthetic_echo_video(CLIP + sample_clips - 1, H, W, seed=0)
+    starts = list(range(sample_clips))
+    t0 = time.perf_counter()
+    probs, mots = [], []
+    for s in starts:
+        seg, mot = model_ref.forward(sd, torch.from_numpy(video[:, s:s + CLIP]).unsqueeze(0))
+        probs.append(torch.softmax(seg, 1)); mots.append(mot)
+    t_model = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    fuse_ref.warp_fuse(torch.cat(probs), torch.cat(mots), starts, CLIP + sample_clips - 1, accumulate=torch.float32)
+    t_fuse = time.perf_counter() - t0
+    # the whole workload = 169 clips: model cost scales with clips, fusion with clip-frames
+    sec_per_video = (t_model + t_fuse) / sample_clips * N_CLIPS
+    return {"frames_per_s": T_VIDEO / sec_per_video, "sec_per_clip_model": t_model / sample_clips, "sec_per_clip_fuse": t_fuse / sample_clips,
+            "threads": torch.get_num_threads()}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return 0
+    import torch
+    sample = 2
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_reference_sample(1)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_reference_sample(sample))
+    wall = time.perf_counter() - t0
+    fps = sum(v["frames_per_s"] for v in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "frames/sec segmented+tracked (fusion on)", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": vals[0]["threads"], "kind": "port",
+                         "sample": f"{sample} of {N_CLIPS} stride-1 clips per step (reference network on PyTorch CPU + oracle warp-fuse), "
+                                   f"scaled to the 169-clip video; {wall:.1f}s of CPU work"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config():
+    return {"workload": "configs[1]: full-video fusion, every stride-1 32-frame clip of one 112x112 200-frame video "
+                        "(169 clips -> 200 fused frames), warp-and-fuse on, bf16 tensor-core mode",
+            "frames": T_VIDEO, "height": H, "width": W, "clips_per_video": N_CLIPS, "clip_len": CLIP, "fusion": "warp",
+            "weights": "random-init R2plus1D_18_MotionNet (seed 0), 31,575,731 parameters",
+            "l2": "no explicit flush: per-step activation traffic (~5 GB) is far larger than the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--batch-clips", type=int, default=int(os.environ.get("CLASFV_BATCH_CLIPS", "16")))
+    ap.add_argument("--precision", default="bf16", choices=("bf16", "fp32"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    import clasfv_b200  # noqa: F401
+    from clasfv_b200 import synthetic
+    from clasfv_b200._lib import OUT_PROB
+    from clasfv_b200.src import fuse_utils
+    from clasfv_b200.src.model.R2plus1D_18_MotionNet import R2plus1D_18_MotionNet
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device - clasfv_b200 has no CPU path (use --impl reference for the CPU arm)")
+    if args.warmup < 3:
+        print("bench.py: note - fewer than 3 warm-up steps requested", file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    net = R2plus1D_18_MotionNet(pretrained=False, precision=args.precision)
+    net.load_state_dict(synthetic.random_state_dict(0))
+    net = net.to(dev).eval()
+    eng = net.engine()
+    out_dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32
+
+    video_host = torch.from_numpy(synthetic.synthetic_echo_video(T_VIDEO, H, W, seed=rank)).pin_memory()
+    video = video_host.to(dev)
+    starts = list(range(N_CLIPS))
+    prob = torch.empty((N_CLIPS, 2, CLIP, H, W), dtype=out_dtype, device=dev)
+    mot = torch.empty((N_CLIPS, 4, CLIP, H, W), dtype=out_dtype, device=dev)
+    bc = args.batch_clips
+
+    def step_resident():
+        for b0 in range(0, N_CLIPS, bc):
+            b1 = min(N_CLIPS, b0 + bc)
+            eng.forward_into(video, prob[b0:b1], mot[b0:b1], OUT_PROB, clip_starts=starts[b0:b1], clip_len=CLIP)
+        return eng.warp_fuse(prob, mot, starts, T_VIDEO)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.profile_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fuse_events = []
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        for b0 in range(0, N_CLIPS, bc):
+            b1 = min(N_CLIPS, b0 + bc)
+            eng.forward_into(video, prob[b0:b1], mot[b0:b1], OUT_PROB, clip_starts=starts[b0:b1], clip_len=CLIP)
+        fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fa.record()
+        res = eng.warp_fuse(prob, mot, starts, T_VIDEO)
+        fb.record()
+        fuse_events.append((fa, fb))
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    stage_ms, calls = eng.profile_end()
+    fuse_ms = sum(a.elapsed_time(b) for a, b in fuse_events) / len(fuse_events)
+
+    # ---- e2e through the public API (pinned host video in, host mask out, every step)
+    for _ in range(2):
+        fuse_utils.segment_a_video_with_fusion(video_host, net, fuse_method="warp", batch_clips=bc)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mask = fuse_utils.segment_a_video_with_fusion(video_host, net, fuse_method="warp", batch_clips=bc)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert mask.shape == (T_VIDEO, H, W)
+
+    times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        ms_per_step = ms_total / args.steps
+        value = world * T_VIDEO * args.steps / (ms_total / 1e3)
+        trunk_ms_per_step = stage_ms["trunk"] / args.steps
+        achieved_tflops = TRUNK_GFLOP_PER_CLIP * N_CLIPS / trunk_ms_per_step          # GFLOP/ms == TFLOP/s
+        elt = 2 if args.precision == "bf16" else 4
+        fuse_bytes = N_CLIPS * CLIP * H * W * 6 * elt + T_VIDEO * H * W * (8 + 1) + T_VIDEO * 8
+        line = {
+            "metric": "frames/sec segmented+tracked (fusion on)", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": dict(workload_config(), batch_clips=bc, parallelism=f"video-sharded x{world}, no collective"),
+            "clip_frames_per_s": world * N_CLIPS * CLIP * args.steps / (ms_total / 1e3),
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()} | {"warp_fuse": fuse_ms},
+            "e2e": {"value": world * T_VIDEO * args.steps / (e2e_ms / 1e3), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(video_host.numel() * 4), "d2h_bytes_per_step": int(T_VIDEO * H * W)},
+            "gpu_launches": args.steps * (((N_CLIPS + bc - 1) // bc) * KERNELS_PER_FORWARD + 1),
+            "roofline": {"kernel": "conv_umma_kernel (trunk: stem 3x1x1 + layer1-4, 36 launches per clip batch)",
+                         "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved_tflops / peaks["bf16_tflops"], "traffic": None,
+                         "peak_source": peaks["source"] + " (sustained; burst %.1f)" % peaks["bf16_tflops_burst"],
+                         "algorithmic_gflop_per_clip": TRUNK_GFLOP_PER_CLIP},
+            "roofline_warp_fuse": {"kernel": "warp_fuse_kernel", "bound": "hbm", "achieved": fuse_bytes / (fuse_ms * 1e6),
+                                   "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fuse_bytes / (fuse_ms * 1e6) / peaks["hbm_gbs"],
+                                   "traffic": None, "algorithmic_bytes": fuse_bytes},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_sample(4)
+            line["cpu_baseline"] = {"value": cb["frames_per_s"], "unit": "frames/s", "cores": cb["threads"], "kind": "port",
+                                    "sample": "4 of 169 stride-1 clips (reference network restated on PyTorch CPU, "
+                                              f"{cb['sec_per_clip_model']:.2f} s/clip) + oracle warp-fuse, scaled to the whole video"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

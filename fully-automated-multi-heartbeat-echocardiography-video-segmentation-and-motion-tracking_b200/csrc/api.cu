@@ -91,6 +91,10 @@ struct clasfv_handle {
   // workspace
   void* ws = nullptr; size_t ws_bytes = 0;
   TableRing ring;
+  // optional stage profiler: 5 events per forward call (start, stem, trunk, laterals, head)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  int prof_calls = 0;
 };
 
 namespace {
@@ -247,6 +251,7 @@ void clasfv_destroy(clasfv_handle* h) {
   cudaDeviceSynchronize();
   free_packed(h);
   if (h->ws) cudaFree(h->ws);
+  for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
   h->ring.destroy();
   delete h;
 }
@@ -412,11 +417,24 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
     for (int i = 0; i < n; ++i) o[i] = clip_offset_host ? clip_offset_host[i] : (int64_t)i * 3 * thw;
   }, &offs_dev);
   if (rc) return rc;
+  auto mark = [&](int stage) -> int {
+    if (!h->profiling) return CLASFV_OK;
+    const size_t idx = (size_t)h->prof_calls * 5 + stage;
+    while (h->prof_events.size() <= idx) {
+      cudaEvent_t ev;
+      CLASFV_CUDA(cudaEventCreate(&ev));
+      h->prof_events.push_back(ev);
+    }
+    CLASFV_CUDA(cudaEventRecord(h->prof_events[idx], stream));
+    return CLASFV_OK;
+  };
+  if ((rc = mark(0))) return rc;
   // ---- stem
   StemArgs sa;
   sa.x = x_dev; sa.clip_offset = static_cast<const int64_t*>(offs_dev); sa.channel_stride = channel_stride;
   sa.n = n; sa.t = t; sa.h = height; sa.w = width; sa.weight = h->stem_w; sa.bias = h->stem_b; sa.out = ws + o_s0; sa.out_channels = STEM_MID_PAD; sa.out_dtype = act;
   if ((rc = launch_stem(sa, stream))) return rc;
+  if ((rc = mark(1))) return rc;
   if ((rc = run_conv(h, make_conv(h->stem_t, n, T[0], H[0], W[0], ws + o_s0, ws + o_f[0], nullptr, 1, act, 0), stream))) return rc;
   // ---- residual layers
   for (int l = 0; l < 4; ++l) {
@@ -441,17 +459,46 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
       in = out; ti = c4.s.to; hi = c4.s.ho; wi = c4.s.wo;
     }
   }
+  if ((rc = mark(2))) return rc;
   // ---- decoder: lateral projections at native resolution (fp32 out), stem + layer1 share one map
   if ((rc = run_conv(h, make_conv(h->lateral[0], n, T[0], H[0], W[0], ws + o_f[0], ws + o_g[0], nullptr, 0, act, 1), stream))) return rc;
   if ((rc = run_conv(h, make_conv(h->lateral[1], n, T[1], H[1], W[1], ws + o_f[1], ws + o_g[0], ws + o_g[0], 0, act, 1), stream))) return rc;
   for (int i = 2; i < 5; ++i)
     if ((rc = run_conv(h, make_conv(h->lateral[i], n, T[i], H[i], W[i], ws + o_f[i], ws + o_g[i - 1], nullptr, 0, act, 1), stream))) return rc;
+  if ((rc = mark(3))) return rc;
   HeadArgs ha;
   for (int i = 0; i < 4; ++i) { ha.g[i] = reinterpret_cast<const float*>(ws + o_g[i]); ha.tl[i] = T[i + 1]; ha.hl[i] = H[i + 1]; ha.wl[i] = W[i + 1]; }
   ha.n = n; ha.t = t; ha.h = height; ha.w = width;
   ha.b1 = h->b1; ha.w2 = h->w2; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;
   ha.seg = seg_dev; ha.motion = motion_dev; ha.out_dtype = out_dtype; ha.out_kind = out_kind;
-  return launch_head(ha, stream);
+  if ((rc = launch_head(ha, stream))) return rc;
+  if ((rc = mark(4))) return rc;
+  if (h->profiling) ++h->prof_calls;
+  return CLASFV_OK;
+}
+
+int clasfv_profile_begin(clasfv_handle* h) {
+  CLASFV_REQUIRE(h, "clasfv_profile_begin: handle is NULL");
+  h->profiling = true; h->prof_calls = 0;
+  return CLASFV_OK;
+}
+
+int clasfv_profile_end(clasfv_handle* h, float* stage_ms_host, int* calls_host) {
+  CLASFV_REQUIRE(h && stage_ms_host, "clasfv_profile_end: null argument");
+  DeviceGuard guard(h->device);
+  h->profiling = false;
+  for (int s = 0; s < 4; ++s) stage_ms_host[s] = 0.f;
+  for (int c = 0; c < h->prof_calls; ++c) {
+    CLASFV_CUDA(cudaEventSynchronize(h->prof_events[(size_t)c * 5 + 4]));
+    for (int s = 0; s < 4; ++s) {
+      float ms = 0.f;
+      CLASFV_CUDA(cudaEventElapsedTime(&ms, h->prof_events[(size_t)c * 5 + s], h->prof_events[(size_t)c * 5 + s + 1]));
+      stage_ms_host[s] += ms;
+    }
+  }
+  if (calls_host) *calls_host = h->prof_calls;
+  h->prof_calls = 0;
+  return CLASFV_OK;
 }
 
 int clasfv_warp(const float* src_dev, const float* flow_dev, float* out_dev, int n, int c, int height, int width, void* stream) {

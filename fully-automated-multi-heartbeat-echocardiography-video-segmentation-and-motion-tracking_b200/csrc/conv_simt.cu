@@ -131,6 +131,13 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_ndhwc_simt(const SimtParams
     }
     __syncthreads();
     if (ks + 1 < ksteps) fetch(ks + 1);
+    // Blocked summation: the 16 products of this K chunk are summed on their own and added to the running
+    // total once, so the rounding error grows with K/16 + 16 instead of K (K reaches 10 368 in layer4).
+    float part[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
@@ -141,8 +148,12 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_ndhwc_simt(const SimtParams
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
   }
 
   const int col = n0 + tx * 4;

@@ -112,12 +112,22 @@ class Engine:
                                       _lib.torch_dtype_code(seg.dtype), seg.data_ptr(), mot.data_ptr(),
                                       _lib.current_stream_ptr(x.device)), "clasfv_forward")
 
+    def profile_begin(self):
+        check(self.lib.clasfv_profile_begin(self._h), "clasfv_profile_begin")
+
+    def profile_end(self):
+        """-> (dict stage -> summed ms, number of forward calls)"""
+        ms = (C.c_float * 4)()
+        calls = C.c_int(0)
+        check(self.lib.clasfv_profile_end(self._h, ms, C.byref(calls)), "clasfv_profile_end")
+        return {"stem": ms[0], "trunk": ms[1], "lateral": ms[2], "head": ms[3]}, calls.value
+
     def workspace_bytes(self):
         return int(self.lib.clasfv_workspace_bytes(self._h))
 
     # ------------------------------------------------------------------ fusion
     def warp_fuse(self, prob, motion, clip_starts, num_frames, edge_hops=False, acc=None, accumulate=False,
-                  want_mask=True, want_area=True):
+                  want_mask=True, want_area=True, cnt=None):
         """F2 (oracle/fuse_ref.py:warp_fuse). Returns dict(acc, cnt, mask, area)."""
         _lib.require_cuda(prob, "prob"); _lib.require_cuda(motion, "motion")
         n, c, clip_len, h, w = prob.shape
@@ -129,8 +139,8 @@ class Engine:
         if acc is None:
             acc = torch.empty((num_frames, 2, h, w), dtype=torch.float32, device=dev)
             accumulate = False
-        cnt = torch.zeros((num_frames,), dtype=torch.int32, device=dev) if not accumulate else None
-        cnt = cnt if cnt is not None else torch.zeros((num_frames,), dtype=torch.int32, device=dev)
+        if cnt is None:
+            cnt = torch.zeros((num_frames,), dtype=torch.int32, device=dev)
         mask = torch.empty((num_frames, h, w), dtype=torch.uint8, device=dev) if want_mask else None
         area = torch.empty((num_frames,), dtype=torch.int32, device=dev) if want_area else None
         check(self.lib.clasfv_warp_fuse(self._h, prob.data_ptr(), motion.data_ptr(), _lib.torch_dtype_code(prob.dtype),

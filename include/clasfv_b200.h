@@ -83,6 +83,15 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
                    int n, int t, int height, int width, int out_kind, int out_dtype,
                    void* seg_dev, void* motion_dev, void* stream);
 
+/* Stage timing of clasfv_forward with CUDA events recorded on the caller's stream (measurement support,
+ * no reference counterpart).  Between begin and end every forward records five events; end waits for
+ * them and returns the summed milliseconds of the four stages
+ *   [0] stem 1x7x7   [1] trunk convolutions (stem 3x1x1 + layer1..4, the tcgen05 kernel in bf16 mode)
+ *   [2] decoder lateral 1x1x1 projections   [3] fused decoder head
+ * and the number of forward calls covered. */
+int clasfv_profile_begin(clasfv_handle* h);
+int clasfv_profile_end(clasfv_handle* h, float* stage_ms_host /* [4] */, int* calls_host);
+
 /* Largest workspace (bytes) the handle currently holds; informational. */
 int64_t clasfv_workspace_bytes(const clasfv_handle* h);
 

@@ -18,6 +18,7 @@ import torch.nn.functional as F
 import clasfv_b200.synthetic as synthetic
 from oracle import model_ref
 
+RESIDUAL_BRANCH_GAIN = 0.25
 CAL_SHAPE = (32, 112, 112)    # (T, H, W) of the calibration clip: the production clip shape
 
 
@@ -28,6 +29,13 @@ def clip_from_video(video, start=0, length=32):
 @functools.lru_cache(maxsize=4)
 def _calibrated(seed, logit_std, flow_px):
     sd = synthetic.random_state_dict(seed)
+    # Damp every residual branch (the BatchNorm that closes a BasicBlock), as zero-init-residual training
+    # leaves it: without this a random 18-layer ReLU network amplifies any perturbation ~10x more than a
+    # trained one, and bf16 evaluation of the *reference itself* (torch.autocast) disagrees with its own
+    # fp32 evaluation on 11 % of the pixels ("Fixture conditioning").
+    for k in sd:
+        if k.endswith(".conv2.1.weight") or k.endswith(".conv2.1.bias"):
+            sd[k] = sd[k] * RESIDUAL_BRANCH_GAIN
     t, h, w = CAL_SHAPE
     x = clip_from_video(synthetic.synthetic_echo_video(t, h, w, seed=seed + 1000), 0, t)
     model_ref.forward(sd, x, calibrate=True)

@@ -1,0 +1,98 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the host logic of
+the drop-ins (planning, error behaviour) works without a GPU, and the product never falls back."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import clasfv_b200
+from clasfv_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "clasfv_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(clasfv_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(_lib.EXPORTS)
+    lib = _lib.lib()
+    assert os.path.dirname(_lib.LIB_PATH).startswith(clasfv_b200.PACKAGE_DIR)      # built in-tree
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.clasfv_abi_version() == 1
+    assert lib.clasfv_last_error() is not None
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_no_cpu_fallback_anywhere():
+    from clasfv_b200.src import fuse_utils
+    from clasfv_b200.src.model.R2plus1D_18_MotionNet import R2plus1D_18_MotionNet
+    lib = _lib.lib()
+    h = C.c_void_p()
+    assert lib.clasfv_create(0, C.byref(h)) == 5                                   # CLASFV_EUNSUPPORTED
+    assert b"no CPU path" in lib.clasfv_last_error()
+    net = R2plus1D_18_MotionNet(pretrained=False).eval()
+    with pytest.raises(_lib.ClasfvError):
+        net(torch.zeros(1, 3, 8, 16, 16))
+    with pytest.raises(_lib.ClasfvError):
+        fuse_utils.divide_to_consecutive_clips(np.zeros((3, 64, 16, 16), np.float32))
+    with pytest.raises(_lib.ClasfvError):
+        fuse_utils.segment_a_video_with_fusion(np.zeros((3, 64, 16, 16), np.float32), net)
+
+
+def test_state_dict_is_the_reference_state_dict():
+    from clasfv_b200 import synthetic
+    from clasfv_b200.src.model.R2plus1D_18_MotionNet import R2plus1D_18_MotionNet
+    net = R2plus1D_18_MotionNet(pretrained=False)
+    sd = net.state_dict()
+    spec = synthetic.state_dict_spec()
+    assert [k for k, _s, _k in spec] == list(sd.keys()) and len(sd) == 242
+    assert sum(p.numel() for p in net.parameters() if p.requires_grad) == 31575731
+    net.load_state_dict(synthetic.random_state_dict(1))                            # same keys, same shapes
+    wrapped = torch.nn.DataParallel(net)
+    assert all(k.startswith("module.") for k in wrapped.state_dict())
+    assert float(net.motion_head.weight.std()) > 0
+    with pytest.raises(_lib.ClasfvError):                                          # training mode is not implemented
+        net.train()(torch.zeros(1, 3, 8, 16, 16))
+
+
+def test_shift_planning_matches_oracle(capsys):
+    from clasfv_b200.src import fuse_utils
+    from oracle import fuse_ref
+    for t, step, f in ((200, 1, 32), (128, 1, 1), (40, 1, 10), (20, 1, 10), (175, 2, 6), (64, 3, 4)):
+        assert fuse_utils.plan_shifts(t, step, f) == fuse_ref.plan_shifts(t, step, f)
+    fuse_utils.plan_shifts(20, 1, 10)
+    assert "Video is too short" in capsys.readouterr().out
+    for length in (48, 80, 112, 175, 176, 200):
+        assert fuse_utils._num_clips(length) == fuse_ref.num_consecutive_clips(length)
+    assert fuse_utils._shift_plan_entry(3, 75, 32, True) == (3, 75, 2)
+    assert fuse_utils._shift_plan_entry(0, 70, 32, False) == (0, 64, 2)           # truncation without resample
+    with pytest.raises(ValueError):
+        fuse_utils._shift_plan_entry(0, 60, 32, False)                            # rounds up: the reference fails in concatenate
+
+
+def test_host_helpers_match_golden(golden_dir):
+    from clasfv_b200.src.echonet_dataset import EDESpairs, zeroone_normalizer
+    g = np.load(os.path.join(golden_dir, "host_helpers.npz"))
+    np.testing.assert_array_equal(zeroone_normalizer(g["v"].copy()), g["norm"])
+    pairs = EDESpairs([0, 31, 62, 95], [14, 47, 49, 80, 120])
+    np.testing.assert_array_equal(np.array(pairs), g["pairs"])
+
+
+def test_ef_from_synthetic_beating_masks():
+    from clasfv_b200.src.fuse_utils import compute_ef_using_putative_clips, get2dPucks
+    t, h, w = 120, 112, 112
+    yy, xx = np.mgrid[0:h, 0:w]
+    masks = np.zeros((t, h, w), np.int64)
+    for i in range(t):
+        s = 1.0 - 0.25 * (0.5 - 0.5 * np.cos(2 * np.pi * i / 40.0))               # 3 beats
+        masks[i] = (((yy - 60) / (30 * s)) ** 2 + ((xx - 56) / (18 * s)) ** 2) <= 1
+    efs, pairs = compute_ef_using_putative_clips(masks, "synthetic", return_edes=True)
+    assert len(pairs) >= 2 and all(es > ed for ed, es in pairs)
+    # volume ~ s^3: EF = 1 - 0.75^3 = 57.8 %
+    assert all(45 < ef < 70 for ef in efs), efs
+    length, radii = get2dPucks(masks[0].astype(int), (1.0, 1.0))
+    assert 55 < length < 65 and len(radii) == 10
