@@ -233,6 +233,7 @@ def main():
     stage_ms, calls = eng.profile_end()
     fuse_ms = sum(a.elapsed_time(b) for a, b in fuse_events) / len(fuse_events)
 
+    flow_px = float((mot.float().abs().mean() * (W / 2)).item())      # what the gather pattern of warp_fuse depends on
     # ---- e2e through the public API (pinned host video in, host mask out, every step)
     for _ in range(2):
         fuse_utils.segment_a_video_with_fusion(video_host, net, fuse_method="warp", batch_clips=bc)
@@ -275,7 +276,7 @@ def main():
             "roofline_warp_fuse": {"kernel": "warp_fuse_kernel", "bound": "hbm", "achieved": fuse_bytes / (fuse_ms * 1e6),
                                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fuse_bytes / (fuse_ms * 1e6) / peaks["hbm_gbs"],
                                    "traffic": None, "algorithmic_bytes": fuse_bytes},
-            "clocks": clocks,
+            "clocks": clocks, "mean_abs_flow_px": flow_px,
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_sample(4)

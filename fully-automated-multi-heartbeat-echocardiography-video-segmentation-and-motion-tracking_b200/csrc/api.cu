@@ -88,6 +88,7 @@ struct clasfv_handle {
   Block blocks[4][2];
   PackedConv lateral[5];
   float *b1 = nullptr, *w2 = nullptr, *b2 = nullptr, *wh = nullptr, *bh = nullptr;
+  __nv_bfloat16* w2_bf16 = nullptr;
   // workspace
   void* ws = nullptr; size_t ws_bytes = 0;
   TableRing ring;
@@ -200,7 +201,7 @@ ConvArgs make_conv(const PackedConv& pc, int n, int ti, int hi, int wi, const vo
   s.n = n; s.ti = ti; s.hi = hi; s.wi = wi; s.cin = pc.cin_pad; s.cout = pc.cout_pad;
   s.kt = pc.kt; s.kh = pc.kh; s.kw = pc.kw; s.st = pc.st; s.sh = pc.sh; s.sw = pc.sw; s.pt = pc.pt; s.ph = pc.ph; s.pw = pc.pw;
   s.to = (ti + 2 * pc.pt - pc.kt) / pc.st + 1; s.ho = (hi + 2 * pc.ph - pc.kh) / pc.sh + 1; s.wo = (wi + 2 * pc.pw - pc.kw) / pc.sw + 1;
-  a.in = in; a.weight = pc.w; a.bias = pc.bias; a.residual = residual; a.out = out;
+  a.in = in; a.in2 = nullptr; a.in_batch_stride = 0; a.weight = pc.w; a.bias = pc.bias; a.residual = residual; a.out = out;
   a.act_dtype = act_dtype; a.out_f32 = out_f32; a.relu = relu;
   return a;
 }
@@ -333,7 +334,22 @@ int clasfv_finalize(clasfv_handle* h, int precision) {
       PackedConv& pc = h->lateral[i];
       pc = PackedConv();
       pc.cin = pc.cin_pad = widths[i]; pc.cout = pc.cout_pad = DEC;
-      if ((rc = pack_weight(h, w1->data.data(), DEC, widths[i], off, 1024, 1, s1.data(), DEC, widths[i], h->precision, &pc.w))) return rc;
+      if (i == 0) {
+        // the stem and layer1 maps share a resolution: one two-source convolution, weights [2][64][64]
+        std::vector<float> two((size_t)2 * DEC * 64);
+        for (int src = 0; src < 2; ++src)
+          for (int co = 0; co < DEC; ++co)
+            for (int ci = 0; ci < 64; ++ci) two[((size_t)src * DEC + co) * 64 + ci] = w1->data[(size_t)co * 1024 + src * 64 + ci] * s1[co];
+        if (h->precision == CLASFV_F32) {
+          if ((rc = dev_upload(h, two.data(), two.size() * 4, &pc.w))) return rc;
+        } else {
+          std::vector<__nv_bfloat16> tb(two.size());
+          for (size_t k = 0; k < two.size(); ++k) tb[k] = __float2bfloat16_rn(two[k]);
+          if ((rc = dev_upload(h, tb.data(), tb.size() * 2, &pc.w))) return rc;
+        }
+      } else if (i >= 2) {
+        if ((rc = pack_weight(h, w1->data.data(), DEC, widths[i], off, 1024, 1, s1.data(), DEC, widths[i], h->precision, &pc.w))) return rc;
+      }
       off += widths[i];
     }
     std::vector<float> b1(DEC), w2p(DEC * DEC), b2(DEC), wh(6 * DEC), bh(6);
@@ -350,6 +366,11 @@ int clasfv_finalize(clasfv_handle* h, int precision) {
     for (int q = 0; q < 4; ++q) bh[2 + q] = bm->data[q];
     if ((rc = dev_upload(h, b1.data(), b1.size() * 4, reinterpret_cast<void**>(&h->b1)))) return rc;
     if ((rc = dev_upload(h, w2p.data(), w2p.size() * 4, reinterpret_cast<void**>(&h->w2)))) return rc;
+    {
+      std::vector<__nv_bfloat16> wb(w2p.size());
+      for (size_t k = 0; k < w2p.size(); ++k) wb[k] = __float2bfloat16_rn(w2p[k]);
+      if ((rc = dev_upload(h, wb.data(), wb.size() * 2, reinterpret_cast<void**>(&h->w2_bf16)))) return rc;
+    }
     if ((rc = dev_upload(h, b2.data(), b2.size() * 4, reinterpret_cast<void**>(&h->b2)))) return rc;
     if ((rc = dev_upload(h, wh.data(), wh.size() * 4, reinterpret_cast<void**>(&h->wh)))) return rc;
     if ((rc = dev_upload(h, bh.data(), bh.size() * 4, reinterpret_cast<void**>(&h->bh)))) return rc;
@@ -405,8 +426,10 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
   const size_t o_ta = region(P[1] * 64 * es);
   const size_t o_x1 = region(P[1] * 64 * es);
   const size_t o_ds = region(P[2] * 128 * es);
+  const bool tc_head = act == CLASFV_BF16 && !h->force_simt;     // tensor-core head reads bf16 lateral maps
+  const size_t gs = tc_head ? 2 : 4;
   size_t o_g[4];
-  for (int i = 0; i < 4; ++i) o_g[i] = region(P[i + 1] * DEC * sizeof(float));
+  for (int i = 0; i < 4; ++i) o_g[i] = region(P[i + 1] * DEC * gs);
   int rc;
   if ((rc = ensure_workspace(h, total))) return rc;
   char* ws = static_cast<char*>(h->ws);
@@ -429,13 +452,27 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
     return CLASFV_OK;
   };
   if ((rc = mark(0))) return rc;
-  // ---- stem
+  // ---- stem.  The 1x7x7 convolution is per frame, so clips that are equally spaced windows of one
+  // resident video share it: it runs once over the union of their frames and the 3x1x1 convolution that
+  // follows reads overlapping windows of that map (clip-edge zero padding comes from the window extent).
+  int64_t frame_step = 0;     // > 0: shared-stem mode, clips start every frame_step frames
+  if (clip_offset_host && n >= 2) {
+    const int64_t d = clip_offset_host[1] - clip_offset_host[0], hw = (int64_t)height * width;
+    bool uniform = d > 0 && d % hw == 0 && d / hw < t;
+    for (int i = 2; i < n && uniform; ++i) uniform = clip_offset_host[i] - clip_offset_host[i - 1] == d;
+    if (uniform) frame_step = d / hw;
+  }
   StemArgs sa;
   sa.x = x_dev; sa.clip_offset = static_cast<const int64_t*>(offs_dev); sa.channel_stride = channel_stride;
   sa.n = n; sa.t = t; sa.h = height; sa.w = width; sa.weight = h->stem_w; sa.bias = h->stem_b; sa.out = ws + o_s0; sa.out_channels = STEM_MID_PAD; sa.out_dtype = act;
+  if (frame_step) { sa.n = 1; sa.t = (int)((n - 1) * frame_step + t); }
   if ((rc = launch_stem(sa, stream))) return rc;
   if ((rc = mark(1))) return rc;
-  if ((rc = run_conv(h, make_conv(h->stem_t, n, T[0], H[0], W[0], ws + o_s0, ws + o_f[0], nullptr, 1, act, 0), stream))) return rc;
+  {
+    ConvArgs c = make_conv(h->stem_t, n, T[0], H[0], W[0], ws + o_s0, ws + o_f[0], nullptr, 1, act, 0);
+    if (frame_step) c.in_batch_stride = frame_step * (int64_t)H[0] * W[0] * STEM_MID_PAD;
+    if ((rc = run_conv(h, c, stream))) return rc;
+  }
   // ---- residual layers
   for (int l = 0; l < 4; ++l) {
     const void* in = ws + o_f[l];
@@ -461,17 +498,21 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
   }
   if ((rc = mark(2))) return rc;
   // ---- decoder: lateral projections at native resolution (fp32 out), stem + layer1 share one map
-  if ((rc = run_conv(h, make_conv(h->lateral[0], n, T[0], H[0], W[0], ws + o_f[0], ws + o_g[0], nullptr, 0, act, 1), stream))) return rc;
-  if ((rc = run_conv(h, make_conv(h->lateral[1], n, T[1], H[1], W[1], ws + o_f[1], ws + o_g[0], ws + o_g[0], 0, act, 1), stream))) return rc;
+  {
+    ConvArgs c = make_conv(h->lateral[0], n, T[0], H[0], W[0], ws + o_f[0], ws + o_g[0], nullptr, 0, act, tc_head ? 0 : 1);
+    c.in2 = ws + o_f[1];
+    if ((rc = run_conv(h, c, stream))) return rc;
+  }
   for (int i = 2; i < 5; ++i)
-    if ((rc = run_conv(h, make_conv(h->lateral[i], n, T[i], H[i], W[i], ws + o_f[i], ws + o_g[i - 1], nullptr, 0, act, 1), stream))) return rc;
+    if ((rc = run_conv(h, make_conv(h->lateral[i], n, T[i], H[i], W[i], ws + o_f[i], ws + o_g[i - 1], nullptr, 0, act, tc_head ? 0 : 1), stream))) return rc;
   if ((rc = mark(3))) return rc;
   HeadArgs ha;
-  for (int i = 0; i < 4; ++i) { ha.g[i] = reinterpret_cast<const float*>(ws + o_g[i]); ha.tl[i] = T[i + 1]; ha.hl[i] = H[i + 1]; ha.wl[i] = W[i + 1]; }
+  for (int i = 0; i < 4; ++i) { ha.g[i] = ws + o_g[i]; ha.tl[i] = T[i + 1]; ha.hl[i] = H[i + 1]; ha.wl[i] = W[i + 1]; }
+  ha.g_dtype = tc_head ? CLASFV_BF16 : CLASFV_F32;
   ha.n = n; ha.t = t; ha.h = height; ha.w = width;
-  ha.b1 = h->b1; ha.w2 = h->w2; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;
+  ha.b1 = h->b1; ha.w2 = h->w2; ha.w2_bf16 = h->w2_bf16; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;
   ha.seg = seg_dev; ha.motion = motion_dev; ha.out_dtype = out_dtype; ha.out_kind = out_kind;
-  if ((rc = launch_head(ha, stream))) return rc;
+  if ((rc = tc_head ? launch_head_umma(ha, stream) : launch_head(ha, stream))) return rc;
   if ((rc = mark(4))) return rc;
   if (h->profiling) ++h->prof_calls;
   return CLASFV_OK;

@@ -5,11 +5,11 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 mkdir -p build
-for f in api conv_simt conv_umma decoder fusion; do
-  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ internal.h -nt build/$f.o ] || [ ../../include/clasfv_b200.h -nt build/$f.o ]; then
+for f in api conv_simt conv_umma decoder decoder_umma fusion; do
+  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ internal.h -nt build/$f.o ] || [ umma_ptx.cuh -nt build/$f.o ] || [ ../../include/clasfv_b200.h -nt build/$f.o ]; then
     $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f.cu -o build/$f.o &
   fi
 done
 wait
-$NVCC -shared -o libclasfv_b200.so build/api.o build/conv_simt.o build/conv_umma.o build/decoder.o build/fusion.o
+$NVCC -shared -o libclasfv_b200.so build/api.o build/conv_simt.o build/conv_umma.o build/decoder.o build/decoder_umma.o build/fusion.o
 echo "built $(pwd)/libclasfv_b200.so"

@@ -58,7 +58,8 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
 
 struct SimtParams {
   ConvShape s;
-  const void* in; const void* weight; const float* bias; const void* residual; void* out;
+  const void* in; const void* in2; const void* weight; const float* bias; const void* residual; void* out;
+  int64_t in_batch_stride;
   int relu; int m_total;
 };
 
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_ndhwc_simt(const SimtParams
     const int ho = r % s.ho; r /= s.ho;
     const int to = r % s.to; r /= s.to;
     ti0 = to * s.st - s.pt; hi0 = ho * s.sh - s.ph; wi0 = wo * s.sw - s.pw;
-    in_n = (int64_t)r * s.ti * s.hi * s.wi;
+    in_n = (int64_t)r * p.in_batch_stride;      // in positions (elements / cin)
   }
   // B-operand role (threads 0..127): output channel row and 8-channel half
   const int b_row = tid & (BN - 1), b_half = (tid >> 6) & 1;
@@ -99,16 +100,20 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_ndhwc_simt(const SimtParams
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   const int kchunks = s.cin / BK;
-  const int ntaps = s.kt * s.kh * s.kw;
+  const InT* __restrict__ in2 = static_cast<const InT*>(p.in2);
+  const int ntaps = s.kt * s.kh * s.kw * (in2 ? 2 : 1);   // two-source 1x1x1: tap 1 reads the second tensor
   const int ksteps = ntaps * kchunks;
 
   Vec8<InT> ra, rb;
   auto fetch = [&](int ks) {
     const int tap = ks / kchunks, c0 = (ks - tap * kchunks) * BK;
-    const int dw = tap % s.kw, dh = (tap / s.kw) % s.kh, dt = tap / (s.kw * s.kh);
+    const InT* src = in;
+    int sp = tap;
+    if (in2 && tap == 1) { src = in2; sp = 0; }
+    const int dw = sp % s.kw, dh = (sp / s.kw) % s.kh, dt = sp / (s.kw * s.kh);
     const int ti = ti0 + dt, hi = hi0 + dh, wi = wi0 + dw;
     const bool ok = row_ok && (unsigned)ti < (unsigned)s.ti && (unsigned)hi < (unsigned)s.hi && (unsigned)wi < (unsigned)s.wi;
-    if (ok) ra.load(in + ((in_n + ((int64_t)ti * s.hi + hi) * s.wi + wi) * s.cin + c0 + a_half * 8));
+    if (ok) ra.load(src + ((in_n + ((int64_t)ti * s.hi + hi) * s.wi + wi) * s.cin + c0 + a_half * 8));
     else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) ra.v[i] = 0.f;
@@ -250,7 +255,11 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t stream) {
   const ConvShape& s = a.s;
   CLASFV_REQUIRE(s.cin % BK == 0 && s.cout % 4 == 0, "conv_simt: cin %% 16 and cout %% 4 required (cin=%d cout=%d)", s.cin, s.cout);
   SimtParams p;
-  p.s = s; p.in = a.in; p.weight = a.weight; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.relu = a.relu;
+  p.s = s; p.in = a.in; p.in2 = a.in2; p.weight = a.weight; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.relu = a.relu;
+  CLASFV_REQUIRE(!a.in2 || (s.kt * s.kh * s.kw == 1 && s.st == 1 && s.sh == 1 && s.sw == 1), "conv_simt: two-source mode is 1x1x1 only");
+  const int64_t dense = (int64_t)s.ti * s.hi * s.wi;
+  CLASFV_REQUIRE(a.in_batch_stride % s.cin == 0, "conv_simt: batch stride must be a whole number of positions");
+  p.in_batch_stride = a.in_batch_stride ? a.in_batch_stride / s.cin : dense;
   const int64_t m_total = (int64_t)s.n * s.to * s.ho * s.wo;
   CLASFV_REQUIRE(m_total > 0 && m_total < (1ll << 31), "conv_simt: bad row count");
   p.m_total = (int)m_total;

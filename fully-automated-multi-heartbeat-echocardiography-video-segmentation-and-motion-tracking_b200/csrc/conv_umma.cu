@@ -22,12 +22,17 @@
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 #include "internal.h"
+#include "umma_ptx.cuh"
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace clasfv {
 namespace {
+
+using namespace ptx;
 
 constexpr int TILE_M = 128;
 constexpr int SLAB_K = 64;          // channels per K slab (128 bytes of bf16 = one swizzle row)
@@ -35,108 +40,51 @@ constexpr int UMMA_K = 16;
 constexpr int UMMA_THREADS = 192;
 constexpr int MAX_TAPS = 27;
 constexpr int MAX_VIEWS = 4;
-constexpr int A_SLAB_BYTES = TILE_M * SLAB_K * 2;   // 16 KiB
+constexpr int SMEM_BUDGET = 222 * 1024;
 
+// Filter taps are organised in GROUPS that share one A slab.  A group is one TMA box load of the input
+// (the output tile's box, grown by a halo along the group's sharing axis); each of its taps is the same
+// 128-row MMA started `row_off` rows further into that slab.  Sharing needs the halo axis to be the
+// outermost varying axis of the box and the per-step row count to be a multiple of 8 (one swizzle atom),
+// so a shifted start is just a different descriptor start address:
+//   3x1x1 temporal, stride 1 : 1 group of 3 taps, halo of 2 frames            (box bw x bh x (bt+2), bb = 1)
+//   1x3x3 spatial,  stride 1 : 3 groups (kw) of 3 taps (kh), halo of 2 rows   (box bw x (bh+2), bt = bb = 1, bw % 8 == 0)
+//   anything else            : every tap its own group, no halo
 struct UmmaParams {
   CUtensorMap tmap_a[MAX_VIEWS];
   CUtensorMap tmap_b;
-  int ntaps, kslabs, k16_last;
-  int8_t tap_view[MAX_TAPS], tap_dw[MAX_TAPS], tap_dh[MAX_TAPS], tap_dt[MAX_TAPS];
+  int ngroups, ntaps, kslabs, k16_last;
+  int8_t grp_view[MAX_TAPS], grp_dw[MAX_TAPS], grp_dh[MAX_TAPS], grp_dt[MAX_TAPS];
+  int8_t grp_first[MAX_TAPS + 1];           // taps of group g: [grp_first[g], grp_first[g+1])
+  int8_t tap_widx[MAX_TAPS];                // index of the tap in the packed weight tensor
+  uint16_t tap_rowoff[MAX_TAPS];            // start row of the tap's MMA inside the group's A slab
   int tiles_w, tiles_h, tiles_t, tiles_b;   // M tiling of the output grid
   int tiles_n;                              // N tiling
-  int bw, bh, bt, bb;                       // box extents (rows = bw*bh*bt*bb <= 128)
+  int bw, bh, bt, bb;                       // output box extents (rows = bw*bh*bt*bb <= 128)
   int bn;                                   // N tile width
   int n, to, ho, wo, cout;
-  int nstages, b_slab_bytes, tx_bytes, tmem_cols;
+  int nstages, a_slab_bytes, a_tx_bytes, b_slab_bytes, b_stage_slabs, resident, tmem_cols, bias_bytes;
   uint32_t idesc;
   const float* bias; const void* residual; void* out;
   int relu, out_f32;
 };
 
-// ---------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done && spin > (1u << 24)) { printf("clasfv conv_umma: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-  }
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);          // start address
-  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset: 8 rows x 128 B
-  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
-  return d;
-}
-
 // ------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A slabs][B slabs][barriers][tmem ptr]; base re-aligned to 1024 for the swizzle atoms
+  // carve: [A slabs][B stage slabs | resident weights][barriers][tmem ptr]; base re-aligned to 1024
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
-  const uint32_t b_base = a_base + (uint32_t)p.nstages * A_SLAB_BYTES;
-  const uint32_t bar_base = b_base + (uint32_t)p.nstages * (uint32_t)p.b_slab_bytes;
+  const uint32_t b_base = a_base + (uint32_t)(p.nstages * p.a_slab_bytes);
+  const uint32_t b_bytes = p.resident ? (uint32_t)(p.ntaps * p.kslabs * p.b_slab_bytes) : (uint32_t)(p.nstages * p.b_stage_slabs * p.b_slab_bytes);
+  const uint32_t bias_base = b_base + b_bytes;                       // [cout] fp32 (zeros when the layer has no bias)
+  const uint32_t bar_base = bias_base + (uint32_t)p.bias_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.nstages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * p.nstages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * p.nstages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * p.nstages + 4);
+  const uint32_t wres_bar = bar_base + 8u * (uint32_t)(2 * p.nstages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * p.nstages + 5);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,7 +96,14 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
     for (int s = 0; s < p.nstages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    mbar_init(wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    // folded-BN bias -> shared memory once: an epilogue that fetched it from global memory per 16-column
+    // chunk spent 30 % of its issue slots waiting on that load (profiles/r01c ncu source page)
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < p.cout; i += UMMA_THREADS) bias_s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -162,6 +117,13 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
+      if (p.resident) {
+        // the whole filter bank of this (single) N tile stays in shared memory for the life of the CTA
+        mbar_arrive_expect_tx(wres_bar, (uint32_t)(p.ntaps * p.kslabs * p.b_slab_bytes));
+        for (int tap = 0; tap < p.ntaps; ++tap)
+          for (int ks = 0; ks < p.kslabs; ++ks)
+            tma_load_3d(b_base + (uint32_t)((tap * p.kslabs + ks) * p.b_slab_bytes), &p.tmap_b, wres_bar, ks * SLAB_K, 0, p.tap_widx[tap]);
+      }
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.tiles_n;
@@ -170,14 +132,19 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
         const int h0 = (mt % p.tiles_h) * p.bh; mt /= p.tiles_h;
         const int t0 = (mt % p.tiles_t) * p.bt; mt /= p.tiles_t;
         const int b0 = mt * p.bb;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const CUtensorMap* map = &p.tmap_a[p.tap_view[tap]];
-          const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], ct = t0 + p.tap_dt[tap];
+        for (int g = 0; g < p.ngroups; ++g) {
+          const CUtensorMap* map = &p.tmap_a[p.grp_view[g]];
+          const int cw = w0 + p.grp_dw[g], ch = h0 + p.grp_dh[g], ct = t0 + p.grp_dt[g];
+          const int tap0 = p.grp_first[g], tap1 = p.grp_first[g + 1];
+          const uint32_t tx = (uint32_t)p.a_tx_bytes + (p.resident ? 0u : (uint32_t)((tap1 - tap0) * p.b_slab_bytes));
           for (int ks = 0; ks < p.kslabs; ++ks) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.tx_bytes);
-            tma_load_5d(a_base + (uint32_t)stage * A_SLAB_BYTES, map, full_bar(stage), ks * SLAB_K, cw, ch, ct, b0);
-            tma_load_3d(b_base + (uint32_t)stage * (uint32_t)p.b_slab_bytes, &p.tmap_b, full_bar(stage), ks * SLAB_K, n_tile * p.bn, tap);
+            mbar_arrive_expect_tx(full_bar(stage), tx);
+            tma_load_5d(a_base + (uint32_t)(stage * p.a_slab_bytes), map, full_bar(stage), ks * SLAB_K, cw, ch, ct, b0);
+            if (!p.resident)
+              for (int tap = tap0; tap < tap1; ++tap)
+                tma_load_3d(b_base + (uint32_t)((stage * p.b_stage_slabs + (tap - tap0)) * p.b_slab_bytes), &p.tmap_b, full_bar(stage),
+                            ks * SLAB_K, n_tile * p.bn, p.tap_widx[tap]);
             if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -186,6 +153,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
+      if (p.resident) { mbar_wait(wres_bar, 0); tc_fence_after(); }
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -194,17 +162,23 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.bn);
         uint32_t accumulate = 0;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
+        for (int g = 0; g < p.ngroups; ++g) {
+          const int tap0 = p.grp_first[g], tap1 = p.grp_first[g + 1];
           for (int ks = 0; ks < p.kslabs; ++ks) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint64_t da = smem_desc_sw128(a_base + (uint32_t)stage * A_SLAB_BYTES);
-            const uint64_t db = smem_desc_sw128(b_base + (uint32_t)stage * (uint32_t)p.b_slab_bytes);
+            const uint32_t a_addr = a_base + (uint32_t)(stage * p.a_slab_bytes);
             const int nk = (ks == p.kslabs - 1) ? p.k16_last : SLAB_K / UMMA_K;
-            for (int k = 0; k < nk; ++k) {
-              // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
-              tc_mma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, accumulate);
-              accumulate = 1;
+            for (int tap = tap0; tap < tap1; ++tap) {
+              const uint64_t da = smem_desc_sw128(a_addr + (uint32_t)p.tap_rowoff[tap] * 128u);
+              const uint32_t b_addr = p.resident ? b_base + (uint32_t)((tap * p.kslabs + ks) * p.b_slab_bytes)
+                                                 : b_base + (uint32_t)((stage * p.b_stage_slabs + (tap - tap0)) * p.b_slab_bytes);
+              const uint64_t db = smem_desc_sw128(b_addr);
+              for (int k = 0; k < nk; ++k) {
+                // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
+                tc_mma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, accumulate);
+                accumulate = 1;
+              }
             }
             tc_commit(empty_bar(stage));          // slab reusable once these MMAs have read it
             if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
@@ -217,6 +191,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
+    const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1; const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -235,55 +210,63 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
       const bool valid = ib < p.bb && ow < p.wo && oh < p.ho && ot < p.to && ob < p.n;
       const int c0 = n_tile * p.bn;
       const int64_t off = ((((int64_t)ob * p.to + ot) * p.ho + oh) * p.wo + ow) * p.cout + c0;
+      const int ncols = min(p.bn, p.cout - c0);   // ragged last N tile: columns past Cout are never stored
+      const bool has_res = p.residual != nullptr && valid;
 
+      // the residual of the first chunk is requested before the accumulator is even complete
+      uint4 res_bf[2]; float4 res_f[4];
+      auto fetch_res = [&](int cc) {
+        if (!has_res) return;
+        if (p.out_f32) {
+          const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + off + cc);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) res_f[i] = __ldg(rp + i);
+        } else {
+          const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off + cc);
+          res_bf[0] = __ldg(rp); res_bf[1] = __ldg(rp + 1);
+        }
+      };
+      fetch_res(0);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.bn);
-      const int ncols = min(p.bn, p.cout - c0);   // ragged last N tile: columns past Cout are never stored
+      uint32_t acc[16];
+      tc_ld16(taddr, acc);
       for (int cc = 0; cc < ncols; cc += 16) {
-        uint32_t acc[16];
-        tc_ld16(taddr + (uint32_t)cc, acc);
         tc_wait_ld();
-        if (valid) {
-          float v[16];
+        float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
-          if (p.bias) {
+        for (int i = 0; i < 4; ++i) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + cc + 4 * i);
+          v[4 * i] = __uint_as_float(acc[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b4.y;
+          v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4.w;
+        }
+        if (cc + 16 < ncols) tc_ld16(taddr + (uint32_t)(cc + 16), acc);      // next chunk's accumulators in flight
+        if (has_res) {
+          if (p.out_f32) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + cc) + i);
-              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            for (int i = 0; i < 4; ++i) { v[4 * i] += res_f[i].x; v[4 * i + 1] += res_f[i].y; v[4 * i + 2] += res_f[i].z; v[4 * i + 3] += res_f[i].w; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&res_bf[i]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hh[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
             }
           }
+          if (cc + 16 < ncols) fetch_res(cc + 16);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (valid) {
           if (p.out_f32) {
             float* o = static_cast<float*>(p.out) + off + cc;
-            if (p.residual) {
-              const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + off + cc);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) { const float4 r4 = rp[i]; v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w; }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           } else {
             __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + off + cc;
-            if (p.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off + cc);
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const uint4 r4 = rp[i];
-                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&r4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hh[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               uint4 w4;
@@ -351,23 +334,38 @@ inline void split_offset(int off, int stride, int* q, int* r) {
   *q = qq; *r = rr;
 }
 
-// Choose the (bw,bh,bt,bb) box of <= 128 output positions that wastes the fewest MMA rows.
-void choose_box(int wo, int ho, int to, int n, int* bw, int* bh, int* bt, int* bb) {
-  double best = -1.0; int best_rows = 0;
+enum ShareMode { SHARE_NONE = 0, SHARE_T = 1, SHARE_H = 2 };
+
+// Choose the (bw,bh,bt,bb) box of <= 128 output positions that wastes the fewest MMA rows, under the
+// layout constraints of the sharing mode (see UmmaParams).  Returns false if no box satisfies them.
+bool choose_box(int wo, int ho, int to, int n, ShareMode mode, int* bw, int* bh, int* bt, int* bb) {
+  double best = -1.0; int best_rows = 0, best_halo = 1 << 30; bool found = false;
   for (int w = 1; w <= wo && w <= TILE_M; ++w)
     for (int h = 1; h <= ho && w * h <= TILE_M; ++h)
       for (int t = 1; t <= to && w * h * t <= TILE_M; ++t) {
         int b = TILE_M / (w * h * t);
         if (b > n) b = n;
         if (b < 1) continue;
+        int halo_rows = 0;
+        if (mode == SHARE_T) {                   // frames are the outermost axis of the box; a frame is whole swizzle atoms
+          b = 1;
+          if ((w * h) % 8 != 0) continue;
+          halo_rows = 2 * w * h;
+        } else if (mode == SHARE_H) {            // rows are the outermost axis; a row is whole swizzle atoms
+          b = 1;
+          if (t != 1 || w % 8 != 0) continue;
+          halo_rows = 2 * w;
+        }
         const int64_t tiles = cdiv(wo, w) * cdiv(ho, h) * cdiv(to, t) * cdiv(n, b);
         const double eff = (double)wo * ho * to * n / ((double)tiles * TILE_M);
         const int rows = w * h * t * b;
-        // prefer higher efficiency, then fuller boxes, then wider rows (longer contiguous runs)
-        if (eff > best + 1e-9 || (eff > best - 1e-9 && (rows > best_rows || (rows == best_rows && w > *bw)))) {
-          best = eff; best_rows = rows; *bw = w; *bh = h; *bt = t; *bb = b;
-        }
+        // prefer higher efficiency, then less halo traffic, then fuller boxes, then wider rows
+        const bool better = eff > best + 1e-9 ||
+                            (eff > best - 1e-9 && (halo_rows < best_halo ||
+                                                   (halo_rows == best_halo && (rows > best_rows || (rows == best_rows && w > *bw)))));
+        if (better) { best = eff; best_rows = rows; best_halo = halo_rows; *bw = w; *bh = h; *bt = t; *bb = b; found = true; }
       }
+  return found;
 }
 
 }  // namespace
@@ -378,14 +376,15 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   const ConvShape& s = a.s;
   CLASFV_REQUIRE(a.act_dtype == CLASFV_BF16, "conv_umma: bf16 activations only");
   CLASFV_REQUIRE(s.cin % 16 == 0 && s.cout % 16 == 0, "conv_umma: channel counts must be multiples of 16 (cin=%d cout=%d)", s.cin, s.cout);
-  const int ntaps = s.kt * s.kh * s.kw;
+  const int sp_taps = s.kt * s.kh * s.kw;
+  const int ntaps = sp_taps * (a.in2 ? 2 : 1);
   CLASFV_REQUIRE(ntaps <= MAX_TAPS, "conv_umma: too many filter taps (%d)", ntaps);
+  CLASFV_REQUIRE(!a.in2 || (sp_taps == 1 && s.st == 1 && s.sh == 1 && s.sw == 1), "conv_umma: two-source mode is 1x1x1 only");
   CLASFV_REQUIRE(((uintptr_t)a.in & 15) == 0 && ((uintptr_t)a.weight & 15) == 0 && ((uintptr_t)a.out & 15) == 0, "conv_umma: pointers must be 16-byte aligned");
 
   UmmaParams p;
   memset(&p, 0, sizeof(p));
-  // ---- N tiling
-  // equal tiles of a multiple of 16 columns when the channel count allows it, else a ragged last tile
+  // ---- N tiling: equal tiles of a multiple of 16 columns when the channel count allows it, else a ragged last tile
   const int min_tiles = (int)cdiv(s.cout, 256);
   int bn = 0;
   for (int nt = min_tiles; nt <= min_tiles + 2 && !bn; ++nt)
@@ -393,42 +392,105 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   if (!bn) bn = round_up((int)cdiv(s.cout, min_tiles), 16);
   CLASFV_REQUIRE(bn >= 16 && bn <= 256, "conv_umma: N tile overflow");
   p.bn = bn; p.tiles_n = (int)cdiv(s.cout, bn);
-  // ---- M tiling
-  choose_box(s.wo, s.ho, s.to, s.n, &p.bw, &p.bh, &p.bt, &p.bb);
-  p.tiles_w = (int)cdiv(s.wo, p.bw); p.tiles_h = (int)cdiv(s.ho, p.bh); p.tiles_t = (int)cdiv(s.to, p.bt); p.tiles_b = (int)cdiv(s.n, p.bb);
+  p.b_slab_bytes = bn * SLAB_K * 2;
   p.n = s.n; p.to = s.to; p.ho = s.ho; p.wo = s.wo; p.cout = s.cout;
   // ---- K
   p.ntaps = ntaps;
   p.kslabs = (int)cdiv(s.cin, SLAB_K);
   p.k16_last = (s.cin - (p.kslabs - 1) * SLAB_K) / UMMA_K;
-  // ---- taps -> (parity view, coordinate shift)
-  int view_key[MAX_VIEWS]; int nviews = 0;
-  int view_rt[MAX_VIEWS], view_rh[MAX_VIEWS], view_rw[MAX_VIEWS];
-  for (int tap = 0; tap < ntaps; ++tap) {
-    const int kw = tap % s.kw, kh = (tap / s.kw) % s.kh, kt = tap / (s.kw * s.kh);
-    int qt, rt, qh, rh, qw, rw;
-    split_offset(kt - s.pt, s.st, &qt, &rt);
-    split_offset(kh - s.ph, s.sh, &qh, &rh);
-    split_offset(kw - s.pw, s.sw, &qw, &rw);
-    const int key = (rt * 8 + rh) * 8 + rw;
-    int v = -1;
-    for (int i = 0; i < nviews; ++i) if (view_key[i] == key) v = i;
-    if (v < 0) {
-      CLASFV_REQUIRE(nviews < MAX_VIEWS, "conv_umma: more than %d stride parities", MAX_VIEWS);
-      v = nviews++; view_key[v] = key; view_rt[v] = rt; view_rh[v] = rh; view_rw[v] = rw;
-    }
-    p.tap_view[tap] = (int8_t)v; p.tap_dw[tap] = (int8_t)qw; p.tap_dh[tap] = (int8_t)qh; p.tap_dt[tap] = (int8_t)qt;
+
+  // ---- tap sharing mode, M tiling, pipeline sizing.  Try the sharing layout first; fall back to one
+  // load per tap when its constraints or the shared-memory budget cannot be met.
+  const bool unit_stride = s.st == 1 && s.sh == 1 && s.sw == 1 && !a.in2;
+  ShareMode want = SHARE_NONE;
+  if (unit_stride && s.kt == 3 && s.kh == 1 && s.kw == 1 && s.pt == 1) want = SHARE_T;
+  if (unit_stride && s.kt == 1 && s.kh == 3 && s.kw == 3 && s.ph == 1 && s.pw == 1 && s.wo % 8 == 0) want = SHARE_H;
+  static const bool no_share = getenv("CLASFV_UMMA_NO_SHARE") != nullptr;
+  if (no_share) want = SHARE_NONE;
+  p.bias_bytes = round_up(s.cout * 4, 128);
+  const int bar_bytes = 8 * (2 * 8 + 6) + 16 + p.bias_bytes;
+  ShareMode mode = SHARE_NONE;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    mode = attempt == 0 ? want : SHARE_NONE;
+    if (!choose_box(s.wo, s.ho, s.to, s.n, mode, &p.bw, &p.bh, &p.bt, &p.bb)) continue;
+    const int rows_out = p.bw * p.bh * p.bt * p.bb;
+    int slab_rows = rows_out, taps_per_group = 1;
+    if (mode == SHARE_T) { slab_rows = p.bw * p.bh * (p.bt + 2); taps_per_group = 3; }
+    if (mode == SHARE_H) { slab_rows = p.bw * (p.bh + 2); taps_per_group = 3; }
+    // the MMA always reads 128 rows from its start row: keep that inside the slab so that no stage reads
+    // another stage's bytes while TMA may be writing them
+    const int max_off = mode == SHARE_T ? 2 * p.bw * p.bh : mode == SHARE_H ? 2 * p.bw : 0;
+    const int slab_alloc_rows = std::max(slab_rows, max_off + TILE_M);
+    p.a_tx_bytes = slab_rows * SLAB_K * 2;
+    p.a_slab_bytes = round_up(slab_alloc_rows * SLAB_K * 2, 1024);
+    p.b_stage_slabs = taps_per_group;
+    const int resident_bytes = ntaps * p.kslabs * p.b_slab_bytes;
+    // resident filter bank: single N tile, and room for >= 3 A stages next to it
+    p.resident = p.tiles_n == 1 && resident_bytes + 3 * p.a_slab_bytes + bar_bytes + 1024 <= SMEM_BUDGET;
+    const int stage_bytes = p.a_slab_bytes + (p.resident ? 0 : taps_per_group * p.b_slab_bytes);
+    int nstages = (SMEM_BUDGET - 1024 - bar_bytes - (p.resident ? resident_bytes : 0)) / stage_bytes;
+    if (nstages > 8) nstages = 8;
+    p.nstages = nstages;
+    if (nstages >= 3 || (mode == SHARE_NONE && nstages >= 2)) break;
+    mode = SHARE_NONE;
   }
-  const uint32_t boxa[5] = {(uint32_t)SLAB_K, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bt, (uint32_t)p.bb};
+  CLASFV_REQUIRE(p.nstages >= 2, "conv_umma: tile does not fit shared memory");
+  p.tiles_w = (int)cdiv(s.wo, p.bw); p.tiles_h = (int)cdiv(s.ho, p.bh); p.tiles_t = (int)cdiv(s.to, p.bt); p.tiles_b = (int)cdiv(s.n, p.bb);
+
+  // ---- groups, taps -> (parity view, coordinate shift, slab row offset)
+  int view_key[MAX_VIEWS]; int nviews = 0;
+  int view_rt[MAX_VIEWS], view_rh[MAX_VIEWS], view_rw[MAX_VIEWS], view_src[MAX_VIEWS];
+  auto find_view = [&](int src, int rt, int rh, int rw) -> int {
+    const int key = ((src * 8 + rt) * 8 + rh) * 8 + rw;
+    for (int i = 0; i < nviews; ++i) if (view_key[i] == key) return i;
+    if (nviews >= MAX_VIEWS) return -1;
+    view_key[nviews] = key; view_rt[nviews] = rt; view_rh[nviews] = rh; view_rw[nviews] = rw; view_src[nviews] = src;
+    return nviews++;
+  };
+  int ng = 0, nt = 0;
+  if (mode == SHARE_T) {
+    const int v = find_view(0, 0, 0, 0);
+    p.grp_view[0] = (int8_t)v; p.grp_dw[0] = 0; p.grp_dh[0] = 0; p.grp_dt[0] = -1; p.grp_first[0] = 0;
+    for (int kt = 0; kt < 3; ++kt) { p.tap_widx[nt] = (int8_t)kt; p.tap_rowoff[nt] = (uint16_t)(kt * p.bw * p.bh); ++nt; }
+    ng = 1;
+  } else if (mode == SHARE_H) {
+    const int v = find_view(0, 0, 0, 0);
+    for (int kw = 0; kw < 3; ++kw) {
+      p.grp_view[ng] = (int8_t)v; p.grp_dw[ng] = (int8_t)(kw - 1); p.grp_dh[ng] = -1; p.grp_dt[ng] = 0; p.grp_first[ng] = (int8_t)nt;
+      for (int kh = 0; kh < 3; ++kh) { p.tap_widx[nt] = (int8_t)(kh * 3 + kw); p.tap_rowoff[nt] = (uint16_t)(kh * p.bw); ++nt; }
+      ++ng;
+    }
+  } else {
+    for (int tap = 0; tap < ntaps; ++tap) {
+      const int src = tap / sp_taps, sp = tap % sp_taps;
+      const int kw = sp % s.kw, kh = (sp / s.kw) % s.kh, kt = sp / (s.kw * s.kh);
+      int qt, rt, qh, rh, qw, rw;
+      split_offset(kt - s.pt, s.st, &qt, &rt);
+      split_offset(kh - s.ph, s.sh, &qh, &rh);
+      split_offset(kw - s.pw, s.sw, &qw, &rw);
+      const int v = find_view(src, rt, rh, rw);
+      CLASFV_REQUIRE(v >= 0, "conv_umma: more than %d stride parities", MAX_VIEWS);
+      p.grp_view[ng] = (int8_t)v; p.grp_dw[ng] = (int8_t)qw; p.grp_dh[ng] = (int8_t)qh; p.grp_dt[ng] = (int8_t)qt; p.grp_first[ng] = (int8_t)nt;
+      p.tap_widx[nt] = (int8_t)tap; p.tap_rowoff[nt] = 0; ++nt; ++ng;
+    }
+  }
+  p.grp_first[ng] = (int8_t)nt;
+  p.ngroups = ng;
+  CLASFV_REQUIRE(nt == ntaps, "conv_umma: internal tap bookkeeping error");
+
+  // ---- tensor maps
+  const int halo_h = mode == SHARE_H ? 2 : 0, halo_t = mode == SHARE_T ? 2 : 0;
+  const uint32_t boxa[5] = {(uint32_t)SLAB_K, (uint32_t)p.bw, (uint32_t)(p.bh + halo_h), (uint32_t)(p.bt + halo_t), (uint32_t)p.bb};
   for (int v = 0; v < MAX_VIEWS; ++v) {
     const int vv = v < nviews ? v : 0;          // unused slots alias view 0 so that prefetch.tensormap is harmless
     const int rt = view_rt[vv], rh = view_rh[vv], rw = view_rw[vv];
     const uint64_t dims[5] = {(uint64_t)s.cin, (uint64_t)cdiv(s.wi - rw, s.sw), (uint64_t)cdiv(s.hi - rh, s.sh),
                               (uint64_t)cdiv(s.ti - rt, s.st), (uint64_t)s.n};
     const uint64_t e = 2;
+    const uint64_t batch_stride = a.in_batch_stride ? (uint64_t)a.in_batch_stride : (uint64_t)s.ti * s.hi * s.wi * s.cin;
     const uint64_t strides[4] = {(uint64_t)s.sw * s.cin * e, (uint64_t)s.sh * s.wi * s.cin * e,
-                                 (uint64_t)s.st * s.hi * s.wi * s.cin * e, (uint64_t)s.ti * s.hi * s.wi * s.cin * e};
-    char* basep = (char*)a.in + (((int64_t)rt * s.hi + rh) * s.wi + rw) * s.cin * (int64_t)e;
+                                 (uint64_t)s.st * s.hi * s.wi * s.cin * e, batch_stride * e};
+    char* basep = (char*)(view_src[vv] ? a.in2 : a.in) + (((int64_t)rt * s.hi + rh) * s.wi + rw) * s.cin * (int64_t)e;
     int rc = encode_map(&p.tmap_a[v], basep, 5, dims, strides, boxa);
     if (rc) return rc;
   }
@@ -439,24 +501,16 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
     int rc = encode_map(&p.tmap_b, const_cast<void*>(a.weight), 3, dims, strides, box);
     if (rc) return rc;
   }
-  // ---- pipeline sizing
-  p.b_slab_bytes = bn * SLAB_K * 2;
-  const int rows_a = p.bw * p.bh * p.bt * p.bb;
-  p.tx_bytes = rows_a * SLAB_K * 2 + p.b_slab_bytes;
-  const int stage_bytes = A_SLAB_BYTES + p.b_slab_bytes;
-  int nstages = (200 * 1024) / stage_bytes;
-  if (nstages > 6) nstages = 6;
-  CLASFV_REQUIRE(nstages >= 2, "conv_umma: tile does not fit shared memory");
-  p.nstages = nstages;
   int cols = 32;
   while (cols < 2 * bn) cols *= 2;
   p.tmem_cols = cols;
-  // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3, M>>4 (cute::UMMA::InstrDescriptor)
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  p.idesc = idesc_bf16_f32(TILE_M, bn);
   p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.relu = a.relu; p.out_f32 = a.out_f32;
 
-  const size_t smem = (size_t)nstages * stage_bytes + 1024 /*align*/ + 8 * (2 * nstages + 4) + 16;
-  CLASFV_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+  const size_t smem = 1024 + (size_t)p.nstages * p.a_slab_bytes +
+                      (p.resident ? (size_t)ntaps * p.kslabs * p.b_slab_bytes : (size_t)p.nstages * p.b_stage_slabs * p.b_slab_bytes) + bar_bytes;
+  CLASFV_REQUIRE(smem <= 227 * 1024, "conv_umma: shared memory overflow (%zu bytes)", smem);
+  CLASFV_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_b * p.tiles_n;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   conv_umma_kernel<<<grid, UMMA_THREADS, smem, stream>>>(p);

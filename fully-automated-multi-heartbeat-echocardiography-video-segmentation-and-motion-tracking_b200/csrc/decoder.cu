@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a, in
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     const AxisTap at = axis_tap(t, a.tl[l], a.t), ah = axis_tap(h, a.hl[l], a.h);
-    const float* __restrict__ g = a.g[l] + (int64_t)n * a.tl[l] * a.hl[l] * a.wl[l] * HC;
+    const float* __restrict__ g = static_cast<const float*>(a.g[l]) + (int64_t)n * a.tl[l] * a.hl[l] * a.wl[l] * HC;
     const int64_t r00 = ((int64_t)at.i0 * a.hl[l] + ah.i0) * a.wl[l], r01 = ((int64_t)at.i0 * a.hl[l] + ah.i1) * a.wl[l];
     const int64_t r10 = ((int64_t)at.i1 * a.hl[l] + ah.i0) * a.wl[l], r11 = ((int64_t)at.i1 * a.hl[l] + ah.i1) * a.wl[l];
     const float w00 = at.l0 * ah.l0, w01 = at.l0 * ah.l1, w10 = at.l1 * ah.l0, w11 = at.l1 * ah.l1;
@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a, in
 }  // namespace
 
 int launch_head(const HeadArgs& a, cudaStream_t stream) {
+  CLASFV_REQUIRE(a.g_dtype == CLASFV_F32, "head: the CUDA-core head reads fp32 lateral maps");
   int rowbuf = 0;
   for (int l = 0; l < 4; ++l) rowbuf += HC * (a.wl[l] | 1);
   const size_t smem = (size_t)(HC * HC + 6 * HC + 2 * HC + 8 + rowbuf) * sizeof(float);

@@ -42,6 +42,9 @@ struct ConvShape {
 struct ConvArgs {
   ConvShape s;
   const void* in;         // (N,Ti,Hi,Wi,Cin)  element type = act_dtype
+  const void* in2;        // optional second source of a two-source 1x1x1 convolution: out = in*W[0] + in2*W[1]
+  int64_t in_batch_stride;  // elements between consecutive clips of `in` (0 = dense Ti*Hi*Wi*Cin); smaller than a
+                            // clip for overlapping temporal windows of one resident video
   const void* weight;     // [tap][Cout][Cin]  element type = act_dtype (fp32 or bf16), BN scale folded
   const float* bias;      // [Cout] fp32 or nullptr
   const void* residual;   // (N,To,Ho,Wo,Cout) element type = out type, or nullptr
@@ -74,11 +77,13 @@ int launch_stem(const StemArgs& a, cudaStream_t stream);
 // Decoder head: 4-level trilinear (align_corners=True) gather-sum of the laterally projected feature
 // maps + bias + ReLU + 64x64 + ReLU + 6x64 heads + softmax / tanh.  decoder.cu
 struct HeadArgs {
-  const float* g[4];           // (N,Tl,Hl,Wl,64) fp32, levels 1/2 (T/1), 1/4 (T/2), 1/8 (T/4), 1/16 (T/8)
+  const void* g[4];            // (N,Tl,Hl,Wl,64) fp32 (g_dtype F32) or bf16, levels 1/2 (T/1), 1/4 (T/2), 1/8 (T/4), 1/16 (T/8)
+  int g_dtype;
   int tl[4], hl[4], wl[4];
   int n, t, h, w;
   const float* b1;             // [64]   folded comb_1 bias + BN1
   const float* w2;             // [64][64] folded comb_2 * BN2 scale, row = output channel
+  const __nv_bfloat16* w2_bf16;  // same, bf16 (tensor-core head)
   const float* b2;             // [64]
   const float* wh;             // [6][64]  rows 0-1 segmentation head, 2-5 motion head
   const float* bh;             // [6]
@@ -86,7 +91,8 @@ struct HeadArgs {
   int out_dtype;               // CLASFV_F32 | CLASFV_BF16
   int out_kind;                // CLASFV_OUT_LOGITS | CLASFV_OUT_PROB
 };
-int launch_head(const HeadArgs& a, cudaStream_t stream);
+int launch_head(const HeadArgs& a, cudaStream_t stream);        // CUDA-core head (fp32 g)
+int launch_head_umma(const HeadArgs& a, cudaStream_t stream);   // tcgen05 head (bf16 g), decoder_umma.cu
 
 // fusion.cu
 int launch_warp(const float* src, const float* flow, float* out, int n, int c, int h, int w, cudaStream_t s);
