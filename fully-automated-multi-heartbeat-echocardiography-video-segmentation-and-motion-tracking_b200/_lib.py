@@ -22,7 +22,7 @@ EXPORTS = (
     "clasfv_abi_version", "clasfv_last_error", "clasfv_create", "clasfv_destroy", "clasfv_set_tensor",
     "clasfv_finalize", "clasfv_forward", "clasfv_workspace_bytes", "clasfv_warp", "clasfv_motion_field",
     "clasfv_warp_fuse", "clasfv_build_shift_clips", "clasfv_fuse_shift_votes", "clasfv_temporal_resample",
-    "clasfv_conv3d", "clasfv_profile_begin", "clasfv_profile_end",
+    "clasfv_conv3d", "clasfv_profile_begin", "clasfv_profile_end", "clasfv_finalize_mask",
 )
 
 
@@ -74,6 +74,7 @@ def lib():
         i32p = C.POINTER(C.c_int32)
         l.clasfv_build_shift_clips.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32p, i32p, i32p, i32p, vp, vp]
         l.clasfv_fuse_shift_votes.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32p, i32p, i32p, vp, vp, vp]
+        l.clasfv_finalize_mask.argtypes = [vp, i32, i32, i32, vp, vp, vp]
         l.clasfv_profile_begin.argtypes = [vp]
         l.clasfv_profile_end.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
         l.clasfv_temporal_resample.argtypes = [vp, vp, i32, i32, i32, i64, vp]

@@ -648,6 +648,11 @@ int clasfv_fuse_shift_votes(clasfv_handle* h, const void* prob_dev, int dtype, i
   return launch_fuse_shift_votes(prob_dev, dtype, t, height, width, clip_len, step, n_shifts, tab, mask_dev, area_dev, stream);
 }
 
+int clasfv_finalize_mask(const float* acc_dev, int t, int height, int width, uint8_t* mask_dev, int32_t* area_dev, void* stream) {
+  CLASFV_REQUIRE(acc_dev && (mask_dev || area_dev) && t >= 1 && height >= 1 && width >= 1, "clasfv_finalize_mask: bad argument");
+  return launch_finalize_mask(acc_dev, t, height, width, mask_dev, area_dev, static_cast<cudaStream_t>(stream));
+}
+
 int clasfv_temporal_resample(const float* in_dev, float* out_dev, int channels, int l_in, int l_out, int64_t hw, void* stream) {
   CLASFV_REQUIRE(in_dev && out_dev && channels >= 1 && l_in >= 1 && l_out >= 1 && hw >= 1, "clasfv_temporal_resample: bad argument");
   return launch_temporal_resample(in_dev, out_dev, channels, l_in, l_out, hw, static_cast<cudaStream_t>(stream));

@@ -222,6 +222,19 @@ __global__ void __launch_bounds__(256) fuse_shift_votes_kernel(const T* __restri
   }
 }
 
+// mask / LV area from already fused class sums (after a multi-GPU halo exchange added the neighbours' votes)
+__global__ void finalize_mask_kernel(const float* __restrict__ acc, int hw, uint8_t* __restrict__ mask, int32_t* __restrict__ area) {
+  const int g = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = pix < hw;
+  const bool lv = valid && acc[((int64_t)g * 2 + 1) * hw + pix] > acc[(int64_t)g * 2 * hw + pix];
+  if (valid && mask) mask[(int64_t)g * hw + pix] = lv ? 1 : 0;
+  if (area) {
+    const int cnt = __syncthreads_count(lv);
+    if (threadIdx.x == 0 && cnt) atomicAdd(area + g, cnt);
+  }
+}
+
 __global__ void temporal_resample_kernel(const float* __restrict__ in, float* __restrict__ out, int l_in, int l_out, int64_t hw) {
   const int d = blockIdx.y, c = blockIdx.z;
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,6 +287,14 @@ int launch_fuse_shift_votes(const void* prob, int dtype, int t, int h, int w, in
     fuse_shift_votes_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(prob), t, h * w, clip_len, step, n_shifts, tab, mask, area);
   else
     fuse_shift_votes_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(prob), t, h * w, clip_len, step, n_shifts, tab, mask, area);
+  CLASFV_CUDA(cudaGetLastError());
+  return CLASFV_OK;
+}
+
+int launch_finalize_mask(const float* acc, int t, int h, int w, uint8_t* mask, int32_t* area, cudaStream_t s) {
+  if (area) CLASFV_CUDA(cudaMemsetAsync(area, 0, sizeof(int32_t) * t, s));
+  dim3 grid((unsigned)cdiv((int64_t)h * w, 256), (unsigned)t);
+  finalize_mask_kernel<<<grid, 256, 0, s>>>(acc, h * w, mask, area);
   CLASFV_CUDA(cudaGetLastError());
   return CLASFV_OK;
 }

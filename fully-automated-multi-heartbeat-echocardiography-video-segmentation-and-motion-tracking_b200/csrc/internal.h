@@ -114,6 +114,7 @@ int launch_build_shift_clips(const float* video, int t, int h, int w, int clip_l
                              cudaStream_t s);
 int launch_fuse_shift_votes(const void* prob, int dtype, int t, int h, int w, int clip_len, int step, int n_shifts,
                             ShiftTable tab, uint8_t* mask, int32_t* area, cudaStream_t s);
+int launch_finalize_mask(const float* acc, int t, int h, int w, uint8_t* mask, int32_t* area, cudaStream_t s);
 int launch_temporal_resample(const float* in, float* out, int channels, int l_in, int l_out, int64_t hw, cudaStream_t s);
 
 }  // namespace clasfv

@@ -228,6 +228,17 @@ def motion_field(offset, height, width):
     return grid
 
 
+def finalize_mask(acc, want_area=True):
+    """acc (T,2,H,W) fp32 CUDA -> (mask (T,H,W) uint8, area (T,) int32): argmax over the class sums, ties -> 0."""
+    _lib.require_cuda(acc, "acc")
+    t, _, h, w = acc.shape
+    mask = torch.empty((t, h, w), dtype=torch.uint8, device=acc.device)
+    area = torch.empty((t,), dtype=torch.int32, device=acc.device) if want_area else None
+    check(_lib.lib().clasfv_finalize_mask(acc.data_ptr(), t, h, w, mask.data_ptr(), area.data_ptr() if area is not None else None,
+                                          _lib.current_stream_ptr(acc.device)), "clasfv_finalize_mask")
+    return mask, area
+
+
 def temporal_resample(x, out_len):
     """(C,L,H,W) fp32 CUDA -> (C,out_len,H,W), linear, align_corners=False."""
     _lib.require_cuda(x, "x")

@@ -1,0 +1,164 @@
+"""Multi-GPU partitioning of the full-video path.  One process per GPU (torchrun).
+
+* Many videos: independent units - ``shard_videos`` assigns them to ranks, no collective on the data path.
+* One long video: clips are independent, only fusion couples neighbours (output frame g receives votes from
+  clips starting in [g-32, g+1]).  Each rank runs its contiguous range of clips, fuses them into *partial*
+  class sums over the frames they touch, and ``exchange_partials`` adds every rank's overflow frames into
+  the rank that owns them with point-to-point sends (NCCL over NVLink on GPUs; the same code runs on gloo
+  with CPU tensors, which is how tests/ exercise it).  No all-reduce: payload is <= 33 frames per boundary.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+CLIP = 32
+
+
+def shard_videos(lengths, rank, world):
+    """Indices of the videos rank ``rank`` processes: longest-processing-time-first bin packing on the
+    number of clips each video needs (videos differ in length; round-robin would leave ranks idle)."""
+    order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
+    loads = [0] * world
+    mine = []
+    for i in order:
+        r = int(np.argmin(loads))
+        loads[r] += max(1, lengths[i] - CLIP + 1)
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
+def clip_starts_for_video(num_frames, step=1):
+    starts = list(range(0, num_frames - CLIP + 1, step))
+    if starts[-1] != num_frames - CLIP:
+        starts.append(num_frames - CLIP)
+    return starts
+
+
+def partition_clips(n_clips, world):
+    """Contiguous, balanced clip ranges [(c0, c1)] - one per rank (ranks may be empty when world > n_clips)."""
+    base, extra = divmod(n_clips, world)
+    out, c = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((c, c + n))
+        c += n
+    return out
+
+
+def frame_owners(starts, ranges, num_frames):
+    """Output frames [f0, f1) each rank finalises: from its first clip's first frame to the next non-empty
+    rank's first frame; rank 0 starts at frame 0, the last non-empty rank ends at num_frames."""
+    world = len(ranges)
+    firsts = [starts[c0] if c1 > c0 else None for c0, c1 in ranges]
+    owners, nxt = [None] * world, num_frames
+    for r in range(world - 1, -1, -1):
+        if firsts[r] is None:
+            owners[r] = (nxt, nxt)
+        else:
+            owners[r] = (firsts[r], nxt)
+            nxt = firsts[r]
+    for r in range(world):                      # frames before the first clip belong to the first non-empty rank
+        if firsts[r] is not None:
+            owners[r] = (0, owners[r][1])
+            break
+        owners[r] = (0, 0)
+    return owners
+
+
+def touched_window(my_starts, num_frames, edge_hops=False):
+    """Frames [lo, hi) the clips of one rank can vote on."""
+    if not my_starts:
+        return (0, 0)
+    e = 1 if edge_hops else 0
+    return (max(0, my_starts[0] - e), min(num_frames, my_starts[-1] + CLIP + e))
+
+
+def exchange_partials(acc, cnt, window, owners, group=None):
+    """acc (hi-lo, 2, H, W), cnt (hi-lo,) = this rank's partial sums over frames window=[lo,hi).
+    Returns (acc_owned, cnt_owned) over this rank's owned frames with every rank's votes added.
+    The windows of all ranks are all-gathered as 2 integers each; the frame data moves point-to-point."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = window
+    wins = [None] * world
+    dist.all_gather_object(wins, (int(lo), int(hi)), group=group)
+    f0, f1 = owners[rank]
+    h, w = acc.shape[-2:]
+    acc_own = torch.zeros((f1 - f0, 2, h, w), dtype=acc.dtype, device=acc.device)
+    cnt_own = torch.zeros((f1 - f0,), dtype=cnt.dtype, device=cnt.device)
+    a, b = max(lo, f0), min(hi, f1)              # my own contribution
+    if b > a:
+        acc_own[a - f0:b - f0] += acc[a - lo:b - lo]
+        cnt_own[a - f0:b - f0] += cnt[a - lo:b - lo]
+    ops, recv_bufs = [], []
+    for q in range(world):
+        if q == rank:
+            continue
+        qf0, qf1 = owners[q]
+        a, b = max(lo, qf0), min(hi, qf1)        # what I hold of q's frames
+        if b > a:
+            ops.append(dist.P2POp(dist.isend, acc[a - lo:b - lo].contiguous(), q, group))
+            ops.append(dist.P2POp(dist.isend, cnt[a - lo:b - lo].contiguous(), q, group))
+        qlo, qhi = wins[q]
+        a, b = max(qlo, f0), min(qhi, f1)        # what q holds of my frames
+        if b > a:
+            ra = torch.empty((b - a, 2, h, w), dtype=acc.dtype, device=acc.device)
+            rc = torch.empty((b - a,), dtype=cnt.dtype, device=cnt.device)
+            ops.append(dist.P2POp(dist.irecv, ra, q, group))
+            ops.append(dist.P2POp(dist.irecv, rc, q, group))
+            recv_bufs.append((q, a, b, ra, rc))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for _q, a, b, ra, rc in sorted(recv_bufs, key=lambda x: x[0]):   # fixed (rank) order: deterministic sums
+        acc_own[a - f0:b - f0] += ra
+        cnt_own[a - f0:b - f0] += rc
+    return acc_own, cnt_own
+
+
+def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=16, group=None, gather=True):
+    """One long video (3,T,H,W) split by clip range across the ranks of ``group`` (BASELINE config 5).
+    Every rank passes the same video; returns the full (T,H,W) int64 mask on every rank when ``gather``,
+    else (owned mask, (f0, f1))."""
+    from . import engine as _engine
+    from ._lib import OUT_PROB
+    from .src.fuse_utils import _to_device_video, _unwrap
+    net = _unwrap(model)
+    eng = net.engine()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    v = _to_device_video(video, eng.device)
+    num_frames, h, w = int(v.shape[1]), int(v.shape[2]), int(v.shape[3])
+    starts = clip_starts_for_video(num_frames, step)
+    ranges = partition_clips(len(starts), world)
+    owners = frame_owners(starts, ranges, num_frames)
+    c0, c1 = ranges[rank]
+    mine = starts[c0:c1]
+    lo, hi = touched_window(mine, num_frames, edge_hops)
+    out_dtype = torch.float32 if eng.precision == 0 else torch.bfloat16
+    if mine:
+        prob = torch.empty((len(mine), 2, CLIP, h, w), dtype=out_dtype, device=v.device)
+        mot = torch.empty((len(mine), 4, CLIP, h, w), dtype=out_dtype, device=v.device)
+        for b0 in range(0, len(mine), batch_clips):
+            b1 = min(len(mine), b0 + batch_clips)
+            eng.forward_into(v, prob[b0:b1], mot[b0:b1], OUT_PROB, clip_starts=mine[b0:b1], clip_len=CLIP)
+        res = eng.warp_fuse(prob, mot, [s - lo for s in mine], hi - lo, edge_hops=edge_hops, want_mask=False, want_area=False)
+        acc, cnt = res["acc"], res["cnt"]
+    else:
+        acc = torch.zeros((0, 2, h, w), dtype=torch.float32, device=v.device)
+        cnt = torch.zeros((0,), dtype=torch.int32, device=v.device)
+    acc_own, cnt_own = exchange_partials(acc, cnt, (lo, hi), owners, group)
+    f0, f1 = owners[rank]
+    if f1 > f0:
+        mask, _area = _engine.finalize_mask(acc_own.contiguous())
+    else:
+        mask = torch.zeros((0, h, w), dtype=torch.uint8, device=v.device)
+    if not gather:
+        return mask.cpu().numpy().astype(np.int64), (f0, f1)
+    parts = [None] * world
+    dist.all_gather_object(parts, (f0, mask.cpu().numpy()), group=group)
+    full = np.zeros((num_frames, h, w), dtype=np.int64)
+    for pf0, pm in parts:
+        full[pf0:pf0 + pm.shape[0]] = pm
+    return full

@@ -122,6 +122,12 @@ int clasfv_warp_fuse(clasfv_handle* h, const void* prob_dev, const void* motion_
                      int edge_hops, int accumulate, float* acc_dev, int32_t* cnt_dev, uint8_t* mask_dev,
                      int32_t* area_dev, void* stream);
 
+/* mask = argmax over the two class sums of acc_dev (t,2,H,W) (ties -> 0) and its per-frame LV area: the last step
+ * of clasfv_warp_fuse on its own, for sums that were completed by adding other ranks' partial sums
+ * (one long video split by clip range across GPUs). */
+int clasfv_finalize_mask(const float* acc_dev, int t, int height, int width, uint8_t* mask_dev, int32_t* area_dev,
+                         void* stream);
+
 /* ---- reference-exact fusion (F1) ---------------------------------------------------------------
  * Replaces the device-independent body of segment_a_video_with_fusion (src/fuse_utils.py:36-102)
  * and divide_to_consecutive_clips (src/fuse_utils.py:16-33).

@@ -391,3 +391,19 @@ def test_motion_segment_cli_config0(tmp_path, sd):
     assert seg.shape == (128, 112, 112) and seg.dtype == np.int64 and set(np.unique(seg)) <= {0, 1}
     r2 = subprocess.run([sys.executable, cli, "-p", str(avi), "-m", str(ckpt), "-d", "cpu"], capture_output=True, text=True, timeout=120)
     assert r2.returncode != 0 and "no CPU path" in (r2.stderr + r2.stdout)
+
+
+# ------------------------------------------------------------------------------------------ multi-GPU path, 1 rank
+def test_long_video_split_single_rank_equals_direct(net_fp32):
+    import torch.distributed as dist
+    from clasfv_b200 import sharding
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29611")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        video = synthetic.synthetic_echo_video(50, 32, 32, seed=9)
+        a = sharding.segment_long_video(video, net_fp32, step=1)
+        b = fuse_utils.segment_a_video_with_fusion(video, net_fp32, fuse_method="warp")
+        assert a.dtype == np.int64 and np.array_equal(a, b)
+    finally:
+        dist.destroy_process_group()
