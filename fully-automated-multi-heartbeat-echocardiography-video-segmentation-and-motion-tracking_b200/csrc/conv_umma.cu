@@ -13,11 +13,11 @@
 // by the tap's parity and whose strides are multiplied by the conv stride), so they are plain box loads
 // too.  Both operands land in the canonical K-major SWIZZLE_128B layout that tcgen05 consumes directly.
 //
-// Warp roles (192 threads, persistent over tiles, one CTA per SM):
+// Warp roles (320 threads, persistent over tiles, one CTA per SM):
 //   warp 0    TMA producer         : NSTAGE-deep ring of {A slab, B slab}, mbarrier full/empty
 //   warp 1    MMA issuer           : one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x <=4 per slab,
 //                                    tcgen05.commit releases the slab / publishes the accumulator
-//   warps 2-5 epilogue             : tcgen05.ld the fp32 accumulator (lane = row), + folded-BN bias,
+//   warps 2-9 epilogue             : tcgen05.ld the fp32 accumulator (lane = row), + folded-BN bias,
 //                                    + residual, ReLU, convert, store channels-last
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
@@ -37,7 +37,8 @@ using namespace ptx;
 constexpr int TILE_M = 128;
 constexpr int SLAB_K = 64;          // channels per K slab (128 bytes of bf16 = one swizzle row)
 constexpr int UMMA_K = 16;
-constexpr int UMMA_THREADS = 192;
+constexpr int UMMA_THREADS = 320;         // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
 constexpr int MAX_TAPS = 27;
 constexpr int MAX_VIEWS = 4;
 constexpr int SMEM_BUDGET = 222 * 1024;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
     for (int v = 0; v < MAX_VIEWS; ++v) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a[v]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
     for (int s = 0; s < p.nstages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
     mbar_init(wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -188,8 +189,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // the two warps of a quarter take alternate 16-column chunks
     const int row = q * 32 + lane;
     const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
     int it = 0;
@@ -226,13 +228,14 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
           res_bf[0] = __ldg(rp); res_bf[1] = __ldg(rp + 1);
         }
       };
-      fetch_res(0);
+      const int cc0 = half * 16;
+      if (cc0 < ncols) fetch_res(cc0);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.bn);
       uint32_t acc[16];
-      tc_ld16(taddr, acc);
-      for (int cc = 0; cc < ncols; cc += 16) {
+      if (cc0 < ncols) tc_ld16(taddr + (uint32_t)cc0, acc);
+      for (int cc = cc0; cc < ncols; cc += 32) {
         tc_wait_ld();
         float v[16];
 #pragma unroll
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
           v[4 * i] = __uint_as_float(acc[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b4.y;
           v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4.w;
         }
-        if (cc + 16 < ncols) tc_ld16(taddr + (uint32_t)(cc + 16), acc);      // next chunk's accumulators in flight
+        if (cc + 32 < ncols) tc_ld16(taddr + (uint32_t)(cc + 32), acc);      // next chunk's accumulators in flight
         if (has_res) {
           if (p.out_f32) {
 #pragma unroll
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
               for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hh[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
             }
           }
-          if (cc + 16 < ncols) fetch_res(cc + 16);
+          if (cc + 32 < ncols) fetch_res(cc + 32);
         }
         if (p.relu) {
 #pragma unroll
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));   // 4 arrivals (one per epilogue warp) free the accumulator
+      if (lane == 0) mbar_arrive(tempty_bar(as));   // 8 arrivals (one per epilogue warp) free the accumulator
     }
   }
 

@@ -51,6 +51,25 @@ __device__ __forceinline__ Bilinear bilinear_setup(int i, int j, float fx, float
   return b;
 }
 
+// same, with the base grid coordinates (linspace values of the pixel) already known
+__device__ __forceinline__ Bilinear bilinear_setup_base(float bx, float by, float fx, float fy, int h, int w) {
+  const float gx = bx + fx, gy = by + fy;
+  float ix = ((gx + 1.f) * (float)w - 1.f) * 0.5f;
+  float iy = ((gy + 1.f) * (float)h - 1.f) * 0.5f;
+  ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
+  iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  Bilinear b;
+  b.x0 = (int)fx0; b.y0 = (int)fy0;
+  const float x1 = fx0 + 1.f, y1 = fy0 + 1.f;
+  b.nw = (x1 - ix) * (y1 - iy);
+  b.ne = (ix - fx0) * (y1 - iy);
+  b.sw = (x1 - ix) * (iy - fy0);
+  b.se = (ix - fx0) * (iy - fy0);
+  b.x1ok = b.x0 + 1 < w; b.y1ok = b.y0 + 1 < h;
+  return b;
+}
+
 template <typename T>
 __device__ __forceinline__ float bilinear_fetch(const T* __restrict__ plane, const Bilinear& b, int w) {
   const T* p = plane + (int64_t)b.y0 * w + b.x0;
@@ -95,6 +114,7 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
   const int hw = a.h * a.w;
   const bool valid = pix < hw;
   const int i = valid ? pix / a.w : 0, j = valid ? pix % a.w : 0;
+  const float base_x = linspace_pm1(j, a.w), base_y = linspace_pm1(i, a.h);
   const int L = a.clip_len;
   const T* __restrict__ prob = static_cast<const T*>(a.prob);
   const T* __restrict__ mot = static_cast<const T*>(a.motion);
@@ -116,7 +136,7 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
       ++votes;
       if (valid) {
         const float fx = ldf<T>(mc + (int64_t)ts * hw + pix), fy = ldf<T>(mc + (int64_t)(L + ts) * hw + pix);
-        const Bilinear b = bilinear_setup(i, j, fx, fy, a.h, a.w);
+        const Bilinear b = bilinear_setup_base(base_x, base_y, fx, fy, a.h, a.w);
         a0 += bilinear_fetch<T>(pc + (int64_t)ts * hw, b, a.w);
         a1 += bilinear_fetch<T>(pc + (int64_t)(L + ts) * hw, b, a.w);
       }
@@ -126,7 +146,7 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
       ++votes;
       if (valid) {
         const float fx = ldf<T>(mc + (int64_t)(2 * L + ts) * hw + pix), fy = ldf<T>(mc + (int64_t)(3 * L + ts) * hw + pix);
-        const Bilinear b = bilinear_setup(i, j, fx, fy, a.h, a.w);
+        const Bilinear b = bilinear_setup_base(base_x, base_y, fx, fy, a.h, a.w);
         a0 += bilinear_fetch<T>(pc + (int64_t)ts * hw, b, a.w);
         a1 += bilinear_fetch<T>(pc + (int64_t)(L + ts) * hw, b, a.w);
       }
