@@ -23,6 +23,7 @@ EXPORTS = (
     "clasfv_finalize", "clasfv_forward", "clasfv_workspace_bytes", "clasfv_warp", "clasfv_motion_field",
     "clasfv_warp_fuse", "clasfv_build_shift_clips", "clasfv_fuse_shift_votes", "clasfv_temporal_resample",
     "clasfv_conv3d", "clasfv_profile_begin", "clasfv_profile_end", "clasfv_finalize_mask",
+    "clasfv_set_option", "clasfv_profile_gflop",
 )
 
 
@@ -77,13 +78,13 @@ def lib():
         l.clasfv_finalize_mask.argtypes = [vp, i32, i32, i32, vp, vp, vp]
         l.clasfv_profile_begin.argtypes = [vp]
         l.clasfv_profile_end.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+        l.clasfv_profile_gflop.argtypes = [vp, C.POINTER(C.c_double)]
+        l.clasfv_set_option.argtypes = [vp, C.c_char_p, i32]
         l.clasfv_temporal_resample.argtypes = [vp, vp, i32, i32, i32, i64, vp]
         l.clasfv_conv3d.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32,
                                     i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp]
         for name in EXPORTS:
-            fn = getattr(l, name)
-            if fn.restype is C.c_int and name not in ("clasfv_abi_version",):
-                pass
+            getattr(l, name)                  # every declared symbol must resolve
         _lib = l
         return _lib
 

@@ -92,10 +92,18 @@ struct clasfv_handle {
   // workspace
   void* ws = nullptr; size_t ws_bytes = 0;
   TableRing ring;
-  // optional stage profiler: 5 events per forward call (start, stem, trunk, laterals, head)
+  // optional stage profiler: an event after every stage of every (sub-)batch; the time since the previous event
+  // of the same call is attributed to that stage.  prof_gflop counts the MACs the convolutions really performed.
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
+  std::vector<int> prof_stage;
+  size_t prof_used = 0;
   int prof_calls = 0;
+  int cur_stage = 0;
+  double prof_gflop[4] = {0, 0, 0, 0};
+  // options (clasfv_set_option)
+  int sub_batch = 16;          // clips per internal batch of clasfv_forward
+  bool dense_video = true;     // share layer-1 work between overlapping windows of one video (bf16 tensor-core path)
 };
 
 namespace {
@@ -197,19 +205,305 @@ int ensure_workspace(clasfv_handle* h, size_t bytes) {
 ConvArgs make_conv(const PackedConv& pc, int n, int ti, int hi, int wi, const void* in, void* out, const void* residual, int relu,
                    int act_dtype, int out_f32) {
   ConvArgs a;
+  memset(&a, 0, sizeof(a));
   ConvShape& s = a.s;
   s.n = n; s.ti = ti; s.hi = hi; s.wi = wi; s.cin = pc.cin_pad; s.cout = pc.cout_pad;
   s.kt = pc.kt; s.kh = pc.kh; s.kw = pc.kw; s.st = pc.st; s.sh = pc.sh; s.sw = pc.sw; s.pt = pc.pt; s.ph = pc.ph; s.pw = pc.pw;
   s.to = (ti + 2 * pc.pt - pc.kt) / pc.st + 1; s.ho = (hi + 2 * pc.ph - pc.kh) / pc.sh + 1; s.wo = (wi + 2 * pc.pw - pc.kw) / pc.sw + 1;
   a.in = in; a.in2 = nullptr; a.in_batch_stride = 0; a.weight = pc.w; a.bias = pc.bias; a.residual = residual; a.out = out;
   a.act_dtype = act_dtype; a.out_f32 = out_f32; a.relu = relu;
+  a.macs_per_pos = (double)pc.cin * pc.cout * pc.kt * pc.kh * pc.kw;
   return a;
 }
 
 int run_conv(clasfv_handle* h, const ConvArgs& a, cudaStream_t stream) {
+  if (h->profiling) h->prof_gflop[h->cur_stage] += 2e-9 * a.macs_per_pos * (double)a.s.n * a.s.to * a.s.ho * a.s.wo;
   if (a.act_dtype == CLASFV_BF16 && !h->force_simt) return launch_conv_umma(a, h->num_sms, stream);
   return launch_conv_simt(a, stream);
 }
+
+
+// ------------------------------------------------------------------------------------------- forward
+// One clasfv_forward call.  The clips are processed in internal batches of h->sub_batch.  Two schedules:
+//
+//  per-clip   every clip runs the whole trunk (any input layout; fp32 mode; short batches).
+//
+//  dense video (bf16 tensor-core path, clips = equally spaced windows of one resident video)
+//             Through the stem and layer1 the network has seen only 5 temporal 3x1x1 convolutions, so frame
+//             j of a clip depends on the clip's zero padding only if j < 5 or j > T-6.  All other frames are the
+//             same numbers in every window that contains them.  They are computed ONCE over the union of the
+//             frames ("video-level" maps V_d / VS_d after the d-th temporal convolution / the spatial convolution
+//             before it), and per clip only the d frames next to each clip edge are recomputed at depth d, the
+//             temporal convolutions reading a virtual clip spliced from the clip's edge frames and the shared
+//             video-level frames (ConvArgs::TimeSeg / ResSeg).  Layer1 is 55 % of the trunk's FLOPs; for stride-1
+//             windows this does 21 % of them.  Results are bit-identical to the per-clip schedule (same kernel,
+//             same K order per output element).
+struct Forward {
+  clasfv_handle* h; cudaStream_t stream;
+  const float* x; const int64_t* offs_host; int64_t channel_stride;
+  int n, t, height, width, out_kind, out_dtype;
+  char* seg; char* motion;
+  // derived
+  int act; size_t es; bool tc_head; size_t gs;
+  int T[5], H[5], W[5], C[5];
+  char* ws = nullptr;
+  size_t o_s0, o_f[5], o_mid, o_ta, o_x1, o_ds, o_g[4];
+  size_t total = 0;
+  size_t region(size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; }
+
+  int mark(int stage) {
+    h->cur_stage = stage < 0 ? 0 : (stage + 1 < 4 ? stage + 1 : 3);
+    if (!h->profiling) return CLASFV_OK;
+    if (h->prof_events.size() <= h->prof_used) {
+      cudaEvent_t ev;
+      CLASFV_CUDA(cudaEventCreate(&ev));
+      h->prof_events.push_back(ev);
+    }
+    CLASFV_CUDA(cudaEventRecord(h->prof_events[h->prof_used], stream));
+    h->prof_stage.push_back(stage);
+    ++h->prof_used;
+    return CLASFV_OK;
+  }
+  void set_stage(int stage) { h->cur_stage = stage; }
+
+  void carve_batch(int nb, bool dense) {
+    int64_t P[5];
+    for (int i = 0; i < 5; ++i) P[i] = (int64_t)nb * T[i] * H[i] * W[i];
+    int64_t mid_elems = 0;
+    for (int l = dense ? 1 : 0; l < 4; ++l)
+      for (int b = 0; b < 2; ++b) {
+        const Block& blk = h->blocks[l][b];
+        // s1 output lives at the block input's temporal extent and the block output's spatial extent
+        const int64_t e1 = (int64_t)nb * (b == 0 ? T[l] : T[l + 1]) * H[l + 1] * W[l + 1] * blk.s1.cout_pad;
+        const int64_t e2 = P[l + 1] * blk.s2.cout_pad;
+        mid_elems = std::max(mid_elems, std::max(e1, e2));
+      }
+    o_s0 = dense ? 0 : region(P[0] * STEM_MID_PAD * es);
+    for (int i = 0; i < 5; ++i) o_f[i] = region(P[i] * C[i] * es);
+    o_mid = region(mid_elems * es);
+    o_ta = region(P[dense ? 2 : 1] * (dense ? 128 : 64) * es);
+    o_x1 = region(P[dense ? 2 : 1] * (dense ? 128 : 64) * es);
+    o_ds = region(P[2] * 128 * es);
+    for (int i = 0; i < 4; ++i) o_g[i] = region(P[i + 1] * DEC * gs);
+  }
+
+  // one residual block on a batch of nb clips
+  int run_block(const Block& blk, int nb, const void* in, int ti, int hi, int wi, void* out, int* to, int* ho, int* wo) {
+    int rc;
+    ConvArgs c1 = make_conv(blk.s1, nb, ti, hi, wi, in, ws + o_mid, nullptr, 1, act, 0);
+    if ((rc = run_conv(h, c1, stream))) return rc;
+    ConvArgs c2 = make_conv(blk.t1, nb, c1.s.to, c1.s.ho, c1.s.wo, ws + o_mid, ws + o_ta, nullptr, 1, act, 0);
+    if ((rc = run_conv(h, c2, stream))) return rc;
+    ConvArgs c3 = make_conv(blk.s2, nb, c2.s.to, c2.s.ho, c2.s.wo, ws + o_ta, ws + o_mid, nullptr, 1, act, 0);
+    if ((rc = run_conv(h, c3, stream))) return rc;
+    const void* res = in;
+    if (blk.has_down) {
+      if ((rc = run_conv(h, make_conv(blk.down, nb, ti, hi, wi, in, ws + o_ds, nullptr, 0, act, 0), stream))) return rc;
+      res = ws + o_ds;
+    }
+    ConvArgs c4 = make_conv(blk.t2, nb, c3.s.to, c3.s.ho, c3.s.wo, ws + o_mid, out, res, 1, act, 0);
+    if ((rc = run_conv(h, c4, stream))) return rc;
+    *to = c4.s.to; *ho = c4.s.ho; *wo = c4.s.wo;
+    return CLASFV_OK;
+  }
+
+  // layers first_layer..4, lateral projections and the head, for a batch whose f[0] (and f[1] if first_layer == 1) are in place
+  int run_tail(int nb, int c0, int first_layer) {
+    int rc;
+    for (int l = first_layer; l < 4; ++l) {
+      const void* in = ws + o_f[l];
+      int ti = T[l], hi = H[l], wi = W[l];
+      for (int b = 0; b < 2; ++b) {
+        void* out = b == 0 ? (void*)(ws + o_x1) : (void*)(ws + o_f[l + 1]);
+        if ((rc = run_block(h->blocks[l][b], nb, in, ti, hi, wi, out, &ti, &hi, &wi))) return rc;
+        in = out;
+      }
+    }
+    if ((rc = mark(1))) return rc;
+    // decoder: lateral projections at native resolution, stem + layer1 share one map
+    {
+      ConvArgs c = make_conv(h->lateral[0], nb, T[0], H[0], W[0], ws + o_f[0], ws + o_g[0], nullptr, 0, act, tc_head ? 0 : 1);
+      c.in2 = ws + o_f[1];
+      c.macs_per_pos *= 2;
+      if ((rc = run_conv(h, c, stream))) return rc;
+    }
+    for (int i = 2; i < 5; ++i)
+      if ((rc = run_conv(h, make_conv(h->lateral[i], nb, T[i], H[i], W[i], ws + o_f[i], ws + o_g[i - 1], nullptr, 0, act, tc_head ? 0 : 1), stream))) return rc;
+    if ((rc = mark(2))) return rc;
+    HeadArgs ha;
+    for (int i = 0; i < 4; ++i) { ha.g[i] = ws + o_g[i]; ha.tl[i] = T[i + 1]; ha.hl[i] = H[i + 1]; ha.wl[i] = W[i + 1]; }
+    ha.g_dtype = tc_head ? CLASFV_BF16 : CLASFV_F32;
+    ha.n = nb; ha.t = t; ha.h = height; ha.w = width;
+    ha.b1 = h->b1; ha.w2 = h->w2; ha.w2_bf16 = h->w2_bf16; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;
+    const size_t oes = out_dtype == CLASFV_F32 ? 4 : 2;
+    const size_t plane = (size_t)t * height * width * oes;
+    ha.seg = seg + (size_t)c0 * 2 * plane; ha.motion = motion + (size_t)c0 * 4 * plane;
+    ha.out_dtype = out_dtype; ha.out_kind = out_kind;
+    if ((rc = tc_head ? launch_head_umma(ha, stream) : launch_head(ha, stream))) return rc;
+    return mark(3);
+  }
+
+  int run() {
+    act = h->precision; es = act == CLASFV_F32 ? 4 : 2;
+    tc_head = act == CLASFV_BF16 && !h->force_simt;     // tensor-core head reads bf16 lateral maps
+    gs = tc_head ? 2 : 4;
+    const int Tn[5] = {t, t, t / 2, t / 4, t / 8};
+    const int Hn[5] = {height / 2, height / 2, height / 4, height / 8, height / 16};
+    const int Wn[5] = {width / 2, width / 2, width / 4, width / 8, width / 16};
+    const int Cn[5] = {64, 64, 128, 256, 512};
+    for (int i = 0; i < 5; ++i) { T[i] = Tn[i]; H[i] = Hn[i]; W[i] = Wn[i]; C[i] = Cn[i]; }
+    // equally spaced windows of one resident video?
+    int64_t frame_step = 0;
+    if (offs_host && n >= 2) {
+      const int64_t d = offs_host[1] - offs_host[0], hw = (int64_t)height * width;
+      bool uniform = d > 0 && d % hw == 0 && d / hw < t;
+      for (int i = 2; i < n && uniform; ++i) uniform = offs_host[i] - offs_host[i - 1] == d;
+      if (uniform) frame_step = d / hw;
+    }
+    const bool dense = h->dense_video && tc_head && frame_step >= 1 && frame_step <= 8 && n >= 4 && t >= 16;
+    return dense ? run_dense((int)frame_step) : run_per_clip(frame_step);
+  }
+
+  // ------------------------------------------------------------------ per-clip schedule
+  int run_per_clip(int64_t frame_step) {
+    const int nbmax = std::min(n, h->sub_batch);
+    total = 0;
+    carve_batch(nbmax, false);
+    int rc;
+    if ((rc = ensure_workspace(h, total))) return rc;
+    ws = static_cast<char*>(h->ws);
+    const int64_t thw = (int64_t)t * height * width;
+    for (int c0 = 0; c0 < n; c0 += nbmax) {
+      const int nb = std::min(nbmax, n - c0);
+      void* offs_dev = nullptr;
+      rc = h->ring.upload((size_t)nb * sizeof(int64_t), stream, [&](char* dst) {
+        int64_t* o = reinterpret_cast<int64_t*>(dst);
+        for (int i = 0; i < nb; ++i) o[i] = offs_host ? offs_host[c0 + i] : (int64_t)(c0 + i) * 3 * thw;
+      }, &offs_dev);
+      if (rc) return rc;
+      if ((rc = mark(-1))) return rc;
+      // The 1x7x7 stem convolution is per frame, so equally spaced windows of one video share it: it runs once
+      // over the union of their frames and the 3x1x1 convolution that follows reads overlapping windows of that map
+      // (clip-edge zero padding comes from the window extent).
+      const int64_t fs = nb >= 2 ? frame_step : 0;
+      StemArgs sa;
+      sa.x = x; sa.clip_offset = static_cast<const int64_t*>(offs_dev); sa.channel_stride = channel_stride;
+      sa.n = nb; sa.t = t; sa.h = height; sa.w = width; sa.weight = h->stem_w; sa.bias = h->stem_b; sa.out = ws + o_s0; sa.out_channels = STEM_MID_PAD; sa.out_dtype = act;
+      if (fs) { sa.n = 1; sa.t = (int)((nb - 1) * fs + t); }
+      if ((rc = launch_stem(sa, stream))) return rc;
+      if ((rc = mark(0))) return rc;
+      {
+        ConvArgs c = make_conv(h->stem_t, nb, T[0], H[0], W[0], ws + o_s0, ws + o_f[0], nullptr, 1, act, 0);
+        if (fs) c.in_batch_stride = fs * (int64_t)H[0] * W[0] * STEM_MID_PAD;
+        if ((rc = run_conv(h, c, stream))) return rc;
+      }
+      if ((rc = run_tail(nb, c0, 0))) return rc;
+    }
+    if (h->profiling) ++h->prof_calls;
+    return CLASFV_OK;
+  }
+
+  // ------------------------------------------------------------------ dense-video schedule
+  int run_dense(int fs) {
+    const int nbmax = std::min(n, h->sub_batch);
+    const int tv = (n - 1) * fs + t;                       // frames of the video this call touches
+    const int64_t FE = (int64_t)H[0] * W[0];
+    const int midc = h->blocks[0][0].s1.cout_pad;          // 144
+    const int64_t F64 = FE * 64, FM = FE * midc;           // elements per frame
+    const int D = 5;                                       // temporal convolutions through the stem and layer1
+    total = 0;
+    const size_t o_s0v = region((size_t)tv * FE * STEM_MID_PAD * es);
+    size_t o_v[6], o_vs[6];                                // V_d (d = 1..5), VS_d (d = 2..5); V_2 and V_4 share a buffer
+    o_v[1] = region((size_t)tv * F64 * es); o_v[3] = region((size_t)tv * F64 * es); o_v[5] = region((size_t)tv * F64 * es);
+    o_v[2] = o_v[4] = region((size_t)tv * F64 * es);
+    for (int d = 2; d <= D; ++d) o_vs[d] = region((size_t)tv * FM * es);
+    size_t o_e[6];
+    for (int d = 1; d < D; ++d) o_e[d] = region((size_t)nbmax * 2 * d * F64 * es);
+    const size_t o_es = region((size_t)nbmax * 2 * (D - 1) * FM * es);
+    carve_batch(nbmax, true);
+    int rc;
+    if ((rc = ensure_workspace(h, total))) return rc;
+    ws = static_cast<char*>(h->ws);
+
+    // ---- video level: stem and layer1 once over the tv frames, as one long clip
+    void* offs_dev = nullptr;
+    rc = h->ring.upload(sizeof(int64_t), stream, [&](char* dst) { *reinterpret_cast<int64_t*>(dst) = offs_host[0]; }, &offs_dev);
+    if (rc) return rc;
+    if ((rc = mark(-1))) return rc;
+    StemArgs sa;
+    sa.x = x; sa.clip_offset = static_cast<const int64_t*>(offs_dev); sa.channel_stride = channel_stride;
+    sa.n = 1; sa.t = tv; sa.h = height; sa.w = width; sa.weight = h->stem_w; sa.bias = h->stem_b; sa.out = ws + o_s0v; sa.out_channels = STEM_MID_PAD; sa.out_dtype = act;
+    if ((rc = launch_stem(sa, stream))) return rc;
+    if ((rc = mark(0))) return rc;
+    const PackedConv* spat[6] = {nullptr, nullptr, &h->blocks[0][0].s1, &h->blocks[0][0].s2, &h->blocks[0][1].s1, &h->blocks[0][1].s2};
+    const PackedConv* temp[6] = {nullptr, &h->stem_t, &h->blocks[0][0].t1, &h->blocks[0][0].t2, &h->blocks[0][1].t1, &h->blocks[0][1].t2};
+    if ((rc = run_conv(h, make_conv(*temp[1], 1, tv, H[0], W[0], ws + o_s0v, ws + o_v[1], nullptr, 1, act, 0), stream))) return rc;
+    for (int d = 2; d <= D; ++d) {
+      if ((rc = run_conv(h, make_conv(*spat[d], 1, tv, H[0], W[0], ws + o_v[d - 1], ws + o_vs[d], nullptr, 1, act, 0), stream))) return rc;
+      const void* res = (d == 3 || d == 5) ? ws + o_v[d - 2] : nullptr;
+      if ((rc = run_conv(h, make_conv(*temp[d], 1, tv, H[0], W[0], ws + o_vs[d], ws + o_v[d], res, 1, act, 0), stream))) return rc;
+    }
+    if ((rc = mark(1))) return rc;
+
+    // ---- per batch of clips: edge frames of layer1, assembly, layers 2-4, decoder
+    for (int c0 = 0; c0 < n; c0 += nbmax) {
+      const int nb = std::min(nbmax, n - c0);
+      if ((rc = mark(-1))) return rc;
+      set_stage(1);
+      // clip window views of the video-level maps: clip i of the batch starts at frame (c0 + i) * fs
+      auto vview = [&](size_t off, int64_t frame_elems) { return ws + off + (size_t)c0 * fs * frame_elems * es; };
+      for (int d = 1; d <= D; ++d) {
+        const int64_t fin = d == 1 ? FE * STEM_MID_PAD : FM;             // input frame (elements)
+        char* e_out = d == D ? ws + o_f[1] : ws + o_e[d];
+        const int64_t e_bstride = d == D ? (int64_t)t * F64 : (int64_t)2 * d * F64;
+        const int e_right = d == D ? t - d : d;                            // first right-edge frame in e_out
+        if (d >= 2 &&
+            (rc = run_conv(h, make_conv(*spat[d], nb, 2 * (d - 1), H[0], W[0], ws + o_e[d - 1], ws + o_es, nullptr, 1, act, 0), stream))) return rc;
+        const char* vsrc = d == 1 ? vview(o_s0v, fin) : vview(o_vs[d], fin);
+        const int r = d - 2;                                               // depth of the block input (residual)
+        const bool has_res = d == 3 || d == 5;
+        // left edge: output frames 0..d-1; virtual input = [edge frames 0..d-2 | video frames d-1, d]
+        {
+          ConvArgs c = make_conv(*temp[d], nb, d, H[0], W[0], d == 1 ? (const void*)vsrc : (const void*)(ws + o_es), e_out, nullptr, 1, act, 0);
+          c.out_batch_stride = e_bstride;
+          c.seg.on = 1; c.seg.to = d; c.seg.split = d - 1;
+          c.seg.a_t = d == 1 ? t : d - 1; c.seg.a_toff = 0; c.in_batch_stride = d == 1 ? fs * fin : (int64_t)2 * (d - 1) * fin;
+          c.seg.b = vsrc; c.seg.b_t = t; c.seg.b_toff = 0; c.seg.b_batch_stride = fs * fin;
+          if (has_res) {
+            c.residual = ws + o_e[r]; c.res.on = 1; c.res.split = r; c.res.a_toff = 0; c.res.a_batch_stride = (int64_t)2 * r * F64;
+            c.res.b = vview(o_v[r], F64); c.res.b_toff = 0; c.res.b_batch_stride = fs * F64;
+          }
+          if ((rc = run_conv(h, c, stream))) return rc;
+        }
+        // right edge: output frames t-d..t-1; virtual input = [video frames t-d-1, t-d | edge frames t-d+1..t-1]
+        {
+          ConvArgs c = make_conv(*temp[d], nb, d, H[0], W[0], vsrc, e_out + (size_t)e_right * F64 * es, nullptr, 1, act, 0);
+          c.out_batch_stride = e_bstride;
+          c.seg.on = 1; c.seg.to = d; c.seg.split = 1;
+          c.seg.a_t = t; c.seg.a_toff = t - d; c.in_batch_stride = fs * fin;
+          if (d == 1) { c.seg.b = vsrc; c.seg.b_t = t; c.seg.b_toff = t - d; c.seg.b_batch_stride = fs * fin; }
+          else { c.seg.b = ws + o_es + (size_t)(d - 1) * fin * es; c.seg.b_t = d - 1; c.seg.b_toff = -1; c.seg.b_batch_stride = (int64_t)2 * (d - 1) * fin; }
+          if (has_res) {
+            c.residual = vview(o_v[r], F64); c.res.on = 1; c.res.split = 2; c.res.a_toff = t - d; c.res.a_batch_stride = fs * F64;
+            c.res.b = ws + o_e[r] + (size_t)r * F64 * es; c.res.b_toff = -2; c.res.b_batch_stride = (int64_t)2 * r * F64;
+          }
+          if ((rc = run_conv(h, c, stream))) return rc;
+        }
+      }
+      // assemble the per-clip stem output (lateral projection input) and the interior of the layer1 output
+      {
+        const int64_t fb = F64 * (int64_t)es;
+        FrameGatherSeg s0[3] = {{ws + o_e[1], 2 * fb, 0, 0, 1}, {vview(o_v[1], F64), fs * fb, 1, 1, t - 2}, {ws + o_e[1], 2 * fb, 1, t - 1, 1}};
+        if ((rc = launch_frame_gather(ws + o_f[0], (int64_t)t * fb, nb, fb, s0, 3, stream))) return rc;
+        FrameGatherSeg s1[1] = {{vview(o_v[D], F64), fs * fb, D, D, t - 2 * D}};
+        if ((rc = launch_frame_gather(ws + o_f[1], (int64_t)t * fb, nb, fb, s1, 1, stream))) return rc;
+      }
+      if ((rc = run_tail(nb, c0, 1))) return rc;
+    }
+    if (h->profiling) ++h->prof_calls;
+    return CLASFV_OK;
+  }
+};
 
 }  // namespace
 
@@ -392,135 +686,32 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
   CLASFV_REQUIRE(out_kind == CLASFV_OUT_LOGITS || out_kind == CLASFV_OUT_PROB, "clasfv_forward: bad out_kind");
   CLASFV_REQUIRE(out_dtype == CLASFV_F32 || out_dtype == CLASFV_BF16, "clasfv_forward: bad out_dtype");
   DeviceGuard guard(h->device);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const int act = h->precision;
-  const size_t es = act == CLASFV_F32 ? 4 : 2;
+  Forward f;
+  f.h = h; f.stream = static_cast<cudaStream_t>(stream_v);
+  f.x = x_dev; f.offs_host = clip_offset_host; f.n = n; f.t = t; f.height = height; f.width = width;
+  f.out_kind = out_kind; f.out_dtype = out_dtype; f.seg = static_cast<char*>(seg_dev); f.motion = static_cast<char*>(motion_dev);
   const int64_t thw = (int64_t)t * height * width;
   if (!clip_offset_host) {
     CLASFV_REQUIRE(channel_stride == 0 || channel_stride == thw, "clasfv_forward: dense input needs channel_stride == T*H*W");
     channel_stride = thw;
   }
-  // ---- geometry of the four resolutions
-  const int T[5] = {t, t, t / 2, t / 4, t / 8};
-  const int H[5] = {height / 2, height / 2, height / 4, height / 8, height / 16};
-  const int W[5] = {width / 2, width / 2, width / 4, width / 8, width / 16};
-  const int C[5] = {64, 64, 128, 256, 512};
-  int64_t P[5];
-  for (int i = 0; i < 5; ++i) P[i] = (int64_t)n * T[i] * H[i] * W[i];
-  // ---- workspace carve-up (256-byte aligned regions)
-  size_t total = 0;
-  auto region = [&](size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; };
-  int64_t mid_elems = 0;
-  for (int l = 0; l < 4; ++l)
-    for (int b = 0; b < 2; ++b) {
-      const Block& blk = h->blocks[l][b];
-      // s1 output lives at the block input's temporal extent and the block output's spatial extent
-      const int64_t e1 = (int64_t)n * (b == 0 ? T[l] : T[l + 1]) * H[l + 1] * W[l + 1] * blk.s1.cout_pad;
-      const int64_t e2 = P[l + 1] * blk.s2.cout_pad;
-      mid_elems = std::max(mid_elems, std::max(e1, e2));
-    }
-  const size_t o_s0 = region(P[0] * STEM_MID_PAD * es);
-  size_t o_f[5];
-  for (int i = 0; i < 5; ++i) o_f[i] = region(P[i] * C[i] * es);
-  const size_t o_mid = region(mid_elems * es);
-  const size_t o_ta = region(P[1] * 64 * es);
-  const size_t o_x1 = region(P[1] * 64 * es);
-  const size_t o_ds = region(P[2] * 128 * es);
-  const bool tc_head = act == CLASFV_BF16 && !h->force_simt;     // tensor-core head reads bf16 lateral maps
-  const size_t gs = tc_head ? 2 : 4;
-  size_t o_g[4];
-  for (int i = 0; i < 4; ++i) o_g[i] = region(P[i + 1] * DEC * gs);
-  int rc;
-  if ((rc = ensure_workspace(h, total))) return rc;
-  char* ws = static_cast<char*>(h->ws);
-  // ---- clip offsets
-  void* offs_dev = nullptr;
-  rc = h->ring.upload((size_t)n * sizeof(int64_t), stream, [&](char* dst) {
-    int64_t* o = reinterpret_cast<int64_t*>(dst);
-    for (int i = 0; i < n; ++i) o[i] = clip_offset_host ? clip_offset_host[i] : (int64_t)i * 3 * thw;
-  }, &offs_dev);
-  if (rc) return rc;
-  auto mark = [&](int stage) -> int {
-    if (!h->profiling) return CLASFV_OK;
-    const size_t idx = (size_t)h->prof_calls * 5 + stage;
-    while (h->prof_events.size() <= idx) {
-      cudaEvent_t ev;
-      CLASFV_CUDA(cudaEventCreate(&ev));
-      h->prof_events.push_back(ev);
-    }
-    CLASFV_CUDA(cudaEventRecord(h->prof_events[idx], stream));
-    return CLASFV_OK;
-  };
-  if ((rc = mark(0))) return rc;
-  // ---- stem.  The 1x7x7 convolution is per frame, so clips that are equally spaced windows of one
-  // resident video share it: it runs once over the union of their frames and the 3x1x1 convolution that
-  // follows reads overlapping windows of that map (clip-edge zero padding comes from the window extent).
-  int64_t frame_step = 0;     // > 0: shared-stem mode, clips start every frame_step frames
-  if (clip_offset_host && n >= 2) {
-    const int64_t d = clip_offset_host[1] - clip_offset_host[0], hw = (int64_t)height * width;
-    bool uniform = d > 0 && d % hw == 0 && d / hw < t;
-    for (int i = 2; i < n && uniform; ++i) uniform = clip_offset_host[i] - clip_offset_host[i - 1] == d;
-    if (uniform) frame_step = d / hw;
-  }
-  StemArgs sa;
-  sa.x = x_dev; sa.clip_offset = static_cast<const int64_t*>(offs_dev); sa.channel_stride = channel_stride;
-  sa.n = n; sa.t = t; sa.h = height; sa.w = width; sa.weight = h->stem_w; sa.bias = h->stem_b; sa.out = ws + o_s0; sa.out_channels = STEM_MID_PAD; sa.out_dtype = act;
-  if (frame_step) { sa.n = 1; sa.t = (int)((n - 1) * frame_step + t); }
-  if ((rc = launch_stem(sa, stream))) return rc;
-  if ((rc = mark(1))) return rc;
-  {
-    ConvArgs c = make_conv(h->stem_t, n, T[0], H[0], W[0], ws + o_s0, ws + o_f[0], nullptr, 1, act, 0);
-    if (frame_step) c.in_batch_stride = frame_step * (int64_t)H[0] * W[0] * STEM_MID_PAD;
-    if ((rc = run_conv(h, c, stream))) return rc;
-  }
-  // ---- residual layers
-  for (int l = 0; l < 4; ++l) {
-    const void* in = ws + o_f[l];
-    int ti = T[l], hi = H[l], wi = W[l];
-    for (int b = 0; b < 2; ++b) {
-      const Block& blk = h->blocks[l][b];
-      void* out = b == 0 ? (void*)(ws + o_x1) : (void*)(ws + o_f[l + 1]);
-      ConvArgs c1 = make_conv(blk.s1, n, ti, hi, wi, in, ws + o_mid, nullptr, 1, act, 0);
-      if ((rc = run_conv(h, c1, stream))) return rc;
-      ConvArgs c2 = make_conv(blk.t1, n, c1.s.to, c1.s.ho, c1.s.wo, ws + o_mid, ws + o_ta, nullptr, 1, act, 0);
-      if ((rc = run_conv(h, c2, stream))) return rc;
-      ConvArgs c3 = make_conv(blk.s2, n, c2.s.to, c2.s.ho, c2.s.wo, ws + o_ta, ws + o_mid, nullptr, 1, act, 0);
-      if ((rc = run_conv(h, c3, stream))) return rc;
-      const void* res = in;
-      if (blk.has_down) {
-        if ((rc = run_conv(h, make_conv(blk.down, n, ti, hi, wi, in, ws + o_ds, nullptr, 0, act, 0), stream))) return rc;
-        res = ws + o_ds;
-      }
-      ConvArgs c4 = make_conv(blk.t2, n, c3.s.to, c3.s.ho, c3.s.wo, ws + o_mid, out, res, 1, act, 0);
-      if ((rc = run_conv(h, c4, stream))) return rc;
-      in = out; ti = c4.s.to; hi = c4.s.ho; wi = c4.s.wo;
-    }
-  }
-  if ((rc = mark(2))) return rc;
-  // ---- decoder: lateral projections at native resolution (fp32 out), stem + layer1 share one map
-  {
-    ConvArgs c = make_conv(h->lateral[0], n, T[0], H[0], W[0], ws + o_f[0], ws + o_g[0], nullptr, 0, act, tc_head ? 0 : 1);
-    c.in2 = ws + o_f[1];
-    if ((rc = run_conv(h, c, stream))) return rc;
-  }
-  for (int i = 2; i < 5; ++i)
-    if ((rc = run_conv(h, make_conv(h->lateral[i], n, T[i], H[i], W[i], ws + o_f[i], ws + o_g[i - 1], nullptr, 0, act, tc_head ? 0 : 1), stream))) return rc;
-  if ((rc = mark(3))) return rc;
-  HeadArgs ha;
-  for (int i = 0; i < 4; ++i) { ha.g[i] = ws + o_g[i]; ha.tl[i] = T[i + 1]; ha.hl[i] = H[i + 1]; ha.wl[i] = W[i + 1]; }
-  ha.g_dtype = tc_head ? CLASFV_BF16 : CLASFV_F32;
-  ha.n = n; ha.t = t; ha.h = height; ha.w = width;
-  ha.b1 = h->b1; ha.w2 = h->w2; ha.w2_bf16 = h->w2_bf16; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;
-  ha.seg = seg_dev; ha.motion = motion_dev; ha.out_dtype = out_dtype; ha.out_kind = out_kind;
-  if ((rc = tc_head ? launch_head_umma(ha, stream) : launch_head(ha, stream))) return rc;
-  if ((rc = mark(4))) return rc;
-  if (h->profiling) ++h->prof_calls;
+  f.channel_stride = channel_stride;
+  return f.run();
+}
+
+int clasfv_set_option(clasfv_handle* h, const char* name, int value) {
+  CLASFV_REQUIRE(h && name, "clasfv_set_option: null argument");
+  const std::string k(name);
+  if (k == "sub_batch") { CLASFV_REQUIRE(value >= 1 && value <= 4096, "clasfv_set_option: sub_batch out of range"); h->sub_batch = value; }
+  else if (k == "dense_video") { h->dense_video = value != 0; }
+  else { set_error("clasfv_set_option: unknown option '%s'", name); return CLASFV_EINVAL; }
   return CLASFV_OK;
 }
 
 int clasfv_profile_begin(clasfv_handle* h) {
   CLASFV_REQUIRE(h, "clasfv_profile_begin: handle is NULL");
-  h->profiling = true; h->prof_calls = 0;
+  h->profiling = true; h->prof_calls = 0; h->prof_used = 0; h->prof_stage.clear();
+  for (int s = 0; s < 4; ++s) h->prof_gflop[s] = 0.0;
   return CLASFV_OK;
 }
 
@@ -529,16 +720,22 @@ int clasfv_profile_end(clasfv_handle* h, float* stage_ms_host, int* calls_host) 
   DeviceGuard guard(h->device);
   h->profiling = false;
   for (int s = 0; s < 4; ++s) stage_ms_host[s] = 0.f;
-  for (int c = 0; c < h->prof_calls; ++c) {
-    CLASFV_CUDA(cudaEventSynchronize(h->prof_events[(size_t)c * 5 + 4]));
-    for (int s = 0; s < 4; ++s) {
-      float ms = 0.f;
-      CLASFV_CUDA(cudaEventElapsedTime(&ms, h->prof_events[(size_t)c * 5 + s], h->prof_events[(size_t)c * 5 + s + 1]));
-      stage_ms_host[s] += ms;
-    }
+  for (size_t i = 0; i < h->prof_used; ++i) {
+    const int stage = h->prof_stage[i];
+    if (stage < 0) continue;                       // first event of a call
+    CLASFV_CUDA(cudaEventSynchronize(h->prof_events[i]));
+    float ms = 0.f;
+    CLASFV_CUDA(cudaEventElapsedTime(&ms, h->prof_events[i - 1], h->prof_events[i]));
+    stage_ms_host[stage] += ms;
   }
   if (calls_host) *calls_host = h->prof_calls;
-  h->prof_calls = 0;
+  h->prof_calls = 0; h->prof_used = 0; h->prof_stage.clear();
+  return CLASFV_OK;
+}
+
+int clasfv_profile_gflop(clasfv_handle* h, double* stage_gflop_host) {
+  CLASFV_REQUIRE(h && stage_gflop_host, "clasfv_profile_gflop: null argument");
+  for (int s = 0; s < 4; ++s) stage_gflop_host[s] = h->prof_gflop[s];
   return CLASFV_OK;
 }
 

@@ -68,6 +68,14 @@ struct UmmaParams {
   uint32_t idesc;
   const float* bias; const void* residual; void* out;
   int relu, out_f32;
+  // frame-wise A loads (time-segmented temporal convolution): the (bt+2)-frame slab is filled by one single-frame
+  // box load per frame, frame v of the virtual clip coming from map 0 (v < fw_split) or map 1
+  int framewise, fw_split, fw_a_toff, fw_b_toff, frame_bytes;
+  int64_t out_bstride;                       // elements between clips of `out`
+  // segmented residual (see ConvArgs::ResSeg); res_split = INT_MAX and res_a_bstride = dense when not segmented
+  const void* residual_b;
+  int res_split, res_a_toff, res_b_toff;
+  int64_t res_a_bstride, res_b_bstride;
 };
 
 // ------------------------------------------------------------------------------------ the kernel
@@ -141,7 +149,16 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
           for (int ks = 0; ks < p.kslabs; ++ks) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_arrive_expect_tx(full_bar(stage), tx);
-            tma_load_5d(a_base + (uint32_t)(stage * p.a_slab_bytes), map, full_bar(stage), ks * SLAB_K, cw, ch, ct, b0);
+            if (p.framewise) {
+              for (int f = 0; f < p.bt + 2; ++f) {
+                const int v = ct + f;           // frame of the virtual clip (ct = t0 - 1)
+                const bool from_a = v < p.fw_split;
+                tma_load_5d(a_base + (uint32_t)(stage * p.a_slab_bytes + f * p.frame_bytes), &p.tmap_a[from_a ? 0 : 1], full_bar(stage),
+                            ks * SLAB_K, cw, ch, v + (from_a ? p.fw_a_toff : p.fw_b_toff), b0);
+              }
+            } else {
+              tma_load_5d(a_base + (uint32_t)(stage * p.a_slab_bytes), map, full_bar(stage), ks * SLAB_K, cw, ch, ct, b0);
+            }
             if (!p.resident)
               for (int tap = tap0; tap < tap1; ++tap)
                 tma_load_3d(b_base + (uint32_t)((stage * p.b_stage_slabs + (tap - tap0)) * p.b_slab_bytes), &p.tmap_b, full_bar(stage),
@@ -211,20 +228,26 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
       const int ow = w0 + iw, oh = h0 + ih, ot = t0 + itt, ob = b0 + ib;
       const bool valid = ib < p.bb && ow < p.wo && oh < p.ho && ot < p.to && ob < p.n;
       const int c0 = n_tile * p.bn;
-      const int64_t off = ((((int64_t)ob * p.to + ot) * p.ho + oh) * p.wo + ow) * p.cout + c0;
+      const int64_t pix = ((int64_t)oh * p.wo + ow) * p.cout + c0;
+      const int64_t frame_elems = (int64_t)p.ho * p.wo * p.cout;
+      const int64_t off = (int64_t)ob * p.out_bstride + (int64_t)ot * frame_elems + pix;
       const int ncols = min(p.bn, p.cout - c0);   // ragged last N tile: columns past Cout are never stored
       const bool has_res = p.residual != nullptr && valid;
+      const bool res_a = ot < p.res_split;
+      const int64_t roff = res_a ? (int64_t)ob * p.res_a_bstride + (int64_t)(ot + p.res_a_toff) * frame_elems + pix
+                                 : (int64_t)ob * p.res_b_bstride + (int64_t)(ot + p.res_b_toff) * frame_elems + pix;
+      const void* res_base = res_a ? p.residual : p.residual_b;
 
       // the residual of the first chunk is requested before the accumulator is even complete
       uint4 res_bf[2]; float4 res_f[4];
       auto fetch_res = [&](int cc) {
         if (!has_res) return;
         if (p.out_f32) {
-          const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + off + cc);
+          const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(res_base) + roff + cc);
 #pragma unroll
           for (int i = 0; i < 4; ++i) res_f[i] = __ldg(rp + i);
         } else {
-          const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off + cc);
+          const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(res_base) + roff + cc);
           res_bf[0] = __ldg(rp); res_bf[1] = __ldg(rp + 1);
         }
       };
@@ -438,6 +461,8 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
     mode = SHARE_NONE;
   }
   CLASFV_REQUIRE(p.nstages >= 2, "conv_umma: tile does not fit shared memory");
+  CLASFV_REQUIRE(!a.seg.on || mode == SHARE_T, "conv_umma: a time-segmented input needs a 3x1x1 stride-1 pad-1 convolution whose frame is whole swizzle atoms");
+  CLASFV_REQUIRE(!a.seg.on || (a.seg.b && a.seg.a_t >= 1 && a.seg.b_t >= 1 && a.seg.to == s.to), "conv_umma: bad time-segment description");
   p.tiles_w = (int)cdiv(s.wo, p.bw); p.tiles_h = (int)cdiv(s.ho, p.bh); p.tiles_t = (int)cdiv(s.to, p.bt); p.tiles_b = (int)cdiv(s.n, p.bb);
 
   // ---- groups, taps -> (parity view, coordinate shift, slab row offset)
@@ -484,7 +509,23 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   // ---- tensor maps
   const int halo_h = mode == SHARE_H ? 2 : 0, halo_t = mode == SHARE_T ? 2 : 0;
   const uint32_t boxa[5] = {(uint32_t)SLAB_K, (uint32_t)p.bw, (uint32_t)(p.bh + halo_h), (uint32_t)(p.bt + halo_t), (uint32_t)p.bb};
-  for (int v = 0; v < MAX_VIEWS; ++v) {
+  if (a.seg.on) {
+    // frame-wise loads: map 0 = source A, map 1 = source B, one frame per box
+    p.framewise = 1; p.fw_split = a.seg.split; p.fw_a_toff = a.seg.a_toff; p.fw_b_toff = a.seg.b_toff;
+    p.frame_bytes = p.bw * p.bh * SLAB_K * 2;
+    const uint32_t boxf[5] = {(uint32_t)SLAB_K, (uint32_t)p.bw, (uint32_t)p.bh, 1u, 1u};
+    const uint64_t e = 2, frame = (uint64_t)s.hi * s.wi * s.cin;
+    for (int v = 0; v < MAX_VIEWS; ++v) {
+      const bool is_b = v == 1;
+      const int tt = is_b ? a.seg.b_t : a.seg.a_t;
+      const uint64_t bstride = is_b ? (uint64_t)a.seg.b_batch_stride : (a.in_batch_stride ? (uint64_t)a.in_batch_stride : frame * tt);
+      const uint64_t dims[5] = {(uint64_t)s.cin, (uint64_t)s.wi, (uint64_t)s.hi, (uint64_t)tt, (uint64_t)s.n};
+      const uint64_t strides[4] = {(uint64_t)s.cin * e, (uint64_t)s.wi * s.cin * e, frame * e, bstride * e};
+      int rc = encode_map(&p.tmap_a[v], const_cast<void*>(is_b ? a.seg.b : a.in), 5, dims, strides, boxf);
+      if (rc) return rc;
+    }
+  }
+  for (int v = 0; v < MAX_VIEWS && !a.seg.on; ++v) {
     const int vv = v < nviews ? v : 0;          // unused slots alias view 0 so that prefetch.tensormap is harmless
     const int rt = view_rt[vv], rh = view_rh[vv], rw = view_rw[vv];
     const uint64_t dims[5] = {(uint64_t)s.cin, (uint64_t)cdiv(s.wi - rw, s.sw), (uint64_t)cdiv(s.hi - rh, s.sh),
@@ -509,6 +550,16 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   p.tmem_cols = cols;
   p.idesc = idesc_bf16_f32(TILE_M, bn);
   p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.relu = a.relu; p.out_f32 = a.out_f32;
+  const int64_t out_frame = (int64_t)s.ho * s.wo * s.cout;
+  p.out_bstride = a.out_batch_stride ? a.out_batch_stride : out_frame * s.to;
+  if (a.res.on) {
+    CLASFV_REQUIRE(a.residual && a.res.b, "conv_umma: a segmented residual needs both sources");
+    p.residual_b = a.res.b; p.res_split = a.res.split; p.res_a_toff = a.res.a_toff; p.res_b_toff = a.res.b_toff;
+    p.res_a_bstride = a.res.a_batch_stride; p.res_b_bstride = a.res.b_batch_stride;
+  } else {
+    p.residual_b = a.residual; p.res_split = 0x7fffffff; p.res_a_toff = 0; p.res_b_toff = 0;
+    p.res_a_bstride = p.out_bstride; p.res_b_bstride = p.out_bstride;
+  }
 
   const size_t smem = 1024 + (size_t)p.nstages * p.a_slab_bytes +
                       (p.resident ? (size_t)ntaps * p.kslabs * p.b_slab_bytes : (size_t)p.nstages * p.b_stage_slabs * p.b_slab_bytes) + bar_bytes;

@@ -52,6 +52,23 @@ struct ConvArgs {
   int act_dtype;          // CLASFV_F32 | CLASFV_BF16: type of in / weight
   int out_f32;            // 1: out (and residual) are fp32 regardless of act_dtype
   int relu;
+  double macs_per_pos;    // true (unpadded) MACs per output position, for the profiler's performed-FLOP count
+  // ---- optional, tcgen05 path only (zero-initialised by make_conv): ragged clip geometry of the dense-video trunk
+  int64_t out_batch_stride;   // elements between consecutive clips of `out` (0 = dense To*Ho*Wo*Cout)
+  // Time-segmented input of a 3x1x1 stride-1 pad-1 convolution (seg.on): the clip the convolution sees is VIRTUAL.
+  // Its input frame v (v = -1 .. to, the convolution's own zero padding included) is frame v + a_toff of source A
+  // (`in`, a_t frames per clip, in_batch_stride) when v < split, else frame v + b_toff of source B (b, b_t frames per
+  // clip, b_batch_stride); a frame index outside its source's [0, *_t) reads as zeros.  The output has `to` frames.
+  struct TimeSeg {
+    int on, to, split, a_t, a_toff, b_t, b_toff;
+    const void* b; int64_t b_batch_stride;
+  } seg;
+  // Segmented residual: output frame ot adds frame ot + a_toff of `residual` (res.a_batch_stride) when ot < split,
+  // else frame ot + b_toff of res.b (res.b_batch_stride).  res.on == 0: residual is dense like `out`.
+  struct ResSeg {
+    int on, split, a_toff, b_toff;
+    int64_t a_batch_stride; const void* b; int64_t b_batch_stride;
+  } res;
 };
 
 // CUDA-core implicit GEMM (both storage types).  conv_simt.cu
@@ -73,6 +90,11 @@ struct StemArgs {
   int out_dtype;
 };
 int launch_stem(const StemArgs& a, cudaStream_t stream);
+
+// Frame gather (conv_simt.cu): dst[clip][dst_t0 + f] = src[clip][src_t0 + f], f < frames, for up to 4 segments
+struct FrameGatherSeg { const void* src; int64_t src_batch_stride_bytes; int src_t0, dst_t0, frames; };
+int launch_frame_gather(void* dst, int64_t dst_batch_stride_bytes, int n, int64_t frame_bytes, const FrameGatherSeg* segs, int nsegs,
+                        cudaStream_t stream);
 
 // Decoder head: 4-level trilinear (align_corners=True) gather-sum of the laterally projected feature
 // maps + bias + ReLU + 64x64 + ReLU + 6x64 heads + softmax / tanh.  decoder.cu

@@ -112,6 +112,28 @@ class Engine:
                                       _lib.torch_dtype_code(seg.dtype), seg.data_ptr(), mot.data_ptr(),
                                       _lib.current_stream_ptr(x.device)), "clasfv_forward")
 
+    def forward_windows(self, video, seg, mot, out_kind, clip_starts, clip_len, batch_clips=16):
+        """All windows [s, s+clip_len) of a resident video (3,Tv,H,W) in as few calls as possible: every maximal run
+        of equally spaced starts is ONE clasfv_forward call, so the library can share the stem and layer1 between
+        the overlapping windows (dense-video schedule) and batches internally (``batch_clips`` per batch)."""
+        self.set_option("sub_batch", batch_clips)
+        starts = [int(s) for s in clip_starts]
+        i, n = 0, len(starts)
+        while i < n:
+            j = i + 1
+            if j < n:
+                d = starts[j] - starts[i]
+                while j + 1 < n and starts[j + 1] - starts[j] == d:
+                    j += 1
+                j += 1
+            self.forward_into(video, seg[i:j], mot[i:j], out_kind, clip_starts=starts[i:j], clip_len=clip_len)
+            i = j
+
+    def set_option(self, name, value):
+        """``sub_batch`` (clips per internal batch of a forward call, default 16) or ``dense_video`` (0/1: share
+        the stem and layer1 between overlapping windows of one resident video, default on)."""
+        check(self.lib.clasfv_set_option(self._h, name.encode(), int(value)), f"clasfv_set_option({name})")
+
     def profile_begin(self):
         check(self.lib.clasfv_profile_begin(self._h), "clasfv_profile_begin")
 
@@ -120,6 +142,9 @@ class Engine:
         ms = (C.c_float * 4)()
         calls = C.c_int(0)
         check(self.lib.clasfv_profile_end(self._h, ms, C.byref(calls)), "clasfv_profile_end")
+        gf = (C.c_double * 4)()
+        check(self.lib.clasfv_profile_gflop(self._h, gf), "clasfv_profile_gflop")
+        self.last_profile_gflop = {"stem": gf[0], "trunk": gf[1], "lateral": gf[2], "head": gf[3]}
         return {"stem": ms[0], "trunk": ms[1], "lateral": ms[2], "head": ms[3]}, calls.value
 
     def workspace_bytes(self):

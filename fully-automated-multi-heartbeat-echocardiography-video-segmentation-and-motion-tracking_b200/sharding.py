@@ -140,9 +140,7 @@ def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=16, gr
     if mine:
         prob = torch.empty((len(mine), 2, CLIP, h, w), dtype=out_dtype, device=v.device)
         mot = torch.empty((len(mine), 4, CLIP, h, w), dtype=out_dtype, device=v.device)
-        for b0 in range(0, len(mine), batch_clips):
-            b1 = min(len(mine), b0 + batch_clips)
-            eng.forward_into(v, prob[b0:b1], mot[b0:b1], OUT_PROB, clip_starts=mine[b0:b1], clip_len=CLIP)
+        eng.forward_windows(v, prob, mot, OUT_PROB, mine, CLIP, batch_clips)
         res = eng.warp_fuse(prob, mot, [s - lo for s in mine], hi - lo, edge_hops=edge_hops, want_mask=False, want_area=False)
         acc, cnt = res["acc"], res["cnt"]
     else:

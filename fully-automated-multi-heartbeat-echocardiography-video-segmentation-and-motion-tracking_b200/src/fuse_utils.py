@@ -125,9 +125,9 @@ def segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num
         n = len(starts)
         prob = torch.empty((n, 2, CLIP, h, w), dtype=out_dtype, device=v.device)
         mot = torch.empty((n, 4, CLIP, h, w), dtype=out_dtype, device=v.device)
-        for b0 in range(0, n, batch_clips):
-            b1 = min(n, b0 + batch_clips)
-            eng.forward_into(v, prob[b0:b1], mot[b0:b1], OUT_PROB, clip_starts=starts[b0:b1], clip_len=CLIP)
+        # one call per run of equally spaced windows: the library batches internally (batch_clips) and shares the stem
+        # and layer1 between the overlapping windows (dense-video schedule, csrc/api.cu)
+        eng.forward_windows(v, prob, mot, OUT_PROB, starts, CLIP, batch_clips)
         res = eng.warp_fuse(prob, mot, starts, num_frames, edge_hops=edge_hops)
         fused = res["mask"].cpu().numpy().astype(np.int64)
         if return_details:
@@ -155,6 +155,7 @@ def segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num
     total = clips.shape[0]
     prob = torch.empty((total, 2, CLIP, h, w), dtype=out_dtype, device=v.device)
     mot = torch.empty((min(batch_clips, total), 4, CLIP, h, w), dtype=out_dtype, device=v.device)
+    eng.set_option("sub_batch", batch_clips)
     for b0 in range(0, total, batch_clips):
         b1 = min(total, b0 + batch_clips)
         eng.forward_into(clips[b0:b1], prob[b0:b1], mot[:b1 - b0], OUT_PROB)

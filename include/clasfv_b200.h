@@ -83,14 +83,26 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
                    int n, int t, int height, int width, int out_kind, int out_dtype,
                    void* seg_dev, void* motion_dev, void* stream);
 
+/* Options of a handle (no reference counterpart):
+ *   "sub_batch"    clips per internal batch of clasfv_forward (default 16): a call with more clips is processed
+ *                  batch by batch inside one workspace
+ *   "dense_video"  0/1 (default 1).  When the clips of a call are equally spaced windows (1..8 frames apart) of one
+ *                  resident video, bf16 tensor-core mode, N >= 4, T >= 16: the stem and layer1 are evaluated once over
+ *                  the union of the frames, and per clip only the <= 5 frames next to each clip edge (the ones the
+ *                  clip's zero padding reaches through 5 temporal convolutions) are recomputed.  Outputs are
+ *                  bit-identical to the per-clip schedule; pass every window of the video in ONE call to benefit. */
+int clasfv_set_option(clasfv_handle* h, const char* name, int value);
+
 /* Stage timing of clasfv_forward with CUDA events recorded on the caller's stream (measurement support,
- * no reference counterpart).  Between begin and end every forward records five events; end waits for
- * them and returns the summed milliseconds of the four stages
+ * no reference counterpart).  Between begin and end every forward records an event after each stage of each
+ * internal batch; end waits for them and returns the summed milliseconds of the four stages
  *   [0] stem 1x7x7   [1] trunk convolutions (stem 3x1x1 + layer1..4, the tcgen05 kernel in bf16 mode)
  *   [2] decoder lateral 1x1x1 projections   [3] fused decoder head
  * and the number of forward calls covered. */
 int clasfv_profile_begin(clasfv_handle* h);
 int clasfv_profile_end(clasfv_handle* h, float* stage_ms_host /* [4] */, int* calls_host);
+/* GFLOP (2 x true, unpadded MACs) the convolutions of each stage performed since clasfv_profile_begin. */
+int clasfv_profile_gflop(clasfv_handle* h, double* stage_gflop_host /* [4] */);
 
 /* Largest workspace (bytes) the handle currently holds; informational. */
 int64_t clasfv_workspace_bytes(const clasfv_handle* h);

@@ -255,6 +255,36 @@ def test_forward_interface_and_errors(net_fp32, sd):
 
 
 # ------------------------------------------------------------------------------------------ F2
+# ------------------------------------------------------------------------------------------ dense-video schedule
+@pytest.mark.parametrize("tv,clip_len,h,w,step,sub_batch", [
+    (43, 32, 32, 32, 1, 5),        # 12 windows, ragged last batch
+    (40, 16, 48, 32, 2, 16),       # stride-2 windows, shortest clip the schedule accepts, one batch
+    (52, 32, 112, 112, 1, 8),      # the benchmark geometry (56x56 layer-1 maps)
+])
+def test_dense_video_schedule_is_bit_identical_to_per_clip(net_bf16, tv, clip_len, h, w, step, sub_batch):
+    """Sharing the stem and layer1 between overlapping windows (csrc/api.cu, Forward::run_dense) must not change a
+    single bit of the outputs: every output element is produced by the same MMA sequence as in the per-clip schedule."""
+    eng = net_bf16.engine()
+    video = torch.from_numpy(synthetic.synthetic_echo_video(tv, h, w, seed=5)).cuda()
+    starts = list(range(0, tv - clip_len + 1, step))
+    outs = []
+    for dense in (1, 0):
+        eng.set_option("dense_video", dense)
+        eng.set_option("sub_batch", sub_batch)
+        seg, mot = eng.forward(video, _lib.OUT_LOGITS, torch.bfloat16, clip_starts=starts, clip_len=clip_len)
+        torch.cuda.synchronize()
+        outs.append((seg.float().cpu(), mot.float().cpu()))
+    eng.set_option("dense_video", 1)
+    eng.set_option("sub_batch", 16)
+    assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[0][1]).all()
+    assert torch.equal(outs[0][0], outs[1][0]), float((outs[0][0] - outs[1][0]).abs().max())
+    assert torch.equal(outs[0][1], outs[1][1]), float((outs[0][1] - outs[1][1]).abs().max())
+    # and the per-clip schedule on a dense (N,3,T,H,W) copy of the same windows gives the same numbers
+    clips = torch.stack([video[:, s:s + clip_len] for s in starts[:3]]).contiguous()
+    seg3, mot3 = eng.forward(clips, _lib.OUT_LOGITS, torch.bfloat16)
+    assert torch.equal(seg3.float().cpu(), outs[0][0][:3]) and torch.equal(mot3.float().cpu(), outs[0][1][:3])
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("edge", [False, True])
 def test_warp_fuse_matches_oracle(eng, dtype, edge):
