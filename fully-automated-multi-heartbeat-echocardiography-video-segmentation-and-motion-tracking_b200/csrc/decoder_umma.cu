@@ -1,21 +1,29 @@
-// decoder_umma.cu - the fused decoder head of decoder.cu with its 64x64 convolution on the tensor cores.
+// decoder_umma.cu - the fused decoder head (upsample x4 levels + comb_1 bias/ReLU + comb_2 + heads + softmax/tanh)
+// with everything that is a contraction on the tensor cores, as a warp-specialised pipeline.  sm_100a only.
 //
-// A persistent CTA (512 threads) produces one output row (n, t, h) of up to 128 voxels at a time:
-//   phase 1  the T- and H-interpolated rows of the four laterally projected maps (bf16 in HBM) are
-//            built in shared memory as fp32 (trilinear, align_corners=True, reference
-//            src/model/R2plus1D_18_MotionNet.py:41-49); corners with zero weight are not read
-//   phase 2  thread (voxel group of 4, channel quarter) W-interpolates and sums the four levels, adds
-//            the folded comb_1 bias, ReLU, converts to bf16 and writes its part of the 128 x 64 A tile
-//            directly in the K-major SWIZZLE_128B layout tcgen05 consumes (adjacent voxels share their
-//            low-resolution taps, so each tap vector is read from shared memory once per group)
-//   MMA 1    one elected thread issues 4 x tcgen05.mma (M=128, N=64, K=16): D = A * W2^T into TMEM
-//   mid      thread = voxel: tcgen05.ld its 64 accumulators, + folded comb_2 bias, ReLU, bf16, back into the
-//            (now free) A tile
-//   MMA 2    4 x tcgen05.mma (M=128, N=16, K=16): the 6x64 segmentation + motion heads (10 zero rows)
-//   epilogue thread = voxel: tcgen05.ld 8 accumulators, + head bias, softmax / tanh, six coalesced planar stores
-// The kernel is instruction-bound, not memory-bound: the interpolated rows are kept in bf16 and the heads run on
-// the tensor core to cut CUDA-core instructions per row and to fit four CTAs per SM.
-// Nothing between the lateral projections and the six output planes touches HBM.
+// Reference: src/model/R2plus1D_18_MotionNet.py:41-71 (trilinear align_corners=True upsampling of the five feature
+// maps, cat, comb_1 + BN + ReLU, comb_2 + BN + ReLU, segmentation / motion heads, tanh) and src/fuse_utils.py:60
+// (softmax).  comb_1 has been commuted with the upsampling (api.cu): the inputs here are the four laterally
+// projected 64-channel maps g_l at 1/2, 1/4, 1/8, 1/16 resolution.
+//
+// One output row (n, t, h) of up to 128 voxels is one "tile".  For that row
+//   R_l[x, c] = sum over the <= 4 (T,H) corners  wT * wH * g_l[n, t_i, h_i, x, c]        (CUDA cores, "phase 1")
+//   h1[v, c]  = relu( sum_l sum_x Wmat_l[v, x] * R_l[x, c] + b1[c] )                      (MMA 0)
+//   h2[v, c]  = relu( sum_k h1[v, k] * W2[c, k] + b2[c] )                                 (MMA 1)
+//   o[v, j]   = sum_k h2[v, k] * Wh[j, k] + bh[j]   -> softmax / tanh -> 6 planar stores   (MMA 2)
+// MMA 0 is the W-axis interpolation written as a GEMM: its A operand is the constant interpolation matrix of the
+// row [128 voxels x K], K = the low-resolution columns of the four levels side by side (+2 columns of ones that
+// pick up b1 as two extra rows of R), split into a bf16 high and low part so the weights carry ~16 mantissa bits;
+// its B operand is R, built per row in shared memory directly in the MN-major SWIZZLE_128B layout (K rows of 64
+// channels = 128 bytes).  ReLU + bf16 conversion of an accumulator is one cvt.rn.relu.bf16x2.f32 per two values.
+//
+// Warp roles (768 threads, persistent, one CTA per SM); every hand-over is an mbarrier, every buffer is doubled:
+//   warp 0           producer: plans the row (corner indices / weights), bulk-copies its raw corner rows (bf16)
+//   warp 1           MMA issuer (one lane): per step MMA0(i), MMA1(i-1), MMA2(i-2)
+//   warps 4-7        epilogue 0: acc0 -> relu -> bf16 -> A tile            (one warp per TMEM lane quarter)
+//   warps 8-11       epilogue 1: acc1 + b2 -> relu -> bf16 -> A tile (in place: MMA 1 has finished reading it)
+//   warps 12-15      epilogue 2: acc2 + bh -> softmax / tanh -> global
+//   warps 2,3,16-23  phase 1: raw corner rows -> R
 #include "internal.h"
 #include "umma_ptx.cuh"
 
@@ -26,331 +34,433 @@ namespace {
 
 using namespace ptx;
 
-constexpr int HU_THREADS = 512;
+constexpr int HU_THREADS = 768;
 constexpr int HC = 64;
-constexpr int ROW_PITCH = HC + 4;       // floats per low-res column: 272 B keeps 16-byte alignment and spreads banks
+constexpr int P1_WARPS = 10;
+constexpr int P1_THREADS = P1_WARPS * 32;
+constexpr int MAX_WT = 4;                 // w tiles of 128 voxels (W <= 512)
+constexpr int KSLABS = 2;                 // K of MMA 0 is always 2 slabs of 64 (interpolation columns + 2 bias rows, zero padded)
 
 struct AxisTap { int i0, i1; float l0, l1; };
-__device__ __forceinline__ AxisTap axis_tap(int dst, int in_size, int out_size) {
+__host__ __device__ __forceinline__ AxisTap axis_tap(int dst, int in_size, int out_size) {
   AxisTap a;
   const float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
   const float src = scale * (float)dst;
-  a.i0 = min((int)src, in_size - 1);
+  a.i0 = (int)src < in_size - 1 ? (int)src : in_size - 1;
   a.i1 = a.i0 + (a.i0 < in_size - 1 ? 1 : 0);
   a.l1 = src - (float)a.i0;
   a.l0 = 1.f - a.l1;
   return a;
 }
 
-__device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
-  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
-  acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
-}
-__device__ __forceinline__ uint32_t pack_relu_bf16(float a, float b) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(b, 0.f));
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-
 template <typename OutT> __device__ __forceinline__ void put(OutT* p, float v);
 template <> __device__ __forceinline__ void put<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void put<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-struct HeadSmem {
-  // byte offsets from the 1024-aligned base
-  static constexpr uint32_t A = 0;                 // 128 x 128 B : relu(h1) for MMA 1, then relu(h2) for MMA 2
-  static constexpr uint32_t B = 16384;             // 64 x 128 B  : W2
-  static constexpr uint32_t B3 = 24576;            // 16 x 128 B  : heads (rows 0-1 seg, 2-5 motion, 6-15 zero)
-  static constexpr uint32_t B1 = B3 + 2048;        // [64] fp32
-  static constexpr uint32_t B2 = B1 + 256;         // [64]
-  static constexpr uint32_t BH = B2 + 256;         // [8]
-  static constexpr uint32_t BAR_RAW = BH + 32;     // mbarrier: raw corner rows landed
-  static constexpr uint32_t BAR = BAR_RAW + 8;     // mbarrier MMA 1
-  static constexpr uint32_t BAR3 = BAR + 8;        // mbarrier MMA 2
-  static constexpr uint32_t TMEM = BAR3 + 8;       // tmem base
-  static constexpr uint32_t PLAN = 27264;          // 2 x TilePlan (double-buffered: written one row ahead by thread 0)
-  static constexpr uint32_t WTAP = 27648;          // [4 levels][128 voxels] WTap: the W-axis taps, computed once per CTA
-  static constexpr uint32_t ROWS = WTAP + 4 * 128 * 16;   // 4 levels x [wl][ROW_PITCH] fp32, then the raw corner rows (bf16)
-};
-
-struct __align__(16) WTap { int i0, i1; float l0, l1; };
-
-__device__ __forceinline__ void bf16x4_to_f32(const uint2& r, float (&f)[4]) {
-  f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
-  f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+// {low 16 bits = bf16(relu(a)), high 16 bits = bf16(relu(b))}: a is the element at the lower address
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
 }
 
-struct TilePlan {                 // one output row (n, t, h): which corner rows feed it and with what weight
-  int n, t, h, w_base;
-  float wgt[4][4];                // [level][corner = 2*tc + hc]
-  int ti[4][2], hi[4][2];         // corner indices per level
+// compiler-level fence: values produced by an asynchronous tcgen05.ld may not be consumed before tcgen05.wait::ld
+__device__ __forceinline__ void reg_fence16(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+
+// Wait used by every role except the MMA issuer: back off between polls so that twenty-odd waiting warps do not
+// take issue slots from the one thread that feeds the tensor core.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done) {
+      __nanosleep(40);
+      if (spin > (1u << 22)) { printf("clasfv head_umma: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+  }
+}
+
+struct HeadGeom {                 // host-computed layout of the K axis of MMA 0 and of a raw corner-row stage
+  int w_tiles, ktot, kpad, nslab;
+  int koff[4];                    // first K row of level l
+  int nxmax[4];                   // K rows reserved for level l
+  int xlo[MAX_WT][4], nx[MAX_WT][4];   // low-resolution columns [xlo, xlo+nx) the voxels of w tile wt touch
+  int raw_off[4];                 // byte offset of level l inside a raw stage: corner slots of nxmax columns each (4, or 2
+                                  // when the level is at the output's temporal resolution and only its H corners exist)
+  int raw_stage_bytes;
+  int total_rows;                 // n * t * h
 };
 
-// Persistent, 512 threads: every CTA loops over output rows (n, t, h).  The kernel is latency-bound, not
-// bandwidth-bound (few thousand instructions per row, each phase a dependent chain), so a row's work is spread
-// over 16 warps and the raw bf16 corner rows of the NEXT row are fetched with 1-D bulk copies
-// (cp.async.bulk -> mbarrier) while the current row is interpolated, multiplied and written out.
+struct TilePlan { float wgt[4][4]; };   // weight of each (T,H) corner per level, [level][2*tc + hc]; 0 = corner not fetched
+
+struct Smem {                     // byte offsets from the 1024-aligned base
+  static constexpr uint32_t W2B = 0;                      // 64 x 128 B   W2, K-major
+  static constexpr uint32_t WHB = W2B + 8192;             // 16 x 128 B   heads, K-major (rows 6..15 zero)
+  static constexpr uint32_t B2 = WHB + 2048;              // [64] fp32
+  static constexpr uint32_t BH = B2 + 256;                // [8] fp32
+  static constexpr uint32_t PLAN = BH + 32;               // 2 x TilePlan
+  static constexpr uint32_t BARS = PLAN + 2 * 64;         // 26 mbarriers
+  static constexpr uint32_t TMEM = BARS + 8 * 26;
+  static constexpr uint32_t AT = 11264;                   // 2 x (128 x 128 B)  A tile of MMA 1 / MMA 2
+  static constexpr uint32_t WA = AT + 2 * 16384;          // interpolation matrix: nslab hi slabs then nslab lo slabs of 16 KB
+  // then: R (2 stages x nslab x 8 KB), raw (2 stages x raw_stage_bytes)
+};
+static_assert(Smem::TMEM + 4 <= Smem::AT, "head smem header overflow");
+static_assert(sizeof(TilePlan) == 64, "plan slot size");
+
+enum Bar {  // index of the first of each pair of mbarriers (one per buffer stage)
+  RAW_FULL = 0, RAW_EMPTY = 2, R_FULL = 4, R_EMPTY = 6, ACC0_FULL = 8, ACC0_EMPTY = 10, A1_FULL = 12, A_EMPTY = 14,
+  ACC1_FULL = 16, ACC1_EMPTY = 18, A2_FULL = 20, ACC2_FULL = 22, ACC2_EMPTY = 24,
+};
+
 template <typename OutT>
-__global__ void __launch_bounds__(HU_THREADS, 2) head_umma_kernel(const HeadArgs a, int w_tiles, int total_tiles, int rows_elems) {
+__global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs a, const HeadGeom g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(sm);
-  float* b1s = reinterpret_cast<float*>(sm + HeadSmem::B1);
-  float* b2s = reinterpret_cast<float*>(sm + HeadSmem::B2);
-  float* bhs = reinterpret_cast<float*>(sm + HeadSmem::BH);
-  TilePlan* plans = reinterpret_cast<TilePlan*>(sm + HeadSmem::PLAN);
-  WTap* wtap = reinterpret_cast<WTap*>(sm + HeadSmem::WTAP);
-  float* rows = reinterpret_cast<float*>(sm + HeadSmem::ROWS);
-  const __nv_bfloat16* raw = reinterpret_cast<const __nv_bfloat16*>(rows + rows_elems);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + HeadSmem::TMEM);
-  const uint32_t bar_raw = sbase + HeadSmem::BAR_RAW, bar = sbase + HeadSmem::BAR, bar3 = sbase + HeadSmem::BAR3;
-  const uint32_t raw_base = sbase + HeadSmem::ROWS + (uint32_t)rows_elems * 4u;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* b2s = reinterpret_cast<float*>(sm + Smem::B2);
+  float* bhs = reinterpret_cast<float*>(sm + Smem::BH);
+  TilePlan* plans = reinterpret_cast<TilePlan*>(sm + Smem::PLAN);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + Smem::TMEM);
+  auto bar = [&](int which, int s) { return sbase + Smem::BARS + 8u * (uint32_t)(which + s); };
+  const uint32_t wa_bytes = (uint32_t)(2 * g.nslab) * 16384u;
+  const uint32_t r_stage_bytes = (uint32_t)g.nslab * 8192u;
+  const uint32_t r_off = Smem::WA + wa_bytes;
+  const uint32_t raw_off0 = r_off + 2u * r_stage_bytes;
 
-  int row_off[4], raw_off[4];             // rows: floats; raw: bf16 elements
-  {
-    int off = 0, roff = 0;
-#pragma unroll
-    // a level whose temporal size equals the output's is sampled at exact frames: only its 2 h-corners exist
-    for (int l = 0; l < 4; ++l) { row_off[l] = off; off += a.wl[l] * ROW_PITCH; raw_off[l] = roff; roff += (a.tl[l] == a.t ? 2 : 4) * a.wl[l] * HC; }
-  }
-  // thread 0 only: plan a row into shared memory and launch the bulk copies of its corner rows
-  auto plan_and_fetch = [&](int tile, TilePlan* pl) {
-    int r = tile;
-    const int wt = r % w_tiles; r /= w_tiles;
-    pl->h = r % a.h; r /= a.h;
-    pl->t = r % a.t; pl->n = r / a.t;
-    pl->w_base = wt * 128;
-    uint32_t bytes = 0;
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      const AxisTap at = axis_tap(pl->t, a.tl[l], a.t), ah = axis_tap(pl->h, a.hl[l], a.h);
-      pl->ti[l][0] = at.i0; pl->ti[l][1] = at.i1; pl->hi[l][0] = ah.i0; pl->hi[l][1] = ah.i1;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float wg = ((c >> 1) ? at.l1 : at.l0) * ((c & 1) ? ah.l1 : ah.l0);
-        pl->wgt[l][c] = wg;
-        if (wg != 0.f) bytes += (uint32_t)a.wl[l] * HC * 2;
-      }
-    }
-    fence_async_smem();
-    mbar_arrive_expect_tx(bar_raw, bytes);
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(a.g[l]) + (int64_t)pl->n * a.tl[l] * a.hl[l] * a.wl[l] * HC;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (pl->wgt[l][c] == 0.f) continue;
-        const __nv_bfloat16* src = g + ((int64_t)pl->ti[l][c >> 1] * a.hl[l] + pl->hi[l][c & 1]) * a.wl[l] * HC;
-        const uint32_t dst = raw_base + (uint32_t)((raw_off[l] + c * a.wl[l] * HC) * 2);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(dst), "l"(src), "r"((uint32_t)a.wl[l] * HC * 2), "r"(bar_raw) : "memory");
-      }
-    }
-  };
+  const int wt = blockIdx.x % g.w_tiles;
+  const int row0 = blockIdx.x / g.w_tiles, row_step = gridDim.x / g.w_tiles;
+  const int w_base = wt * 128;
+  const int my_rows = row0 < g.total_rows ? (g.total_rows - row0 + row_step - 1) / row_step : 0;
 
-  // ---- one-time setup
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + HeadSmem::TMEM), "r"(64u) : "memory");
+  // ------------------------------------------------------------------ one-time setup (all threads)
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::TMEM), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(bar_raw, 1);
-    mbar_init(bar, 1);
-    mbar_init(bar3, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(RAW_FULL, s), 1); mbar_init(bar(RAW_EMPTY, s), P1_WARPS);
+      mbar_init(bar(R_FULL, s), P1_WARPS); mbar_init(bar(R_EMPTY, s), 1);
+      mbar_init(bar(ACC0_FULL, s), 1); mbar_init(bar(ACC0_EMPTY, s), 4);
+      mbar_init(bar(A1_FULL, s), 4); mbar_init(bar(A_EMPTY, s), 1);
+      mbar_init(bar(ACC1_FULL, s), 1); mbar_init(bar(ACC1_EMPTY, s), 4);
+      mbar_init(bar(A2_FULL, s), 4); mbar_init(bar(ACC2_FULL, s), 1); mbar_init(bar(ACC2_EMPTY, s), 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  {
-    // W2 (64 out x 64 in, bf16) into the K-major swizzled B tile: 512 chunks of 16 bytes, one per thread
+  // zero the interpolation matrix and both R stages (unused K rows / columns must be exact zeros, not stale NaNs)
+  for (uint32_t i = (uint32_t)tid * 16u; i < wa_bytes + 2u * r_stage_bytes; i += HU_THREADS * 16u)
+    *reinterpret_cast<uint4*>(sm + Smem::WA + i) = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 512) {
+    // W2 (64 out x 64 in, bf16) into the K-major swizzled B tile: 512 chunks of 16 bytes
     const int row = tid >> 3, chunk = tid & 7;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.w2_bf16 + row * HC) + chunk);
-    *reinterpret_cast<uint4*>(sm + HeadSmem::B + sw128_offset(row, chunk)) = v;
-  }
-  if (tid < 128) {
-    // heads (6 x 64 fp32 -> bf16) into the K-major swizzled B3 tile, rows 6..15 zero: 128 chunks of 16 bytes
-    const int row = tid >> 3, chunk = tid & 7;
+    *reinterpret_cast<uint4*>(sm + Smem::W2B + sw128_offset(row, chunk)) = v;
+  } else if (tid < 640) {
+    // heads (6 x 64 fp32 -> bf16) into the K-major swizzled tile, rows 6..15 zero
+    const int i = tid - 512, row = i >> 3, chunk = i & 7;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (row < 6) {
       const float* src = a.wh + row * HC + chunk * 8;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(__ldg(src + 0), __ldg(src + 1)), h1 = __floats2bfloat162_rn(__ldg(src + 2), __ldg(src + 3));
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(__ldg(src + 4), __ldg(src + 5)), h3 = __floats2bfloat162_rn(__ldg(src + 6), __ldg(src + 7));
-      v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
-      v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+      v.x = cvt_bf16x2(__ldg(src + 0), __ldg(src + 1)); v.y = cvt_bf16x2(__ldg(src + 2), __ldg(src + 3));
+      v.z = cvt_bf16x2(__ldg(src + 4), __ldg(src + 5)); v.w = cvt_bf16x2(__ldg(src + 6), __ldg(src + 7));
     }
-    *reinterpret_cast<uint4*>(sm + HeadSmem::B3 + sw128_offset(row, chunk)) = v;
+    *reinterpret_cast<uint4*>(sm + Smem::WHB + sw128_offset(row, chunk)) = v;
+  } else if (tid < 640 + HC) {
+    b2s[tid - 640] = __ldg(a.b2 + tid - 640);
+  } else if (tid < 640 + HC + 6) {
+    bhs[tid - 704] = __ldg(a.bh + tid - 704);
   }
-  if (tid < HC) { b1s[tid] = __ldg(a.b1 + tid); b2s[tid] = __ldg(a.b2 + tid); }
-  if (tid < 6) bhs[tid] = __ldg(a.bh + tid);
-  auto fill_wtaps = [&](int w_base) {       // 4 levels x 128 voxels = 512 entries, one per thread
-    const int l = tid >> 7, v = tid & 127;
-    const AxisTap aw = axis_tap(min(w_base + v, a.w - 1), a.wl[l], a.w);
-    WTap tp; tp.i0 = aw.i0; tp.i1 = aw.i1; tp.l0 = aw.l0; tp.l1 = aw.l1;
-    wtap[tid] = tp;
-  };
-  int wtap_base = 0;
-  fill_wtaps(0);
+  __syncthreads();
+  {
+    // interpolation matrix: element (voxel v, K column k) of slab k/64, hi and lo parts
+    auto put_w = [&](int v, int k, float w) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+      const uint32_t o = (uint32_t)(k >> 6) * 16384u + sw128_offset((uint32_t)v, (uint32_t)((k & 63) >> 3)) + (uint32_t)(k & 7) * 2u;
+      *reinterpret_cast<__nv_bfloat16*>(sm + Smem::WA + o) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(sm + Smem::WA + (uint32_t)g.nslab * 16384u + o) = lo;
+    };
+    for (int i = tid; i < 4 * 128; i += HU_THREADS) {
+      const int l = i >> 7, v = i & 127;
+      if (w_base + v < a.w) {
+        const AxisTap aw = axis_tap(w_base + v, a.wl[l], a.w);
+        put_w(v, g.koff[l] + aw.i0 - g.xlo[wt][l], aw.l0);
+        if (aw.l1 != 0.f) put_w(v, g.koff[l] + aw.i1 - g.xlo[wt][l], aw.l1);
+      }
+    }
+    if (tid >= 512 && tid < 640) { put_w(tid - 512, g.ktot - 2, 1.f); put_w(tid - 512, g.ktot - 1, 1.f); }
+    // the two constant rows of R: b1 = hi + lo (both stages)
+    if (tid >= 640 && tid < 640 + 2 * HC) {
+      const int c = (tid - 640) & 63, s = (tid - 640) >> 6;
+      const float b = __ldg(a.b1 + c);
+      const __nv_bfloat16 hi = __float2bfloat16_rn(b), lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+      const uint32_t base = r_off + (uint32_t)s * r_stage_bytes;
+      *reinterpret_cast<__nv_bfloat16*>(sm + base + sw128_offset((uint32_t)(g.ktot - 2), (uint32_t)(c >> 3)) + (uint32_t)(c & 7) * 2u) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(sm + base + sw128_offset((uint32_t)(g.ktot - 1), (uint32_t)(c >> 3)) + (uint32_t)(c & 7) * 2u) = lo;
+    }
+  }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint64_t desc_a = smem_desc_sw128(sbase + HeadSmem::A), desc_b = smem_desc_sw128(sbase + HeadSmem::B),
-                 desc_b3 = smem_desc_sw128(sbase + HeadSmem::B3);
-  const uint32_t idesc1 = idesc_bf16_f32(128, 64), idesc2 = idesc_bf16_f32(128, 16);
+  const uint32_t acc0 = tmem_base, acc1 = tmem_base + 128u, acc2 = tmem_base + 256u;   // 2 x 64, 2 x 64, 2 x 16 columns
 
-  int tile = blockIdx.x;
-  if (tile < total_tiles && tid == 0) plan_and_fetch(tile, &plans[0]);
-  __syncthreads();
-  uint32_t phase = 0;
-  for (; tile < total_tiles; tile += gridDim.x, phase ^= 1u) {
-    const TilePlan& p = plans[phase];
-    if (p.w_base != wtap_base) {            // only for frames wider than 128 voxels (uniform branch)
-      __syncthreads();
-      wtap_base = p.w_base;
-      fill_wtaps(wtap_base);
-      __syncthreads();
+  auto decode_row = [&](int i, int& n, int& t, int& h) {
+    int r = row0 + i * row_step;
+    h = r % a.h; r /= a.h;
+    t = r % a.t; n = r / a.t;
+  };
+
+  if (warp == 0) {
+    // ================================================================ producer (lane = level * 4 + corner, 16 lanes)
+    const int l = (lane >> 2) & 3, c = lane & 3;
+    const bool has_slot = lane < 16 && (c < 2 || a.tl[l] != a.t);
+    const __nv_bfloat16* gbase = static_cast<const __nv_bfloat16*>(a.g[l]) + (int64_t)g.xlo[wt][l] * HC;
+    const int64_t clip_elems = (int64_t)a.tl[l] * a.hl[l] * a.wl[l] * HC, row_elems = (int64_t)a.wl[l] * HC;
+    const uint32_t my_bytes = (uint32_t)g.nx[wt][l] * 128u;
+    const uint32_t my_dst = sbase + raw_off0 + (uint32_t)g.raw_off[l] + (uint32_t)(c * g.nxmax[l]) * 128u;
+    for (int i = 0; i < my_rows; ++i) {
+      const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      int n, t, h;
+      decode_row(i, n, t, h);
+      const AxisTap at = axis_tap(t, a.tl[l], a.t), ah = axis_tap(h, a.hl[l], a.h);
+      const float wg = ((c >> 1) ? at.l1 : at.l0) * ((c & 1) ? ah.l1 : ah.l0);
+      const bool fetch = has_slot && wg != 0.f;
+      const uint32_t bytes = __reduce_add_sync(0xffffffffu, fetch ? my_bytes : 0u);
+      const __nv_bfloat16* src = gbase + n * clip_elems + ((int64_t)((c >> 1) ? at.i1 : at.i0) * a.hl[l] + ((c & 1) ? ah.i1 : ah.i0)) * row_elems;
+      mbar_wait_sleep(bar(RAW_EMPTY, s), ph ^ 1u);
+      if (lane < 16) plans[s].wgt[l][c] = fetch ? wg : 0.f;
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(bar(RAW_FULL, s), bytes);
+      __syncwarp();
+      if (fetch)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(my_dst + (uint32_t)s * (uint32_t)g.raw_stage_bytes), "l"(src), "r"(my_bytes), "r"(bar(RAW_FULL, s)) : "memory");
     }
-    // ---- phase 1: T/H-interpolated rows (fp32) from the raw corner rows, rows[off_l + x*ROW_PITCH + c]
-    mbar_wait(bar_raw, phase);
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc0 = idesc_bf16_f32(128, 64) | (1u << 16);      // B (= R) is MN-major
+      const uint32_t idesc1 = idesc_bf16_f32(128, 64), idesc2 = idesc_bf16_f32(128, 16);
+      const uint64_t desc_w2 = smem_desc_sw128(sbase + Smem::W2B), desc_wh = smem_desc_sw128(sbase + Smem::WHB);
+      const uint64_t desc_wa = smem_desc_sw128(sbase + Smem::WA), desc_r = smem_desc_sw128(sbase + r_off);
+      const uint64_t desc_at = smem_desc_sw128(sbase + Smem::AT);
+      for (int k = 0; k < my_rows + 2; ++k) {
+        if (k < my_rows) {
+          const int s = k & 1; const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+          mbar_wait(bar(R_FULL, s), ph);
+          mbar_wait(bar(ACC0_EMPTY, s), ph ^ 1u);
+          tc_fence_after();
+          // K is always 2 slabs = 128 (zero rows / columns beyond ktot): 16 instructions with constant descriptor
+          // offsets, nothing to compute in this single-thread critical path.  MN-major B: 16 K rows of 128 bytes
+          // per instruction = two 8-row swizzle atoms (SBO = 1024), so K advances by 2048 bytes = 128 descriptor units.
+          const uint64_t db0 = desc_r + (uint64_t)(s * (int)(KSLABS * 8192 / 16));
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      float wgt[4];
+          for (int part = 0; part < 2; ++part)           // hi weights, then lo weights, against the same R
 #pragma unroll
-      for (int c = 0; c < 4; ++c) wgt[c] = p.wgt[l][c];
-      const __nv_bfloat16* src = raw + raw_off[l];
-      float* dst = rows + row_off[l];
-      const int total = a.wl[l] * (HC / 4);
-      for (int i = tid; i < total; i += HU_THREADS) {
-        const int x = i >> 4, c4 = i & 15;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (wgt[c] == 0.f) continue;
-          float f[4];
-          bf16x4_to_f32(*reinterpret_cast<const uint2*>(src + ((size_t)c * a.wl[l] + x) * HC + 4 * c4), f);
-          o.x = fmaf(wgt[c], f[0], o.x); o.y = fmaf(wgt[c], f[1], o.y); o.z = fmaf(wgt[c], f[2], o.z); o.w = fmaf(wgt[c], f[3], o.w);
+            for (int kk = 0; kk < KSLABS * 4; ++kk)
+              tc_mma_bf16(acc0 + (uint32_t)(s * 64), desc_wa + (uint64_t)((part * KSLABS + (kk >> 2)) * 1024 + 2 * (kk & 3)),
+                          db0 + (uint64_t)(kk * 128), idesc0, (part | kk) ? 1u : 0u);
+          tc_commit(bar(R_EMPTY, s));
+          tc_commit(bar(ACC0_FULL, s));
         }
-        *reinterpret_cast<float4*>(dst + x * ROW_PITCH + 4 * c4) = o;
+        if (k >= 1 && k <= my_rows) {
+          const int j = k - 1, s = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+          mbar_wait(bar(A1_FULL, s), ph);
+          mbar_wait(bar(ACC1_EMPTY, s), ph ^ 1u);
+          tc_fence_after();
+          const uint64_t da = desc_at + (uint64_t)(s * 1024);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(acc1 + (uint32_t)(s * 64), da + (uint64_t)(2 * kk), desc_w2 + (uint64_t)(2 * kk), idesc1, kk > 0 ? 1u : 0u);
+          tc_commit(bar(ACC1_FULL, s));
+        }
+        if (k >= 2) {
+          const int j = k - 2, s = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+          mbar_wait(bar(A2_FULL, s), ph);
+          mbar_wait(bar(ACC2_EMPTY, s), ph ^ 1u);
+          tc_fence_after();
+          const uint64_t da = desc_at + (uint64_t)(s * 1024);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(acc2 + (uint32_t)(s * 16), da + (uint64_t)(2 * kk), desc_wh + (uint64_t)(2 * kk), idesc2, kk > 0 ? 1u : 0u);
+          tc_commit(bar(A_EMPTY, s));
+          tc_commit(bar(ACC2_FULL, s));
+        }
       }
     }
-    tc_fence_before();          // (the epilogue of the previous row read TMEM)
-    __syncthreads();
-    // the raw buffer is free: plan the next row and fetch its corner rows behind the rest of this row
-    if (tid == 0 && tile + (int)gridDim.x < total_tiles) plan_and_fetch(tile + gridDim.x, &plans[phase ^ 1u]);
-
-    // ---- phase 2: A tile.  thread = (voxel group vg of 4 voxels, channel group c4 of 4 channels)
-    {
-      const int vg = tid >> 4, c4 = tid & 15;
-      float4 f[4];
-      const float4 bias = *reinterpret_cast<const float4*>(b1s + 4 * c4);
+  } else if (warp >= 4 && warp < 16) {
+    // ================================================================ epilogues (warp % 4 = TMEM lane quarter)
+    const int role = (warp - 4) >> 2, q = warp & 3;
+    const int vrow = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    if (role == 0) {
+      for (int i = 0; i < my_rows; ++i) {
+        const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+        mbar_wait_sleep(bar(ACC0_FULL, s), ph);
+        mbar_wait_sleep(bar(A_EMPTY, s), ph ^ 1u);        // MMA 2 of row i-2 has finished reading this A tile
+        tc_fence_after();
+        const uint32_t taddr = acc0 + lane_addr + (uint32_t)(s * 64);
+        uint8_t* arow = sm + Smem::AT + (uint32_t)s * 16384u;
+        uint32_t v0[16], v1[16];
+        tc_ld16(taddr, v0);
+        tc_ld16(taddr + 16u, v1);
 #pragma unroll
-      for (int v = 0; v < 4; ++v) f[v] = bias;
+        for (int half = 0; half < 2; ++half) {
+          tc_wait_ld(); reg_fence16(v0); reg_fence16(v1);
+          uint32_t pk[16];
 #pragma unroll
-      for (int l = 0; l < 4; ++l) {
-        const float* r = rows + row_off[l] + 4 * c4;
-        int cached = -1;
-        float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 8; ++j) {
+            pk[j] = cvt_relu_bf16x2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+            pk[8 + j] = cvt_relu_bf16x2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+          }
+          if (half == 0) { tc_ld16(taddr + 32u, v0); tc_ld16(taddr + 48u, v1); }
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const WTap tp = wtap[l * 128 + vg * 4 + v];
-          if (tp.i0 != cached) { tv = *reinterpret_cast<const float4*>(r + tp.i0 * ROW_PITCH); cached = tp.i0; }
-          fma4(f[v], tp.l0, tv);
-          if (tp.l1 != 0.f) {
-            if (tp.i1 != cached) { tv = *reinterpret_cast<const float4*>(r + tp.i1 * ROW_PITCH); cached = tp.i1; }
-            fma4(f[v], tp.l1, tv);
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(arow + sw128_offset((uint32_t)vrow, (uint32_t)(4 * half + c))) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(bar(ACC0_EMPTY, s)); mbar_arrive(bar(A1_FULL, s)); }
+      }
+    } else if (role == 1) {
+      for (int i = 0; i < my_rows; ++i) {
+        const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+        mbar_wait_sleep(bar(ACC1_FULL, s), ph);           // MMA 1 done: acc1 complete AND the A tile may be overwritten
+        tc_fence_after();
+        const uint32_t taddr = acc1 + lane_addr + (uint32_t)(s * 64);
+        uint8_t* arow = sm + Smem::AT + (uint32_t)s * 16384u;
+        uint32_t v0[16], v1[16];
+        tc_ld16(taddr, v0);
+        tc_ld16(taddr + 16u, v1);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          tc_wait_ld(); reg_fence16(v0); reg_fence16(v1);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 ba = *reinterpret_cast<const float2*>(b2s + 32 * half + 2 * j);
+            const float2 bb = *reinterpret_cast<const float2*>(b2s + 32 * half + 16 + 2 * j);
+            pk[j] = cvt_relu_bf16x2(__uint_as_float(v0[2 * j]) + ba.x, __uint_as_float(v0[2 * j + 1]) + ba.y);
+            pk[8 + j] = cvt_relu_bf16x2(__uint_as_float(v1[2 * j]) + bb.x, __uint_as_float(v1[2 * j + 1]) + bb.y);
+          }
+          if (half == 0) { tc_ld16(taddr + 32u, v0); tc_ld16(taddr + 48u, v1); }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(arow + sw128_offset((uint32_t)vrow, (uint32_t)(4 * half + c))) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(bar(ACC1_EMPTY, s)); mbar_arrive(bar(A2_FULL, s)); }
+      }
+    } else {
+      const int64_t plane = (int64_t)a.h * a.w;
+      const int w = w_base + vrow;
+      for (int i = 0; i < my_rows; ++i) {
+        const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+        int n, t, h;
+        decode_row(i, n, t, h);
+        mbar_wait_sleep(bar(ACC2_FULL, s), ph);
+        tc_fence_after();
+        uint32_t r8[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r8[0]), "=r"(r8[1]), "=r"(r8[2]), "=r"(r8[3]), "=r"(r8[4]), "=r"(r8[5]), "=r"(r8[6]), "=r"(r8[7])
+                     : "r"(acc2 + lane_addr + (uint32_t)(s * 16)));
+        tc_wait_ld();
+        asm volatile("" : "+r"(r8[0]), "+r"(r8[1]), "+r"(r8[2]), "+r"(r8[3]), "+r"(r8[4]), "+r"(r8[5]), "+r"(r8[6]), "+r"(r8[7]));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(ACC2_EMPTY, s));
+        float o[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o[k] = __uint_as_float(r8[k]) + bhs[k];
+        if (w < a.w) {
+          float s0 = o[0], s1 = o[1];
+          if (a.out_kind == CLASFV_OUT_PROB) {
+            const float mx = fmaxf(s0, s1);
+            const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
+            const float inv = 1.f / (e0 + e1);
+            s0 = e0 * inv; s1 = e1 * inv;
+          }
+          const int64_t pix = (int64_t)h * a.w + w;
+          OutT* seg = static_cast<OutT*>(a.seg) + ((int64_t)n * 2 * a.t + t) * plane + pix;
+          put<OutT>(seg, s0);
+          put<OutT>(seg + (int64_t)a.t * plane, s1);
+          OutT* mot = static_cast<OutT*>(a.motion) + ((int64_t)n * 4 * a.t + t) * plane + pix;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float th;     // MUFU.TANH: |error| ~ 2^-11, below the bf16 resolution of everything upstream in this mode
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(o[2 + k]));
+            put<OutT>(mot + (int64_t)k * a.t * plane, th);
           }
         }
       }
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const uint32_t row = (uint32_t)(vg * 4 + v);
-        uint2 pk;
-        pk.x = pack_relu_bf16(f[v].x, f[v].y); pk.y = pack_relu_bf16(f[v].z, f[v].w);
-        *reinterpret_cast<uint2*>(sm + HeadSmem::A + sw128_offset(row, (uint32_t)(c4 >> 1)) + (uint32_t)((c4 & 1) * 8)) = pk;
-      }
     }
-    fence_async_smem();          // generic-proxy writes of A (and B) -> visible to the tensor core's async proxy
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- MMA 1: D[128 x 64] = A[128 x 64] * W2[64 x 64]^T
-    if (tid == 0) {
-      tc_fence_after();
+  } else {
+    // ================================================================ phase 1: R = (T,H)-interpolated rows, bf16, MN-major swizzled
+    const int ptid = (warp < 4 ? warp - 2 : warp - 14) * 32 + lane;       // 0 .. P1_THREADS-1
+    for (int i = 0; i < my_rows; ++i) {
+      const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      mbar_wait_sleep(bar(RAW_FULL, s), ph);
+      mbar_wait_sleep(bar(R_EMPTY, s), ph ^ 1u);          // MMA 0 of row i-2 has finished reading this R stage
+      const TilePlan& pl = plans[s];
+      const uint8_t* stage = sm + raw_off0 + (uint32_t)s * (uint32_t)g.raw_stage_bytes;
+      uint8_t* rst = sm + r_off + (uint32_t)s * r_stage_bytes;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_base, desc_a + (uint64_t)(2 * k), desc_b + (uint64_t)(2 * k), idesc1, k > 0 ? 1u : 0u);
-      tc_commit(bar);
-    }
-
-    // ---- mid: warp = (TMEM lane quarter q, 16-column chunk): h2 = relu(D + b2) -> bf16 -> A tile
-    mbar_wait(bar, phase);
-    tc_fence_after();
-    const int q = warp & 3, chunk = warp >> 2;
-    const int vrow = q * 32 + (tid & 31);
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    {
-      uint32_t acc[16];
-      tc_ld16(taddr + (uint32_t)(16 * chunk), acc);
-      tc_wait_ld();
-      uint32_t pk[8];
+      for (int l = 0; l < 4; ++l) {
+        float wgt[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        pk[j] = pack_relu_bf16(__uint_as_float(acc[2 * j]) + b2s[16 * chunk + 2 * j], __uint_as_float(acc[2 * j + 1]) + b2s[16 * chunk + 2 * j + 1]);
-      *reinterpret_cast<uint4*>(sm + HeadSmem::A + sw128_offset((uint32_t)vrow, (uint32_t)(2 * chunk))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(sm + HeadSmem::A + sw128_offset((uint32_t)vrow, (uint32_t)(2 * chunk + 1))) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();            // every warp has drained its accumulators: the same TMEM columns take the head outputs
-
-    // ---- MMA 2: D3[128 x 16] = relu(h2)[128 x 64] * Wh[16 x 64]^T
-    if (tid == 0) {
-      tc_fence_after();
+        for (int c = 0; c < 4; ++c) wgt[c] = pl.wgt[l][c];
+        const uint8_t* src = stage + g.raw_off[l];
+        const int items = g.nx[wt][l] * 8;
+        const uint32_t cstride = (uint32_t)g.nxmax[l] * 128u;
+        for (int it = ptid; it < items; it += P1_THREADS) {
+          const int x = it >> 3, j = it & 7;
+          float o[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_base, desc_a + (uint64_t)(2 * k), desc_b3 + (uint64_t)(2 * k), idesc2, k > 0 ? 1u : 0u);
-      tc_commit(bar3);
-    }
-
-    // ---- epilogue: the first warp of every lane quarter, thread = voxel
-    if (chunk == 0) {
-      mbar_wait(bar3, phase);
-      tc_fence_after();
-      uint32_t r8[8];
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                   : "=r"(r8[0]), "=r"(r8[1]), "=r"(r8[2]), "=r"(r8[3]), "=r"(r8[4]), "=r"(r8[5]), "=r"(r8[6]), "=r"(r8[7]) : "r"(taddr));
-      tc_wait_ld();
-      float o[6];
+          for (int e = 0; e < 8; ++e) o[e] = 0.f;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) o[k] = __uint_as_float(r8[k]) + bhs[k];
-      const int w = p.w_base + vrow;
-      if (w < a.w) {
-        float s0 = o[0], s1 = o[1];
-        if (a.out_kind == CLASFV_OUT_PROB) {
-          const float mx = fmaxf(s0, s1);
-          const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
-          const float inv = 1.f / (e0 + e1);
-          s0 = e0 * inv; s1 = e1 * inv;
+          for (int c = 0; c < 4; ++c) {
+            if (wgt[c] == 0.f) continue;
+            const uint4 r = *reinterpret_cast<const uint4*>(src + (uint32_t)c * cstride + (uint32_t)it * 16u);
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              o[2 * e] = fmaf(wgt[c], __uint_as_float(rr[e] << 16), o[2 * e]);
+              o[2 * e + 1] = fmaf(wgt[c], __uint_as_float(rr[e] & 0xffff0000u), o[2 * e + 1]);
+            }
+          }
+          const uint4 pk = make_uint4(cvt_bf16x2(o[0], o[1]), cvt_bf16x2(o[2], o[3]), cvt_bf16x2(o[4], o[5]), cvt_bf16x2(o[6], o[7]));
+          *reinterpret_cast<uint4*>(rst + sw128_offset((uint32_t)(g.koff[l] + x), (uint32_t)j)) = pk;
         }
-        const int64_t plane = (int64_t)a.h * a.w;
-        const int64_t pix = (int64_t)p.h * a.w + w;
-        OutT* seg = static_cast<OutT*>(a.seg) + ((int64_t)p.n * 2 * a.t + p.t) * plane + pix;
-        put<OutT>(seg, s0);
-        put<OutT>(seg + (int64_t)a.t * plane, s1);
-        OutT* mot = static_cast<OutT*>(a.motion) + ((int64_t)p.n * 4 * a.t + p.t) * plane + pix;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) put<OutT>(mot + (int64_t)k * a.t * plane, tanhf(o[2 + k]));
       }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(R_FULL, s)); mbar_arrive(bar(RAW_EMPTY, s)); }
     }
-    // the other warps run ahead into the next row's phase 1; MMA 1 of that row is issued only after two more
-    // __syncthreads, by which time the epilogue warps above have drained D3
   }
+
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -358,26 +468,41 @@ __global__ void __launch_bounds__(HU_THREADS, 2) head_umma_kernel(const HeadArgs
 
 int launch_head_umma(const HeadArgs& a, cudaStream_t stream) {
   CLASFV_REQUIRE(a.g_dtype == CLASFV_BF16 && a.w2_bf16, "head_umma: bf16 lateral maps and bf16 W2 required");
-  int rowbuf = 0, rawelems = 0;
-  for (int l = 0; l < 4; ++l) { rowbuf += a.wl[l] * ROW_PITCH; rawelems += (a.tl[l] == a.t ? 2 : 4) * a.wl[l] * HC; }
-  const size_t smem = 1024 + HeadSmem::ROWS + (size_t)rowbuf * sizeof(float) + (size_t)rawelems * sizeof(__nv_bfloat16);
-  static_assert(sizeof(TilePlan) * 2 <= HeadSmem::WTAP - HeadSmem::PLAN, "plan slots overflow");
-  static_assert(HeadSmem::TMEM + 4 <= HeadSmem::PLAN, "smem header overlap");
-  CLASFV_REQUIRE(smem <= 227 * 1024, "head_umma: frame too wide for the row buffers (W=%d)", a.w);
-  const int w_tiles = (a.w + 127) / 128;
-  const int64_t total = (int64_t)a.n * a.t * a.h * w_tiles;
+  HeadGeom g;
+  memset(&g, 0, sizeof(g));
+  g.w_tiles = (a.w + 127) / 128;
+  CLASFV_REQUIRE(g.w_tiles <= MAX_WT, "head_umma: frames wider than %d voxels are not supported (W=%d)", MAX_WT * 128, a.w);
+  for (int l = 0; l < 4; ++l) {
+    for (int wt = 0; wt < g.w_tiles; ++wt) {
+      const int v0 = wt * 128, v1 = std::min(a.w, v0 + 128) - 1;
+      const AxisTap t0 = axis_tap(v0, a.wl[l], a.w), t1 = axis_tap(v1, a.wl[l], a.w);
+      g.xlo[wt][l] = t0.i0; g.nx[wt][l] = t1.i1 - t0.i0 + 1;
+      g.nxmax[l] = std::max(g.nxmax[l], g.nx[wt][l]);
+    }
+  }
+  int k = 0, raw = 0;
+  for (int l = 0; l < 4; ++l) { g.koff[l] = k; k += g.nxmax[l]; g.raw_off[l] = raw; raw += (a.tl[l] == a.t ? 2 : 4) * g.nxmax[l] * 128; }
+  g.ktot = k + 2;                               // + the two bias rows
+  g.kpad = round_up(g.ktot, 16);
+  g.nslab = KSLABS;
+  g.raw_stage_bytes = raw;
+  CLASFV_REQUIRE(g.kpad <= KSLABS * 64, "head_umma: interpolation K too large (%d)", g.kpad);
+  const int64_t total = (int64_t)a.n * a.t * a.h;
   CLASFV_REQUIRE(total < (1ll << 31), "head_umma: too many rows");
+  g.total_rows = (int)total;
+  const size_t smem = 1024 + Smem::WA + (size_t)2 * g.nslab * 16384 + (size_t)2 * g.nslab * 8192 + (size_t)2 * g.raw_stage_bytes;
+  CLASFV_REQUIRE(smem <= 227 * 1024, "head_umma: shared memory overflow (%zu bytes, W=%d)", smem, a.w);
   int dev = 0, sms = 0;
   CLASFV_CUDA(cudaGetDevice(&dev));
   CLASFV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int per_sm = smem <= 113 * 1024 ? 2 : 1;
-  const int grid = (int)std::min<int64_t>(total, (int64_t)sms * per_sm);
+  int grid = (int)std::min<int64_t>(total * g.w_tiles, (int64_t)(sms / g.w_tiles) * g.w_tiles);
+  grid = std::max(grid / g.w_tiles, 1) * g.w_tiles;
   if (a.out_dtype == CLASFV_F32) {
     CLASFV_CUDA(cudaFuncSetAttribute(head_umma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_umma_kernel<float><<<grid, HU_THREADS, smem, stream>>>(a, w_tiles, (int)total, rowbuf);
+    head_umma_kernel<float><<<grid, HU_THREADS, smem, stream>>>(a, g);
   } else {
     CLASFV_CUDA(cudaFuncSetAttribute(head_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_umma_kernel<__nv_bfloat16><<<grid, HU_THREADS, smem, stream>>>(a, w_tiles, (int)total, rowbuf);
+    head_umma_kernel<__nv_bfloat16><<<grid, HU_THREADS, smem, stream>>>(a, g);
   }
   CLASFV_CUDA(cudaGetLastError());
   return CLASFV_OK;
