@@ -7,7 +7,7 @@
 // projected 64-channel maps g_l at 1/2, 1/4, 1/8, 1/16 resolution.
 //
 // One output row (n, t, h) of up to 128 voxels is one "tile".  For that row
-//   R_l[x, c] = sum over the <= 4 (T,H) corners  wT * wH * g_l[n, t_i, h_i, x, c]        (CUDA cores, "phase 1")
+//   R_l[x, c] = sum over the <= 4 (T,H) corners  wT * wH * g_l[n, t_i, h_i, x, c]        (CUDA cores, "phase 1", -> fp16)
 //   h1[v, c]  = relu( sum_l sum_x Wmat_l[v, x] * R_l[x, c] + b1[c] )                      (MMA 0)
 //   h2[v, c]  = relu( sum_k h1[v, k] * W2[c, k] + b2[c] )                                 (MMA 1)
 //   o[v, j]   = sum_k h2[v, k] * Wh[j, k] + bh[j]   -> softmax / tanh -> 6 planar stores   (MMA 2)
@@ -28,6 +28,8 @@
 #include "umma_ptx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cuda_fp16.h>
 
 namespace clasfv {
 namespace {
@@ -39,6 +41,7 @@ constexpr int HC = 64;
 constexpr int P1_WARPS = 10;
 constexpr int P1_THREADS = P1_WARPS * 32;
 constexpr int MAX_WT = 4;                 // w tiles of 128 voxels (W <= 512)
+ constexpr int NRAW = 3;                   // raw corner-row stages in flight
 constexpr int KSLABS = 2;                 // K of MMA 0 is always 2 slabs of 64 (interpolation columns + 2 bias rows, zero padded)
 
 struct AxisTap { int i0, i1; float l0, l1; };
@@ -66,6 +69,13 @@ __device__ __forceinline__ uint32_t cvt_relu_bf16x2(float a, float b) {
 __device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
   uint32_t d;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+
+// fp16 pair, saturating to the largest finite value instead of overflowing to infinity
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
   return d;
 }
 
@@ -110,19 +120,19 @@ struct Smem {                     // byte offsets from the 1024-aligned base
   static constexpr uint32_t WHB = W2B + 8192;             // 16 x 128 B   heads, K-major (rows 6..15 zero)
   static constexpr uint32_t B2 = WHB + 2048;              // [64] fp32
   static constexpr uint32_t BH = B2 + 256;                // [8] fp32
-  static constexpr uint32_t PLAN = BH + 32;               // 2 x TilePlan
-  static constexpr uint32_t BARS = PLAN + 2 * 64;         // 26 mbarriers
-  static constexpr uint32_t TMEM = BARS + 8 * 26;
+  static constexpr uint32_t PLAN = BH + 32;               // NRAW x TilePlan
+  static constexpr uint32_t BARS = PLAN + NRAW * 64;      // 13 groups of up to 4 mbarriers
+  static constexpr uint32_t TMEM = BARS + 8 * 52;
   static constexpr uint32_t AT = 11264;                   // 2 x (128 x 128 B)  A tile of MMA 1 / MMA 2
-  static constexpr uint32_t WA = AT + 2 * 16384;          // interpolation matrix: nslab hi slabs then nslab lo slabs of 16 KB
+  static constexpr uint32_t WA = AT + 2 * 16384;          // interpolation matrix (fp16): KSLABS slabs of 16 KB
   // then: R (2 stages x nslab x 8 KB), raw (2 stages x raw_stage_bytes)
 };
 static_assert(Smem::TMEM + 4 <= Smem::AT, "head smem header overflow");
 static_assert(sizeof(TilePlan) == 64, "plan slot size");
 
-enum Bar {  // index of the first of each pair of mbarriers (one per buffer stage)
-  RAW_FULL = 0, RAW_EMPTY = 2, R_FULL = 4, R_EMPTY = 6, ACC0_FULL = 8, ACC0_EMPTY = 10, A1_FULL = 12, A_EMPTY = 14,
-  ACC1_FULL = 16, ACC1_EMPTY = 18, A2_FULL = 20, ACC2_FULL = 22, ACC2_EMPTY = 24,
+enum Bar {  // index of the first mbarrier of each group (one per buffer stage, up to 4 stages)
+  RAW_FULL = 0, RAW_EMPTY = 4, R_FULL = 8, R_EMPTY = 12, ACC0_FULL = 16, ACC0_EMPTY = 20, A1_FULL = 24, A_EMPTY = 28,
+  ACC1_FULL = 32, ACC1_EMPTY = 36, A2_FULL = 40, ACC2_FULL = 44, ACC2_EMPTY = 48,
 };
 
 template <typename OutT>
@@ -136,7 +146,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   TilePlan* plans = reinterpret_cast<TilePlan*>(sm + Smem::PLAN);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + Smem::TMEM);
   auto bar = [&](int which, int s) { return sbase + Smem::BARS + 8u * (uint32_t)(which + s); };
-  const uint32_t wa_bytes = (uint32_t)(2 * g.nslab) * 16384u;
+  const uint32_t wa_bytes = (uint32_t)KSLABS * 16384u;
   const uint32_t r_stage_bytes = (uint32_t)g.nslab * 8192u;
   const uint32_t r_off = Smem::WA + wa_bytes;
   const uint32_t raw_off0 = r_off + 2u * r_stage_bytes;
@@ -152,8 +162,8 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
+    for (int s = 0; s < NRAW; ++s) { mbar_init(bar(RAW_FULL, s), 1); mbar_init(bar(RAW_EMPTY, s), P1_WARPS); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar(RAW_FULL, s), 1); mbar_init(bar(RAW_EMPTY, s), P1_WARPS);
       mbar_init(bar(R_FULL, s), P1_WARPS); mbar_init(bar(R_EMPTY, s), 1);
       mbar_init(bar(ACC0_FULL, s), 1); mbar_init(bar(ACC0_EMPTY, s), 4);
       mbar_init(bar(A1_FULL, s), 4); mbar_init(bar(A_EMPTY, s), 1);
@@ -188,12 +198,10 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   __syncthreads();
   {
     // interpolation matrix: element (voxel v, K column k) of slab k/64, hi and lo parts
+    // fp16 (11-bit significand, weights in [0,1]): 8x finer than the bf16 rounding of everything downstream
     auto put_w = [&](int v, int k, float w) {
-      const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-      const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
       const uint32_t o = (uint32_t)(k >> 6) * 16384u + sw128_offset((uint32_t)v, (uint32_t)((k & 63) >> 3)) + (uint32_t)(k & 7) * 2u;
-      *reinterpret_cast<__nv_bfloat16*>(sm + Smem::WA + o) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(sm + Smem::WA + (uint32_t)g.nslab * 16384u + o) = lo;
+      *reinterpret_cast<__half*>(sm + Smem::WA + o) = __float2half_rn(w);
     };
     for (int i = tid; i < 4 * 128; i += HU_THREADS) {
       const int l = i >> 7, v = i & 127;
@@ -208,10 +216,10 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     if (tid >= 640 && tid < 640 + 2 * HC) {
       const int c = (tid - 640) & 63, s = (tid - 640) >> 6;
       const float b = __ldg(a.b1 + c);
-      const __nv_bfloat16 hi = __float2bfloat16_rn(b), lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+      const __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
       const uint32_t base = r_off + (uint32_t)s * r_stage_bytes;
-      *reinterpret_cast<__nv_bfloat16*>(sm + base + sw128_offset((uint32_t)(g.ktot - 2), (uint32_t)(c >> 3)) + (uint32_t)(c & 7) * 2u) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(sm + base + sw128_offset((uint32_t)(g.ktot - 1), (uint32_t)(c >> 3)) + (uint32_t)(c & 7) * 2u) = lo;
+      *reinterpret_cast<__half*>(sm + base + sw128_offset((uint32_t)(g.ktot - 2), (uint32_t)(c >> 3)) + (uint32_t)(c & 7) * 2u) = hi;
+      *reinterpret_cast<__half*>(sm + base + sw128_offset((uint32_t)(g.ktot - 1), (uint32_t)(c >> 3)) + (uint32_t)(c & 7) * 2u) = lo;
     }
   }
   fence_async_smem();
@@ -221,11 +229,20 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc0 = tmem_base, acc1 = tmem_base + 128u, acc2 = tmem_base + 256u;   // 2 x 64, 2 x 64, 2 x 16 columns
 
-  auto decode_row = [&](int i, int& n, int& t, int& h) {
-    int r = row0 + i * row_step;
-    h = r % a.h; r /= a.h;
-    t = r % a.t; n = r / a.t;
+  // rows of this CTA: row0, row0 + row_step, ...; (n, t, h) advance by a fixed carry-propagated step (no divisions
+  // in the per-row paths: the producer's planning latency is on the critical path of the whole pipeline)
+  struct RowIter {
+    int n, t, h, dn, dt, dh, T, H;
+    __device__ __forceinline__ void next() {
+      h += dh; int c = h >= H ? 1 : 0; h -= c * H;
+      t += dt + c; c = t >= T ? 1 : 0; t -= c * T;
+      n += dn + c;
+    }
   };
+  RowIter it0;
+  it0.T = a.t; it0.H = a.h;
+  it0.h = row0 % a.h; it0.t = (row0 / a.h) % a.t; it0.n = row0 / (a.h * a.t);
+  it0.dh = row_step % a.h; it0.dt = (row_step / a.h) % a.t; it0.dn = row_step / (a.h * a.t);
 
   if (warp == 0) {
     // ================================================================ producer (lane = level * 4 + corner, 16 lanes)
@@ -235,16 +252,15 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     const int64_t clip_elems = (int64_t)a.tl[l] * a.hl[l] * a.wl[l] * HC, row_elems = (int64_t)a.wl[l] * HC;
     const uint32_t my_bytes = (uint32_t)g.nx[wt][l] * 128u;
     const uint32_t my_dst = sbase + raw_off0 + (uint32_t)g.raw_off[l] + (uint32_t)(c * g.nxmax[l]) * 128u;
-    for (int i = 0; i < my_rows; ++i) {
-      const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-      int n, t, h;
-      decode_row(i, n, t, h);
-      const AxisTap at = axis_tap(t, a.tl[l], a.t), ah = axis_tap(h, a.hl[l], a.h);
+    RowIter it = it0;
+    for (int i = 0; i < my_rows; ++i, it.next()) {
+      const int s = i % NRAW; const uint32_t ph = (uint32_t)(i / NRAW) & 1u;
+      const AxisTap at = axis_tap(it.t, a.tl[l], a.t), ah = axis_tap(it.h, a.hl[l], a.h);
       const float wg = ((c >> 1) ? at.l1 : at.l0) * ((c & 1) ? ah.l1 : ah.l0);
       const bool fetch = has_slot && wg != 0.f;
+      const __nv_bfloat16* src = gbase + it.n * clip_elems + ((int64_t)((c >> 1) ? at.i1 : at.i0) * a.hl[l] + ((c & 1) ? ah.i1 : ah.i0)) * row_elems;
       const uint32_t bytes = __reduce_add_sync(0xffffffffu, fetch ? my_bytes : 0u);
-      const __nv_bfloat16* src = gbase + n * clip_elems + ((int64_t)((c >> 1) ? at.i1 : at.i0) * a.hl[l] + ((c & 1) ? ah.i1 : ah.i0)) * row_elems;
-      mbar_wait_sleep(bar(RAW_EMPTY, s), ph ^ 1u);
+      mbar_wait(bar(RAW_EMPTY, s), ph ^ 1u);
       if (lane < 16) plans[s].wgt[l][c] = fetch ? wg : 0.f;
       __syncwarp();
       if (lane == 0) mbar_arrive_expect_tx(bar(RAW_FULL, s), bytes);
@@ -255,52 +271,63 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc0 = idesc_bf16_f32(128, 64) | (1u << 16);      // B (= R) is MN-major
-      const uint32_t idesc1 = idesc_bf16_f32(128, 64), idesc2 = idesc_bf16_f32(128, 16);
-      const uint64_t desc_w2 = smem_desc_sw128(sbase + Smem::W2B), desc_wh = smem_desc_sw128(sbase + Smem::WHB);
-      const uint64_t desc_wa = smem_desc_sw128(sbase + Smem::WA), desc_r = smem_desc_sw128(sbase + r_off);
-      const uint64_t desc_at = smem_desc_sw128(sbase + Smem::AT);
-      for (int k = 0; k < my_rows + 2; ++k) {
-        if (k < my_rows) {
-          const int s = k & 1; const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-          mbar_wait(bar(R_FULL, s), ph);
-          mbar_wait(bar(ACC0_EMPTY, s), ph ^ 1u);
-          tc_fence_after();
-          // K is always 2 slabs = 128 (zero rows / columns beyond ktot): 16 instructions with constant descriptor
-          // offsets, nothing to compute in this single-thread critical path.  MN-major B: 16 K rows of 128 bytes
-          // per instruction = two 8-row swizzle atoms (SBO = 1024), so K advances by 2048 bytes = 128 descriptor units.
-          const uint64_t db0 = desc_r + (uint64_t)(s * (int)(KSLABS * 8192 / 16));
+    // The whole warp runs this loop (uniform control flow, so descriptors live in uniform registers); only the
+    // tcgen05 instructions themselves are issued by one elected lane.
+    // MMA 0: A = fp16 interpolation weights, B = R in fp16 (formats 0; the hardware rejects mixed f16 x bf16 operands),
+    // MN-major B, fp32 accumulate
+    const uint32_t idesc0 = (idesc_bf16_f32(128, 64) & ~((7u << 7) | (7u << 10))) | (1u << 16);
+    const uint32_t idesc1 = idesc_bf16_f32(128, 64), idesc2 = idesc_bf16_f32(128, 16);
+    const uint64_t desc_w2 = smem_desc_sw128(sbase + Smem::W2B), desc_wh = smem_desc_sw128(sbase + Smem::WHB);
+    const uint64_t desc_wa = smem_desc_sw128(sbase + Smem::WA), desc_r = smem_desc_sw128(sbase + r_off);
+    const uint64_t desc_at = smem_desc_sw128(sbase + Smem::AT);
+    for (int k = 0; k < my_rows + 2; ++k) {
+      if (k < my_rows) {
+        const int s = k & 1; const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+        mbar_wait(bar(R_FULL, s), ph);
+        mbar_wait(bar(ACC0_EMPTY, s), ph ^ 1u);
+        tc_fence_after();
+        // K is always 2 slabs = 128 (zero rows / columns beyond ktot): 16 instructions with constant descriptor
+        // offsets.  MN-major B: 16 K rows of 128 bytes per instruction = two 8-row swizzle atoms (SBO = 1024), so K
+        // advances by 2048 bytes = 128 descriptor units.
+        const uint64_t db0 = desc_r + (uint64_t)(s * (int)(KSLABS * 8192 / 16));
+        const uint32_t d0 = acc0 + (uint32_t)(s * 64);
+        if (elect_one()) {
 #pragma unroll
-          for (int part = 0; part < 2; ++part)           // hi weights, then lo weights, against the same R
-#pragma unroll
-            for (int kk = 0; kk < KSLABS * 4; ++kk)
-              tc_mma_bf16(acc0 + (uint32_t)(s * 64), desc_wa + (uint64_t)((part * KSLABS + (kk >> 2)) * 1024 + 2 * (kk & 3)),
-                          db0 + (uint64_t)(kk * 128), idesc0, (part | kk) ? 1u : 0u);
+          for (int kk = 0; kk < KSLABS * 4; ++kk)
+            tc_mma_bf16(d0, desc_wa + (uint64_t)((kk >> 2) * 1024 + 2 * (kk & 3)), db0 + (uint64_t)(kk * 128), idesc0, kk ? 1u : 0u);
           tc_commit(bar(R_EMPTY, s));
           tc_commit(bar(ACC0_FULL, s));
         }
-        if (k >= 1 && k <= my_rows) {
-          const int j = k - 1, s = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-          mbar_wait(bar(A1_FULL, s), ph);
-          mbar_wait(bar(ACC1_EMPTY, s), ph ^ 1u);
-          tc_fence_after();
-          const uint64_t da = desc_at + (uint64_t)(s * 1024);
+        __syncwarp();
+      }
+      if (k >= 1 && k <= my_rows) {
+        const int j = k - 1, s = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        mbar_wait(bar(A1_FULL, s), ph);
+        mbar_wait(bar(ACC1_EMPTY, s), ph ^ 1u);
+        tc_fence_after();
+        const uint64_t da = desc_at + (uint64_t)(s * 1024);
+        const uint32_t d1 = acc1 + (uint32_t)(s * 64);
+        if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(acc1 + (uint32_t)(s * 64), da + (uint64_t)(2 * kk), desc_w2 + (uint64_t)(2 * kk), idesc1, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(d1, da + (uint64_t)(2 * kk), desc_w2 + (uint64_t)(2 * kk), idesc1, kk > 0 ? 1u : 0u);
           tc_commit(bar(ACC1_FULL, s));
         }
-        if (k >= 2) {
-          const int j = k - 2, s = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-          mbar_wait(bar(A2_FULL, s), ph);
-          mbar_wait(bar(ACC2_EMPTY, s), ph ^ 1u);
-          tc_fence_after();
-          const uint64_t da = desc_at + (uint64_t)(s * 1024);
+        __syncwarp();
+      }
+      if (k >= 2) {
+        const int j = k - 2, s = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        mbar_wait(bar(A2_FULL, s), ph);
+        mbar_wait(bar(ACC2_EMPTY, s), ph ^ 1u);
+        tc_fence_after();
+        const uint64_t da = desc_at + (uint64_t)(s * 1024);
+        const uint32_t d2 = acc2 + (uint32_t)(s * 16);
+        if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(acc2 + (uint32_t)(s * 16), da + (uint64_t)(2 * kk), desc_wh + (uint64_t)(2 * kk), idesc2, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(d2, da + (uint64_t)(2 * kk), desc_wh + (uint64_t)(2 * kk), idesc2, kk > 0 ? 1u : 0u);
           tc_commit(bar(A_EMPTY, s));
           tc_commit(bar(ACC2_FULL, s));
         }
+        __syncwarp();
       }
     }
   } else if (warp >= 4 && warp < 16) {
@@ -372,10 +399,10 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     } else {
       const int64_t plane = (int64_t)a.h * a.w;
       const int w = w_base + vrow;
-      for (int i = 0; i < my_rows; ++i) {
+      RowIter it = it0;
+      for (int i = 0; i < my_rows; ++i, it.next()) {
         const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-        int n, t, h;
-        decode_row(i, n, t, h);
+        const int n = it.n, t = it.t, h = it.h;
         mbar_wait_sleep(bar(ACC2_FULL, s), ph);
         tc_fence_after();
         uint32_t r8[8];
@@ -417,10 +444,11 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     const int ptid = (warp < 4 ? warp - 2 : warp - 14) * 32 + lane;       // 0 .. P1_THREADS-1
     for (int i = 0; i < my_rows; ++i) {
       const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-      mbar_wait_sleep(bar(RAW_FULL, s), ph);
+      const int rs = i % NRAW; const uint32_t rph = (uint32_t)(i / NRAW) & 1u;
+      mbar_wait_sleep(bar(RAW_FULL, rs), rph);
       mbar_wait_sleep(bar(R_EMPTY, s), ph ^ 1u);          // MMA 0 of row i-2 has finished reading this R stage
-      const TilePlan& pl = plans[s];
-      const uint8_t* stage = sm + raw_off0 + (uint32_t)s * (uint32_t)g.raw_stage_bytes;
+      const TilePlan& pl = plans[rs];
+      const uint8_t* stage = sm + raw_off0 + (uint32_t)rs * (uint32_t)g.raw_stage_bytes;
       uint8_t* rst = sm + r_off + (uint32_t)s * r_stage_bytes;
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
@@ -446,13 +474,13 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
               o[2 * e + 1] = fmaf(wgt[c], __uint_as_float(rr[e] & 0xffff0000u), o[2 * e + 1]);
             }
           }
-          const uint4 pk = make_uint4(cvt_bf16x2(o[0], o[1]), cvt_bf16x2(o[2], o[3]), cvt_bf16x2(o[4], o[5]), cvt_bf16x2(o[6], o[7]));
+          const uint4 pk = make_uint4(cvt_f16x2_sat(o[0], o[1]), cvt_f16x2_sat(o[2], o[3]), cvt_f16x2_sat(o[4], o[5]), cvt_f16x2_sat(o[6], o[7]));
           *reinterpret_cast<uint4*>(rst + sw128_offset((uint32_t)(g.koff[l] + x), (uint32_t)j)) = pk;
         }
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(bar(R_FULL, s)); mbar_arrive(bar(RAW_EMPTY, s)); }
+      if (lane == 0) { mbar_arrive(bar(R_FULL, s)); mbar_arrive(bar(RAW_EMPTY, rs)); }
     }
   }
 
@@ -490,7 +518,7 @@ int launch_head_umma(const HeadArgs& a, cudaStream_t stream) {
   const int64_t total = (int64_t)a.n * a.t * a.h;
   CLASFV_REQUIRE(total < (1ll << 31), "head_umma: too many rows");
   g.total_rows = (int)total;
-  const size_t smem = 1024 + Smem::WA + (size_t)2 * g.nslab * 16384 + (size_t)2 * g.nslab * 8192 + (size_t)2 * g.raw_stage_bytes;
+  const size_t smem = 1024 + Smem::WA + (size_t)KSLABS * 16384 + (size_t)2 * KSLABS * 8192 + (size_t)NRAW * g.raw_stage_bytes;
   CLASFV_REQUIRE(smem <= 227 * 1024, "head_umma: shared memory overflow (%zu bytes, W=%d)", smem, a.w);
   int dev = 0, sms = 0;
   CLASFV_CUDA(cudaGetDevice(&dev));
