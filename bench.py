@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
-    ap.add_argument("--batch-clips", type=int, default=int(os.environ.get("CLASFV_BATCH_CLIPS", "16")))
+    ap.add_argument("--batch-clips", type=int, default=int(os.environ.get("CLASFV_BATCH_CLIPS", "64")))
     ap.add_argument("--precision", default="bf16", choices=("bf16", "fp32"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-clip", action="store_true", help="disable the dense-video schedule (every clip runs the whole trunk)")

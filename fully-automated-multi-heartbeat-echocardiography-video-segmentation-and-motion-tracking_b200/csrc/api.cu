@@ -102,7 +102,7 @@ struct clasfv_handle {
   int cur_stage = 0;
   double prof_gflop[4] = {0, 0, 0, 0};
   // options (clasfv_set_option)
-  int sub_batch = 16;          // clips per internal batch of clasfv_forward
+  int sub_batch = 32;          // clips per internal batch of clasfv_forward
   bool dense_video = true;     // share layer-1 work between overlapping windows of one video (bf16 tensor-core path)
 };
 

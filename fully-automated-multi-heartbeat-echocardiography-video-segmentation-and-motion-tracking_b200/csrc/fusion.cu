@@ -8,6 +8,10 @@
 //   divide_to_consecutive_clips      src/fuse_utils.py:16-33        temporal resample, align_corners=False
 //   segment_a_video_with_fusion      src/fuse_utils.py:70-98        resample back, argmax, per-frame vote
 #include "internal.h"
+#include "umma_ptx.cuh"
+
+#include <algorithm>
+#include <cstdlib>
 
 namespace clasfv {
 namespace {
@@ -164,6 +168,186 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
   if (a.cnt && blockIdx.x == 0 && threadIdx.x == 0) a.cnt[g] = (a.accumulate ? a.cnt[g] : 0) + votes;
 }
 
+// ------------------------------------------------------------------------------------------- F2, staged
+// The same operator with the gather sources staged in shared memory.  warp_fuse_kernel above is bound by the
+// L1/LSU pipe (16 scattered global loads per clip and pixel); here a CTA owns one output frame g and one slice of
+// its pixels, and for every hop (clip c, source frame ts) landing on g a producer warp bulk-copies the two class
+// planes prob[c, :, ts] (contiguous H*W elements each) into a ring of shared-memory units (mbarrier full / empty).
+// Consumer threads own fixed pixel pairs for the whole CTA lifetime: running sums live in registers, flow and direct
+// votes are read from global memory as coalesced pair loads, and the eight bilinear taps of a hop are LDS.  The
+// order of additions per pixel is exactly warp_fuse_kernel's (clip by clip: direct, forward hop, backward hop), so
+// both kernels give bit-identical sums.  No float atomics, no intermediate warped volume.
+constexpr int WS_THREADS = 1024;
+constexpr int WS_CONSUMERS = WS_THREADS - 32;       // warp 0 is the producer
+constexpr int WS_PAIRS = 4;                         // pixel pairs per consumer thread
+constexpr int WS_MAX_UNITS = 8;
+
+template <typename T> struct Pair;
+template <> struct Pair<float> {
+  static __device__ __forceinline__ float2 ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+};
+template <> struct Pair<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) {
+    const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(p));
+    return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
+  }
+};
+template <typename T> __device__ __forceinline__ float lds_val(const T* p);
+template <> __device__ __forceinline__ float lds_val<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float lds_val<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+template <typename T>
+__device__ __forceinline__ float bilinear_fetch_smem(const T* plane, const Bilinear& b, int w) {
+  const T* p = plane + b.y0 * w + b.x0;
+  float v = lds_val<T>(p) * b.nw;
+  if (b.x1ok) v += lds_val<T>(p + 1) * b.ne;
+  if (b.y1ok) v += lds_val<T>(p + w) * b.sw;
+  if (b.x1ok && b.y1ok) v += lds_val<T>(p + w + 1) * b.se;
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const WarpFuseArgs a, int n_units, int slice_pix) {
+  extern __shared__ __align__(128) uint8_t ws_smem[];
+  using namespace ptx;
+  const int g = blockIdx.y;
+  const int hw = a.h * a.w;
+  const int L = a.clip_len;
+  const uint32_t plane_bytes = (uint32_t)hw * (uint32_t)sizeof(T);
+  const uint32_t unit_bytes = 2u * plane_bytes;
+  const uint32_t sbase = smem_u32(ws_smem);
+  const uint32_t bar0 = sbase + (uint32_t)n_units * unit_bytes;         // full[u] at bar0 + 8u, empty[u] at bar0 + 8(n_units + u)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* __restrict__ prob = static_cast<const T*>(a.prob);
+  const T* __restrict__ mot = static_cast<const T*>(a.motion);
+  const int lo = __ldg(a.frame_lo + g), hi = __ldg(a.frame_hi + g);
+
+  if (threadIdx.x == 0) {
+    for (int u = 0; u < n_units; ++u) { mbar_init(bar0 + 8u * u, 1); mbar_init(bar0 + 8u * (n_units + u), WS_CONSUMERS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer: one bulk copy per class plane of every hop
+    if (lane == 0) {
+      int item = 0;
+      for (int c = lo; c < hi; ++c) {
+        const int t = g - __ldg(a.clip_start + c);
+        const T* pc = prob + (int64_t)c * 2 * L * hw;
+        for (int hop = 0; hop < 2; ++hop) {
+          const int ts = hop == 0 ? t - 1 : t + 1;
+          const bool on = ts >= 0 && ts < L && (a.edge_hops || (hop == 0 ? ts + 1 < L : ts >= 1));
+          if (!on) continue;
+          const int u = item % n_units; const uint32_t ph = (uint32_t)(item / n_units) & 1u;
+          mbar_wait(bar0 + 8u * (n_units + u), ph ^ 1u);
+          mbar_arrive_expect_tx(bar0 + 8u * u, unit_bytes);
+          const uint32_t dst = sbase + (uint32_t)u * unit_bytes;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst), "l"(pc + (int64_t)ts * hw), "r"(plane_bytes), "r"(bar0 + 8u * u) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst + plane_bytes), "l"(pc + (int64_t)(L + ts) * hw), "r"(plane_bytes), "r"(bar0 + 8u * u) : "memory");
+          ++item;
+        }
+      }
+    }
+    // the producer warp also owns the vote count of the frame
+    if (lane == 1 && a.cnt && blockIdx.x == 0) {
+      int votes = 0;
+      for (int c = lo; c < hi; ++c) {
+        const int t = g - __ldg(a.clip_start + c);
+        if (t >= 0 && t < L) ++votes;
+        int ts = t - 1;
+        if (ts >= 0 && ts < L && (a.edge_hops || ts + 1 < L)) ++votes;
+        ts = t + 1;
+        if (ts >= 0 && ts < L && (a.edge_hops || ts >= 1)) ++votes;
+      }
+      a.cnt[g] = (a.accumulate ? a.cnt[g] : 0) + votes;
+    }
+  } else {
+    // ---------------------------------------------------------------- consumers: fixed pixel pairs, sums in registers
+    const int ctid = threadIdx.x - 32;
+    const int pix0 = blockIdx.x * slice_pix;
+    const int pix_end = min(hw, pix0 + slice_pix);
+    int px[WS_PAIRS];
+    float bx0[WS_PAIRS], bx1[WS_PAIRS], by[WS_PAIRS];
+    float s0[2 * WS_PAIRS], s1[2 * WS_PAIRS];
+    float* acc = a.acc + (int64_t)g * 2 * hw;
+#pragma unroll
+    for (int k = 0; k < WS_PAIRS; ++k) {
+      const int p = pix0 + 2 * (ctid + k * WS_CONSUMERS);
+      px[k] = p < pix_end ? p : -1;
+      const int i = p < pix_end ? p / a.w : 0, j = p < pix_end ? p % a.w : 0;     // W is even: a pair never straddles rows
+      bx0[k] = linspace_pm1(j, a.w); bx1[k] = linspace_pm1(j + 1 < a.w ? j + 1 : j, a.w); by[k] = linspace_pm1(i, a.h);
+      s0[2 * k] = s0[2 * k + 1] = s1[2 * k] = s1[2 * k + 1] = 0.f;
+      if (a.accumulate && px[k] >= 0) {
+        const float2 o0 = *reinterpret_cast<const float2*>(acc + p), o1 = *reinterpret_cast<const float2*>(acc + hw + p);
+        s0[2 * k] = o0.x; s0[2 * k + 1] = o0.y; s1[2 * k] = o1.x; s1[2 * k + 1] = o1.y;
+      }
+    }
+    int item = 0;
+    for (int c = lo; c < hi; ++c) {
+      const int t = g - __ldg(a.clip_start + c);
+      const T* pc = prob + (int64_t)c * 2 * L * hw;
+      const T* mc = mot + (int64_t)c * 4 * L * hw;
+      if (t >= 0 && t < L) {                                   // direct vote
+#pragma unroll
+        for (int k = 0; k < WS_PAIRS; ++k) {
+          if (px[k] < 0) continue;
+          const float2 v0 = Pair<T>::ld(pc + (int64_t)t * hw + px[k]), v1 = Pair<T>::ld(pc + (int64_t)(L + t) * hw + px[k]);
+          s0[2 * k] += v0.x; s0[2 * k + 1] += v0.y; s1[2 * k] += v1.x; s1[2 * k + 1] += v1.y;
+        }
+      }
+#pragma unroll
+      for (int hop = 0; hop < 2; ++hop) {
+        const int ts = hop == 0 ? t - 1 : t + 1;
+        const bool on = ts >= 0 && ts < L && (a.edge_hops || (hop == 0 ? ts + 1 < L : ts >= 1));
+        if (!on) continue;
+        const T* fxp = mc + (int64_t)((hop == 0 ? 0 : 2 * L) + ts) * hw;
+        const T* fyp = mc + (int64_t)((hop == 0 ? L : 3 * L) + ts) * hw;
+        float2 fx[WS_PAIRS], fy[WS_PAIRS];
+#pragma unroll
+        for (int k = 0; k < WS_PAIRS; ++k)
+          if (px[k] >= 0) { fx[k] = Pair<T>::ld(fxp + px[k]); fy[k] = Pair<T>::ld(fyp + px[k]); }
+        const int u = item % n_units; const uint32_t ph = (uint32_t)(item / n_units) & 1u;
+        mbar_wait(bar0 + 8u * u, ph);
+        const T* u0 = reinterpret_cast<const T*>(ws_smem + (size_t)u * unit_bytes);
+        const T* u1 = u0 + hw;
+#pragma unroll
+        for (int k = 0; k < WS_PAIRS; ++k) {
+          if (px[k] < 0) continue;
+          const Bilinear ba = bilinear_setup_base(bx0[k], by[k], fx[k].x, fy[k].x, a.h, a.w);
+          s0[2 * k] += bilinear_fetch_smem<T>(u0, ba, a.w);
+          s1[2 * k] += bilinear_fetch_smem<T>(u1, ba, a.w);
+          const Bilinear bb = bilinear_setup_base(bx1[k], by[k], fx[k].y, fy[k].y, a.h, a.w);
+          s0[2 * k + 1] += bilinear_fetch_smem<T>(u0, bb, a.w);
+          s1[2 * k + 1] += bilinear_fetch_smem<T>(u1, bb, a.w);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8u * (n_units + u));
+        ++item;
+      }
+    }
+    int lv_count = 0;
+#pragma unroll
+    for (int k = 0; k < WS_PAIRS; ++k) {
+      if (px[k] < 0) continue;
+      const int p = px[k];
+      *reinterpret_cast<float2*>(acc + p) = make_float2(s0[2 * k], s0[2 * k + 1]);
+      *reinterpret_cast<float2*>(acc + hw + p) = make_float2(s1[2 * k], s1[2 * k + 1]);
+      const int m0 = s1[2 * k] > s0[2 * k] ? 1 : 0, m1 = s1[2 * k + 1] > s0[2 * k + 1] ? 1 : 0;
+      lv_count += m0 + m1;
+      if (a.mask) *reinterpret_cast<uchar2*>(a.mask + (int64_t)g * hw + p) = make_uchar2((unsigned char)m0, (unsigned char)m1);
+    }
+    if (a.area) {
+      lv_count = __reduce_add_sync(0xffffffffu, lv_count);
+      if (lane == 0 && lv_count) atomicAdd(a.area + g, lv_count);
+    }
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------- F1
 struct Lerp { int i0, i1; float l0, l1; };
 // PyTorch linear resample, align_corners=False: src = max(scale*(dst+0.5)-0.5, 0)
@@ -282,6 +466,35 @@ int launch_motion_field(const float* flow, float* grid_out, int n, int h, int w,
 
 int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
   if (a.area) CLASFV_CUDA(cudaMemsetAsync(a.area, 0, sizeof(int32_t) * a.t_out, s));
+  // staged kernel: needs at least two ring units of two class planes in shared memory, an even width (pixel pairs)
+  // and 16-byte aligned planes (bulk copies); otherwise the direct-gather kernel runs
+  {
+    const int64_t hw = (int64_t)a.h * a.w;
+    const size_t es = a.dtype == CLASFV_F32 ? 4 : 2;
+    const size_t unit = 2 * (size_t)hw * es;
+    const size_t budget = 225 * 1024;
+    int units = (int)std::min<size_t>((budget - 16 * WS_MAX_UNITS) / unit, (size_t)WS_MAX_UNITS);
+    static const bool no_staged = getenv("CLASFV_WARP_FUSE_DIRECT") != nullptr;
+    const bool aligned = (hw * es) % 16 == 0 && a.w % 2 == 0 && ((uintptr_t)a.prob % 16) == 0 && ((uintptr_t)a.acc % 8) == 0 &&
+                         (!a.mask || ((uintptr_t)a.mask % 2) == 0);
+    if (units >= 2 && aligned && !no_staged) {
+      const int per_cta = WS_CONSUMERS * 2 * WS_PAIRS;
+      const int slices = (int)cdiv(hw, per_cta);
+      int slice_pix = (int)cdiv(hw, slices);
+      slice_pix += slice_pix & 1;                           // even: pixel pairs
+      const size_t smem = (size_t)units * unit + 16 * (size_t)units;
+      dim3 grid((unsigned)slices, (unsigned)a.t_out);
+      if (a.dtype == CLASFV_F32) {
+        CLASFV_CUDA(cudaFuncSetAttribute(warp_fuse_staged_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        warp_fuse_staged_kernel<float><<<grid, WS_THREADS, smem, s>>>(a, units, slice_pix);
+      } else {
+        CLASFV_CUDA(cudaFuncSetAttribute(warp_fuse_staged_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        warp_fuse_staged_kernel<__nv_bfloat16><<<grid, WS_THREADS, smem, s>>>(a, units, slice_pix);
+      }
+      CLASFV_CUDA(cudaGetLastError());
+      return CLASFV_OK;
+    }
+  }
   dim3 grid((unsigned)cdiv((int64_t)a.h * a.w, WF_THREADS), (unsigned)a.t_out);
   if (a.dtype == CLASFV_F32) warp_fuse_kernel<float><<<grid, WF_THREADS, 0, s>>>(a);
   else warp_fuse_kernel<__nv_bfloat16><<<grid, WF_THREADS, 0, s>>>(a);

@@ -112,7 +112,7 @@ class Engine:
                                       _lib.torch_dtype_code(seg.dtype), seg.data_ptr(), mot.data_ptr(),
                                       _lib.current_stream_ptr(x.device)), "clasfv_forward")
 
-    def forward_windows(self, video, seg, mot, out_kind, clip_starts, clip_len, batch_clips=16):
+    def forward_windows(self, video, seg, mot, out_kind, clip_starts, clip_len, batch_clips=64):
         """All windows [s, s+clip_len) of a resident video (3,Tv,H,W) in as few calls as possible: every maximal run
         of equally spaced starts is ONE clasfv_forward call, so the library can share the stem and layer1 between
         the overlapping windows (dense-video schedule) and batches internally (``batch_clips`` per batch)."""

@@ -118,7 +118,7 @@ def exchange_partials(acc, cnt, window, owners, group=None):
     return acc_own, cnt_own
 
 
-def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=16, group=None, gather=True):
+def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=32, group=None, gather=True):
     """One long video (3,T,H,W) split by clip range across the ranks of ``group`` (BASELINE config 5).
     Every rank passes the same video; returns the full (T,H,W) int64 mask on every rank when ``gather``,
     else (owned mask, (f0, f1))."""

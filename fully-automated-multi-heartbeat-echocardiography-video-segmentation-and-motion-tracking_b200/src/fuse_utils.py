@@ -105,7 +105,7 @@ def plan_shifts(num_frames, step=1, num_clips=10):
 
 
 def segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num_clips=10,
-                                fuse_method="simple", class_list=[0, 1], batch_clips=16, edge_hops=False,
+                                fuse_method="simple", class_list=[0, 1], batch_clips=64, edge_hops=False,
                                 return_details=False):
     net = _unwrap(model)
     eng = net.engine()

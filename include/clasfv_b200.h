@@ -84,7 +84,7 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
                    void* seg_dev, void* motion_dev, void* stream);
 
 /* Options of a handle (no reference counterpart):
- *   "sub_batch"    clips per internal batch of clasfv_forward (default 16): a call with more clips is processed
+ *   "sub_batch"    clips per internal batch of clasfv_forward (default 32): a call with more clips is processed
  *                  batch by batch inside one workspace
  *   "dense_video"  0/1 (default 1).  When the clips of a call are equally spaced windows (1..8 frames apart) of one
  *                  resident video, bf16 tensor-core mode, N >= 4, T >= 16: the stem and layer1 are evaluated once over

@@ -275,7 +275,7 @@ def test_dense_video_schedule_is_bit_identical_to_per_clip(net_bf16, tv, clip_le
         torch.cuda.synchronize()
         outs.append((seg.float().cpu(), mot.float().cpu()))
     eng.set_option("dense_video", 1)
-    eng.set_option("sub_batch", 16)
+    eng.set_option("sub_batch", 32)
     assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[0][1]).all()
     assert torch.equal(outs[0][0], outs[1][0]), float((outs[0][0] - outs[1][0]).abs().max())
     assert torch.equal(outs[0][1], outs[1][1]), float((outs[0][1] - outs[1][1]).abs().max())
