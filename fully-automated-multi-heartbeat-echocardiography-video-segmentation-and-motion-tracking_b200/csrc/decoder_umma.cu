@@ -41,7 +41,7 @@ constexpr int HC = 64;
 constexpr int P1_WARPS = 10;
 constexpr int P1_THREADS = P1_WARPS * 32;
 constexpr int MAX_WT = 4;                 // w tiles of 128 voxels (W <= 512)
- constexpr int NRAW = 3;                   // raw corner-row stages in flight
+constexpr int NRAW = 3;                   // raw corner-row stages in flight (2 when 3 do not fit shared memory)
 constexpr int KSLABS = 2;                 // K of MMA 0 is always 2 slabs of 64 (interpolation columns + 2 bias rows, zero padded)
 
 struct AxisTap { int i0, i1; float l0, l1; };
@@ -111,6 +111,8 @@ struct HeadGeom {                 // host-computed layout of the K axis of MMA 0
                                   // when the level is at the output's temporal resolution and only its H corners exist)
   int raw_stage_bytes;
   int total_rows;                 // n * t * h
+  int nraw;                       // raw stages actually used (2 or NRAW)
+  int wt_vox;                     // voxels per w tile (128, or fewer when the tile's interpolation columns would exceed K)
 };
 
 struct TilePlan { float wgt[4][4]; };   // weight of each (T,H) corner per level, [level][2*tc + hc]; 0 = corner not fetched
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
 
   const int wt = blockIdx.x % g.w_tiles;
   const int row0 = blockIdx.x / g.w_tiles, row_step = gridDim.x / g.w_tiles;
-  const int w_base = wt * 128;
+  const int w_base = wt * g.wt_vox;
   const int my_rows = row0 < g.total_rows ? (g.total_rows - row0 + row_step - 1) / row_step : 0;
 
   // ------------------------------------------------------------------ one-time setup (all threads)
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     };
     for (int i = tid; i < 4 * 128; i += HU_THREADS) {
       const int l = i >> 7, v = i & 127;
-      if (w_base + v < a.w) {
+      if (v < g.wt_vox && w_base + v < a.w) {
         const AxisTap aw = axis_tap(w_base + v, a.wl[l], a.w);
         put_w(v, g.koff[l] + aw.i0 - g.xlo[wt][l], aw.l0);
         if (aw.l1 != 0.f) put_w(v, g.koff[l] + aw.i1 - g.xlo[wt][l], aw.l1);
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     const uint32_t my_dst = sbase + raw_off0 + (uint32_t)g.raw_off[l] + (uint32_t)(c * g.nxmax[l]) * 128u;
     RowIter it = it0;
     for (int i = 0; i < my_rows; ++i, it.next()) {
-      const int s = i % NRAW; const uint32_t ph = (uint32_t)(i / NRAW) & 1u;
+      const int s = i % g.nraw; const uint32_t ph = (uint32_t)(i / g.nraw) & 1u;
       const AxisTap at = axis_tap(it.t, a.tl[l], a.t), ah = axis_tap(it.h, a.hl[l], a.h);
       const float wg = ((c >> 1) ? at.l1 : at.l0) * ((c & 1) ? ah.l1 : ah.l0);
       const bool fetch = has_slot && wg != 0.f;
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
         float o[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) o[k] = __uint_as_float(r8[k]) + bhs[k];
-        if (w < a.w) {
+        if (vrow < g.wt_vox && w < a.w) {
           float s0 = o[0], s1 = o[1];
           if (a.out_kind == CLASFV_OUT_PROB) {
             const float mx = fmaxf(s0, s1);
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     const int ptid = (warp < 4 ? warp - 2 : warp - 14) * 32 + lane;       // 0 .. P1_THREADS-1
     for (int i = 0; i < my_rows; ++i) {
       const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-      const int rs = i % NRAW; const uint32_t rph = (uint32_t)(i / NRAW) & 1u;
+      const int rs = i % g.nraw; const uint32_t rph = (uint32_t)(i / g.nraw) & 1u;
       mbar_wait_sleep(bar(RAW_FULL, rs), rph);
       mbar_wait_sleep(bar(R_EMPTY, s), ph ^ 1u);          // MMA 0 of row i-2 has finished reading this R stage
       const TilePlan& pl = plans[rs];
@@ -498,16 +500,21 @@ int launch_head_umma(const HeadArgs& a, cudaStream_t stream) {
   CLASFV_REQUIRE(a.g_dtype == CLASFV_BF16 && a.w2_bf16, "head_umma: bf16 lateral maps and bf16 W2 required");
   HeadGeom g;
   memset(&g, 0, sizeof(g));
-  g.w_tiles = (a.w + 127) / 128;
-  CLASFV_REQUIRE(g.w_tiles <= MAX_WT, "head_umma: frames wider than %d voxels are not supported (W=%d)", MAX_WT * 128, a.w);
-  for (int l = 0; l < 4; ++l) {
-    for (int wt = 0; wt < g.w_tiles; ++wt) {
-      const int v0 = wt * 128, v1 = std::min(a.w, v0 + 128) - 1;
-      const AxisTap t0 = axis_tap(v0, a.wl[l], a.w), t1 = axis_tap(v1, a.wl[l], a.w);
-      g.xlo[wt][l] = t0.i0; g.nx[wt][l] = t1.i1 - t0.i0 + 1;
-      g.nxmax[l] = std::max(g.nxmax[l], g.nx[wt][l]);
-    }
+  // w tile: 128 voxels unless the low-resolution columns they touch (plus the 2 bias rows) exceed the fixed K
+  for (g.wt_vox = 128; g.wt_vox >= 16; g.wt_vox -= 16) {
+    g.w_tiles = (a.w + g.wt_vox - 1) / g.wt_vox;
+    if (g.w_tiles > MAX_WT) break;
+    for (int l = 0; l < 4; ++l) g.nxmax[l] = 0;
+    for (int l = 0; l < 4; ++l)
+      for (int wt = 0; wt < g.w_tiles; ++wt) {
+        const int v0 = wt * g.wt_vox, v1 = std::min(a.w, v0 + g.wt_vox) - 1;
+        const AxisTap t0 = axis_tap(v0, a.wl[l], a.w), t1 = axis_tap(v1, a.wl[l], a.w);
+        g.xlo[wt][l] = t0.i0; g.nx[wt][l] = t1.i1 - t0.i0 + 1;
+        g.nxmax[l] = std::max(g.nxmax[l], g.nx[wt][l]);
+      }
+    if (g.nxmax[0] + g.nxmax[1] + g.nxmax[2] + g.nxmax[3] + 2 <= KSLABS * 64) break;
   }
+  CLASFV_REQUIRE(g.wt_vox >= 16 && g.w_tiles <= MAX_WT, "head_umma: frame width %d is not supported", a.w);
   int k = 0, raw = 0;
   for (int l = 0; l < 4; ++l) { g.koff[l] = k; k += g.nxmax[l]; g.raw_off[l] = raw; raw += (a.tl[l] == a.t ? 2 : 4) * g.nxmax[l] * 128; }
   g.ktot = k + 2;                               // + the two bias rows
@@ -518,7 +525,9 @@ int launch_head_umma(const HeadArgs& a, cudaStream_t stream) {
   const int64_t total = (int64_t)a.n * a.t * a.h;
   CLASFV_REQUIRE(total < (1ll << 31), "head_umma: too many rows");
   g.total_rows = (int)total;
-  const size_t smem = 1024 + Smem::WA + (size_t)KSLABS * 16384 + (size_t)2 * KSLABS * 8192 + (size_t)NRAW * g.raw_stage_bytes;
+  const size_t fixed = 1024 + Smem::WA + (size_t)KSLABS * 16384 + (size_t)2 * KSLABS * 8192;
+  g.nraw = fixed + (size_t)NRAW * g.raw_stage_bytes <= 227 * 1024 ? NRAW : 2;
+  const size_t smem = fixed + (size_t)g.nraw * g.raw_stage_bytes;
   CLASFV_REQUIRE(smem <= 227 * 1024, "head_umma: shared memory overflow (%zu bytes, W=%d)", smem, a.w);
   int dev = 0, sms = 0;
   CLASFV_CUDA(cudaGetDevice(&dev));

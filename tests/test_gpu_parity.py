@@ -254,12 +254,39 @@ def test_forward_interface_and_errors(net_fp32, sd):
     assert float((b - a - 1.0).abs().max()) <= 1e-5
 
 
-# ------------------------------------------------------------------------------------------ F2
+# ------------------------------------------------------------------------------------------ head geometry
+@pytest.mark.parametrize("t,h,w", [(16, 224, 224), (8, 48, 144), (8, 32, 272)])
+def test_tensor_core_head_geometries_against_fp32_path(net_bf16, net_fp32, t, h, w):
+    """The tcgen05 head tiles a row in 128-voxel pieces (W = 224: two pieces, 272: three, 144: ragged second piece) with
+    a per-piece interpolation matrix.  Its bf16-mode output is checked against this library's own fp32 path (itself
+    pinned to the oracle above) with the bf16 gates of DESIGN.md section 5: mean softmax error <= 2e-2 and >= 99.9 %
+    argmax agreement away from the decision boundary; flow mean end-point error <= 1.5e-3 of the frame size (bf16
+    output resolution is 2^-9 of the tanh range = 0.2 px at 112 px)."""
+    x = fixtures.synthetic_clip(t, h, w, seed=31, batch=2).cuda()
+    seg_ref, mot_ref = net_fp32(x)
+    seg, mot = net_bf16(x)
+    assert torch.isfinite(seg).all() and torch.isfinite(mot).all()
+    m = softmax_metrics(seg, seg_ref.cpu())
+    far = (m["pr"][:, 1] - 0.5).abs() >= 0.25
+    lv, lvr = m["p"][:, 1] > 0.5, m["pr"][:, 1] > 0.5
+    agree_far = float((lv == lvr)[far].float().mean())
+    d = (mot.float() - mot_ref.float()).cpu()
+    epe = torch.sqrt((d[:, 0] * w / 2) ** 2 + (d[:, 1] * h / 2) ** 2)
+    print(f"\n[bf16 head {t}x{h}x{w}] softmax mean {m['mean']:.4f} max {m['max']:.3f} agree(far) {agree_far:.5f} EPE mean {float(epe.mean()):.4f} px")
+    assert m["mean"] <= 2e-2
+    assert agree_far >= 0.999
+    assert float(epe.mean()) <= 1.5e-3 * max(h, w)
+    # no column of the frame is special: the error must not concentrate at the 128-voxel piece boundaries
+    col_err = (m["p"] - m["pr"]).abs().mean(dim=(0, 1, 2, 3))
+    assert float(col_err.max()) <= 6 * float(col_err.mean()) + 1e-3
+
+
 # ------------------------------------------------------------------------------------------ dense-video schedule
 @pytest.mark.parametrize("tv,clip_len,h,w,step,sub_batch", [
     (43, 32, 32, 32, 1, 5),        # 12 windows, ragged last batch
     (40, 16, 48, 32, 2, 16),       # stride-2 windows, shortest clip the schedule accepts, one batch
     (52, 32, 112, 112, 1, 8),      # the benchmark geometry (56x56 layer-1 maps)
+    (22, 16, 224, 224, 1, 4),      # config-5 geometry: 112x112 layer-1 maps, head with two 128-voxel w tiles
 ])
 def test_dense_video_schedule_is_bit_identical_to_per_clip(net_bf16, tv, clip_len, h, w, step, sub_batch):
     """Sharing the stem and layer1 between overlapping windows (csrc/api.cu, Forward::run_dense) must not change a
