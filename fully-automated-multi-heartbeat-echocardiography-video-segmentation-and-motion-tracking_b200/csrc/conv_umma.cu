@@ -188,6 +188,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
             const uint32_t a_addr = a_base + (uint32_t)(stage * p.a_slab_bytes);
             const int nk = (ks == p.kslabs - 1) ? p.k16_last : SLAB_K / UMMA_K;
             for (int tap = tap0; tap < tap1; ++tap) {
+              // A tap may start in the middle of an 8-row swizzle atom (any multiple of 128 bytes): the tensor core applies
+              // the SWIZZLE_128B pattern from absolute shared-memory address bits, exactly as TMA wrote it, so the descriptor
+              // needs no base offset (measured: tests/test_gpu_parity.py conv cases with 28-, 14-, 2-row tap shifts).
               const uint64_t da = smem_desc_sw128(a_addr + (uint32_t)p.tap_rowoff[tap] * 128u);
               const uint32_t b_addr = p.resident ? b_base + (uint32_t)((tap * p.kslabs + ks) * p.b_slab_bytes)
                                                  : b_base + (uint32_t)((stage * p.b_stage_slabs + (tap - tap0)) * p.b_slab_bytes);
@@ -361,10 +364,11 @@ inline void split_offset(int off, int stride, int* q, int* r) {
 }
 
 enum ShareMode { SHARE_NONE = 0, SHARE_T = 1, SHARE_H = 2 };
+bool g_unaligned_taps = true;       // tap starts inside a swizzle atom are fine (CLASFV_UMMA_ALIGNED_TAPS=1 restores whole-atom shifts)
 
 // Choose the (bw,bh,bt,bb) box of <= 128 output positions that wastes the fewest MMA rows, under the
 // layout constraints of the sharing mode (see UmmaParams).  Returns false if no box satisfies them.
-bool choose_box(int wo, int ho, int to, int n, ShareMode mode, int* bw, int* bh, int* bt, int* bb) {
+bool choose_box(int wo, int ho, int to, int n, ShareMode mode, int* bw, int* bh, int* bt, int* bb, double* eff_out = nullptr) {
   double best = -1.0; int best_rows = 0, best_halo = 1 << 30; bool found = false;
   for (int w = 1; w <= wo && w <= TILE_M; ++w)
     for (int h = 1; h <= ho && w * h <= TILE_M; ++h)
@@ -375,11 +379,11 @@ bool choose_box(int wo, int ho, int to, int n, ShareMode mode, int* bw, int* bh,
         int halo_rows = 0;
         if (mode == SHARE_T) {                   // frames are the outermost axis of the box; a frame is whole swizzle atoms
           b = 1;
-          if ((w * h) % 8 != 0) continue;
+          if ((w * h) % 8 != 0 && !g_unaligned_taps) continue;
           halo_rows = 2 * w * h;
         } else if (mode == SHARE_H) {            // rows are the outermost axis; a row is whole swizzle atoms
           b = 1;
-          if (t != 1 || w % 8 != 0) continue;
+          if (t != 1 || (w % 8 != 0 && !g_unaligned_taps)) continue;
           halo_rows = 2 * w;
         }
         const int64_t tiles = cdiv(wo, w) * cdiv(ho, h) * cdiv(to, t) * cdiv(n, b);
@@ -391,6 +395,7 @@ bool choose_box(int wo, int ho, int to, int n, ShareMode mode, int* bw, int* bh,
                                                    (halo_rows == best_halo && (rows > best_rows || (rows == best_rows && w > *bw)))));
         if (better) { best = eff; best_rows = rows; best_halo = halo_rows; *bw = w; *bh = h; *bt = t; *bb = b; found = true; }
       }
+  if (eff_out) *eff_out = best;
   return found;
 }
 
@@ -430,15 +435,22 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   const bool unit_stride = s.st == 1 && s.sh == 1 && s.sw == 1 && !a.in2;
   ShareMode want = SHARE_NONE;
   if (unit_stride && s.kt == 3 && s.kh == 1 && s.kw == 1 && s.pt == 1) want = SHARE_T;
-  if (unit_stride && s.kt == 1 && s.kh == 3 && s.kw == 3 && s.ph == 1 && s.pw == 1 && s.wo % 8 == 0) want = SHARE_H;
+  g_unaligned_taps = getenv("CLASFV_UMMA_ALIGNED_TAPS") == nullptr;
+  if (unit_stride && s.kt == 1 && s.kh == 3 && s.kw == 3 && s.ph == 1 && s.pw == 1 && (s.wo % 8 == 0 || g_unaligned_taps)) want = SHARE_H;
   static const bool no_share = getenv("CLASFV_UMMA_NO_SHARE") != nullptr;
   if (no_share) want = SHARE_NONE;
   p.bias_bytes = round_up(s.cout * 4, 128);
   const int bar_bytes = 8 * (2 * 8 + 6) + 16 + p.bias_bytes;
   ShareMode mode = SHARE_NONE;
+  // sharing cuts the A traffic of the tap group 3x but constrains the box: keep it only while the MMA rows it fills stay
+  // within 80 % of what the unconstrained tiling fills (a time-segmented input has no unshared form)
+  double eff_none = 0.0;
+  { int w_, h_, t_, b_; choose_box(s.wo, s.ho, s.to, s.n, SHARE_NONE, &w_, &h_, &t_, &b_, &eff_none); }
   for (int attempt = 0; attempt < 2; ++attempt) {
     mode = attempt == 0 ? want : SHARE_NONE;
-    if (!choose_box(s.wo, s.ho, s.to, s.n, mode, &p.bw, &p.bh, &p.bt, &p.bb)) continue;
+    double eff = 0.0;
+    if (!choose_box(s.wo, s.ho, s.to, s.n, mode, &p.bw, &p.bh, &p.bt, &p.bb, &eff)) continue;
+    if (mode != SHARE_NONE && !a.seg.on && eff < 0.8 * eff_none) continue;
     const int rows_out = p.bw * p.bh * p.bt * p.bb;
     int slab_rows = rows_out, taps_per_group = 1;
     if (mode == SHARE_T) { slab_rows = p.bw * p.bh * (p.bt + 2); taps_per_group = 3; }

@@ -130,6 +130,9 @@ CONV_CASES = [
     (3, 4, 7, 7, 960, 512, (3, 1, 1), (2, 1, 1), (1, 0, 0), False, True, False),
     (1, 4, 7, 7, 512, 1152, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, False),
     (1, 8, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, False),       # 196 tiles: persistent loop wraps
+    (2, 4, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, False),      # layer2 geometry: 28-wide rows
+    (2, 4, 14, 14, 256, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, False),      # layer3 geometry
+    (2, 8, 14, 14, 576, 256, (3, 1, 1), (1, 1, 1), (1, 0, 0), True, True, False),       # layer3 temporal: 196-row frames
 ]
 
 
