@@ -71,6 +71,7 @@ struct UmmaParams {
   // frame-wise A loads (time-segmented temporal convolution): the (bt+2)-frame slab is filled by one single-frame
   // box load per frame, frame v of the virtual clip coming from map 0 (v < fw_split) or map 1
   int framewise, fw_split, fw_a_toff, fw_b_toff, frame_bytes;
+  int tpg, tap_step_rows;                    // every group has tpg taps (1 or 3); tap j of a group starts j * tap_step_rows rows into the slab
   int64_t out_bstride;                       // elements between clips of `out`
   // segmented residual (see ConvArgs::ResSeg); res_split = INT_MAX and res_a_bstride = dense when not segmented
   const void* residual_b;
@@ -125,85 +126,115 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    // One elected thread.  Every kernel parameter it needs is copied into registers first: the asm statements below
+    // carry "memory" clobbers, after which the compiler would otherwise re-read the parameter (constant) bank each time.
     if (elect_one()) {
-      if (p.resident) {
+      const int nst = p.nstages, kslabs = p.kslabs, ngroups = p.ngroups, tpg = p.tpg, resident = p.resident, tiles_n = p.tiles_n;
+      const int tw = p.tiles_w, th = p.tiles_h, tt = p.tiles_t, bw = p.bw, bh = p.bh, bt = p.bt, bb = p.bb, bn = p.bn;
+      const int a_slab_bytes = p.a_slab_bytes, b_slab_bytes = p.b_slab_bytes, b_stage_slabs = p.b_stage_slabs, frame_bytes = p.frame_bytes;
+      const int framewise = p.framewise, fw_split = p.fw_split, fw_a_toff = p.fw_a_toff, fw_b_toff = p.fw_b_toff;
+      const uint32_t tx = (uint32_t)p.a_tx_bytes + (resident ? 0u : (uint32_t)(tpg * b_slab_bytes));
+      if (resident) {
         // the whole filter bank of this (single) N tile stays in shared memory for the life of the CTA
-        mbar_arrive_expect_tx(wres_bar, (uint32_t)(p.ntaps * p.kslabs * p.b_slab_bytes));
+        mbar_arrive_expect_tx(wres_bar, (uint32_t)(p.ntaps * kslabs * b_slab_bytes));
         for (int tap = 0; tap < p.ntaps; ++tap)
-          for (int ks = 0; ks < p.kslabs; ++ks)
-            tma_load_3d(b_base + (uint32_t)((tap * p.kslabs + ks) * p.b_slab_bytes), &p.tmap_b, wres_bar, ks * SLAB_K, 0, p.tap_widx[tap]);
+          for (int ks = 0; ks < kslabs; ++ks)
+            tma_load_3d(b_base + (uint32_t)((tap * kslabs + ks) * b_slab_bytes), &p.tmap_b, wres_bar, ks * SLAB_K, 0, p.tap_widx[tap]);
       }
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.tiles_n;
-        int mt = tile / p.tiles_n;
-        const int w0 = (mt % p.tiles_w) * p.bw; mt /= p.tiles_w;
-        const int h0 = (mt % p.tiles_h) * p.bh; mt /= p.tiles_h;
-        const int t0 = (mt % p.tiles_t) * p.bt; mt /= p.tiles_t;
-        const int b0 = mt * p.bb;
-        for (int g = 0; g < p.ngroups; ++g) {
+        const int n_tile = tile % tiles_n;
+        int mt = tile / tiles_n;
+        const int w0 = (mt % tw) * bw; mt /= tw;
+        const int h0 = (mt % th) * bh; mt /= th;
+        const int t0 = (mt % tt) * bt; mt /= tt;
+        const int b0 = mt * bb;
+        for (int g = 0; g < ngroups; ++g) {
           const CUtensorMap* map = &p.tmap_a[p.grp_view[g]];
           const int cw = w0 + p.grp_dw[g], ch = h0 + p.grp_dh[g], ct = t0 + p.grp_dt[g];
-          const int tap0 = p.grp_first[g], tap1 = p.grp_first[g + 1];
-          const uint32_t tx = (uint32_t)p.a_tx_bytes + (p.resident ? 0u : (uint32_t)((tap1 - tap0) * p.b_slab_bytes));
-          for (int ks = 0; ks < p.kslabs; ++ks) {
+          int widx[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) widx[j] = (!resident && j < tpg) ? p.tap_widx[g * tpg + j] : 0;
+          for (int ks = 0; ks < kslabs; ++ks) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_arrive_expect_tx(full_bar(stage), tx);
-            if (p.framewise) {
-              for (int f = 0; f < p.bt + 2; ++f) {
+            const uint32_t a_dst = a_base + (uint32_t)(stage * a_slab_bytes);
+            if (framewise) {
+              for (int f = 0; f < bt + 2; ++f) {
                 const int v = ct + f;           // frame of the virtual clip (ct = t0 - 1)
-                const bool from_a = v < p.fw_split;
-                tma_load_5d(a_base + (uint32_t)(stage * p.a_slab_bytes + f * p.frame_bytes), &p.tmap_a[from_a ? 0 : 1], full_bar(stage),
-                            ks * SLAB_K, cw, ch, v + (from_a ? p.fw_a_toff : p.fw_b_toff), b0);
+                const bool from_a = v < fw_split;
+                tma_load_5d(a_dst + (uint32_t)(f * frame_bytes), &p.tmap_a[from_a ? 0 : 1], full_bar(stage),
+                            ks * SLAB_K, cw, ch, v + (from_a ? fw_a_toff : fw_b_toff), b0);
               }
             } else {
-              tma_load_5d(a_base + (uint32_t)(stage * p.a_slab_bytes), map, full_bar(stage), ks * SLAB_K, cw, ch, ct, b0);
+              tma_load_5d(a_dst, map, full_bar(stage), ks * SLAB_K, cw, ch, ct, b0);
             }
-            if (!p.resident)
-              for (int tap = tap0; tap < tap1; ++tap)
-                tma_load_3d(b_base + (uint32_t)((stage * p.b_stage_slabs + (tap - tap0)) * p.b_slab_bytes), &p.tmap_b, full_bar(stage),
-                            ks * SLAB_K, n_tile * p.bn, p.tap_widx[tap]);
-            if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+            if (!resident) {
+              const uint32_t b_dst = b_base + (uint32_t)(stage * b_stage_slabs * b_slab_bytes);
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                if (j < tpg) tma_load_3d(b_dst + (uint32_t)(j * b_slab_bytes), &p.tmap_b, full_bar(stage), ks * SLAB_K, n_tile * bn, widx[j]);
+            }
+            if (++stage == nst) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // One elected thread; for the 64-column layers this thread's instruction stream IS the critical path (ncu:
+    // profiles/r01w), so the loop body is a handful of 32-bit adds per tcgen05.mma: parameters in registers, descriptor
+    // low words strength-reduced (the high word of a SWIZZLE_128B K-major descriptor is a constant).
     if (elect_one()) {
       if (p.resident) { mbar_wait(wres_bar, 0); tc_fence_after(); }
+      const int nst = p.nstages, kslabs = p.kslabs, ngroups = p.ngroups, tpg = p.tpg, resident = p.resident, bn = p.bn;
+      const uint32_t k16_last = (uint32_t)p.k16_last, idesc = p.idesc;
+      const uint32_t desc_hi = (uint32_t)(smem_desc_sw128(0) >> 32);
+      const uint32_t a_lo0 = (uint32_t)smem_desc_sw128(a_base), b_lo0 = (uint32_t)smem_desc_sw128(b_base);
+      const uint32_t a_st16 = (uint32_t)p.a_slab_bytes >> 4, bs16 = (uint32_t)p.b_slab_bytes >> 4, tap16 = (uint32_t)p.tap_step_rows * 8u;
+      const uint32_t b_stage16 = (uint32_t)(p.b_stage_slabs * p.b_slab_bytes) >> 4;
+      auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1; const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.bn);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * bn);
         uint32_t accumulate = 0;
-        for (int g = 0; g < p.ngroups; ++g) {
-          const int tap0 = p.grp_first[g], tap1 = p.grp_first[g + 1];
-          for (int ks = 0; ks < p.kslabs; ++ks) {
+        uint32_t b_res = b_lo0;                  // resident weights: slot (tap * kslabs + ks), visited in exactly this order
+        for (int g = 0; g < ngroups; ++g) {
+          for (int ks = 0; ks < kslabs; ++ks) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint32_t a_addr = a_base + (uint32_t)(stage * p.a_slab_bytes);
-            const int nk = (ks == p.kslabs - 1) ? p.k16_last : SLAB_K / UMMA_K;
-            for (int tap = tap0; tap < tap1; ++tap) {
-              // A tap may start in the middle of an 8-row swizzle atom (any multiple of 128 bytes): the tensor core applies
-              // the SWIZZLE_128B pattern from absolute shared-memory address bits, exactly as TMA wrote it, so the descriptor
-              // needs no base offset (measured: tests/test_gpu_parity.py conv cases with 28-, 14-, 2-row tap shifts).
-              const uint64_t da = smem_desc_sw128(a_addr + (uint32_t)p.tap_rowoff[tap] * 128u);
-              const uint32_t b_addr = p.resident ? b_base + (uint32_t)((tap * p.kslabs + ks) * p.b_slab_bytes)
-                                                 : b_base + (uint32_t)((stage * p.b_stage_slabs + (tap - tap0)) * p.b_slab_bytes);
-              const uint64_t db = smem_desc_sw128(b_addr);
-              for (int k = 0; k < nk; ++k) {
-                // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
-                tc_mma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, accumulate);
+            const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_st16;
+            const uint32_t nk = (ks == kslabs - 1) ? k16_last : (uint32_t)(SLAB_K / UMMA_K);
+            const uint32_t b_lo = resident ? b_res + (uint32_t)ks * bs16 : b_lo0 + (uint32_t)stage * b_stage16;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              if (j < tpg) {
+                // A tap may start in the middle of an 8-row swizzle atom (any multiple of 128 bytes): the tensor core
+                // applies the SWIZZLE_128B pattern from absolute shared-memory address bits, exactly as TMA wrote it.
+                const uint32_t da = a_lo + (uint32_t)j * tap16;
+                const uint32_t db = b_lo + (uint32_t)j * (resident ? (uint32_t)kslabs * bs16 : bs16);
+                // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field.
+                // Only the first instruction of a tile overwrites the accumulator; a full slab is four unpredicated issues.
+                tc_mma_bf16(tmem_d, desc(da), desc(db), idesc, accumulate);
                 accumulate = 1;
+                if (nk == 4) {
+                  tc_mma_bf16(tmem_d, desc(da + 2u), desc(db + 2u), idesc, 1u);
+                  tc_mma_bf16(tmem_d, desc(da + 4u), desc(db + 4u), idesc, 1u);
+                  tc_mma_bf16(tmem_d, desc(da + 6u), desc(db + 6u), idesc, 1u);
+                } else {
+                  if (nk > 1) tc_mma_bf16(tmem_d, desc(da + 2u), desc(db + 2u), idesc, 1u);
+                  if (nk > 2) tc_mma_bf16(tmem_d, desc(da + 4u), desc(db + 4u), idesc, 1u);
+                }
               }
             }
             tc_commit(empty_bar(stage));          // slab reusable once these MMAs have read it
-            if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+            if (++stage == nst) { stage = 0; phase ^= 1u; }
           }
+          b_res += (uint32_t)(tpg * kslabs) * bs16;
         }
         tc_commit(tfull_bar(as));                 // accumulator complete
       }
@@ -516,6 +547,8 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   }
   p.grp_first[ng] = (int8_t)nt;
   p.ngroups = ng;
+  p.tpg = mode == SHARE_NONE ? 1 : 3;
+  p.tap_step_rows = mode == SHARE_T ? p.bw * p.bh : mode == SHARE_H ? p.bw : 0;
   CLASFV_REQUIRE(nt == ntaps, "conv_umma: internal tap bookkeeping error");
 
   // ---- tensor maps

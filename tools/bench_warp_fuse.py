@@ -21,7 +21,11 @@ def main():
     ap.add_argument("--flow-px", type=float, nargs="*", default=[0.0, 1.0, 4.0, 8.0])
     ap.add_argument("--dtypes", nargs="*", default=["fp32", "bf16"])
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--once", action="store_true", help="one point per dtype (256 clips, 4 px), 1 warm-up + 1 launch: for ncu captures")
     args = ap.parse_args()
+    warm = 3
+    if args.once:
+        args.clips, args.flow_px, args.iters, warm = [256], [4.0], 1, 1
     try:
         peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
@@ -38,7 +42,7 @@ def main():
                 mot = torch.tanh(torch.randn(n, 4, 32, h, w, generator=g, device="cuda") * (px / 56.0)).to(dtype)
                 starts = list(range(n))
                 t_out = n + 31
-                for _ in range(3):
+                for _ in range(warm):
                     eng.warp_fuse(prob, mot, starts, t_out)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -15,6 +15,9 @@ net = R2plus1D_18_MotionNet(pretrained=False, precision="bf16")
 net.load_state_dict(synthetic.random_state_dict(0))
 net = net.cuda().eval()
 eng = net.engine()
+if len(sys.argv) > 3:
+    eng.set_option("dense_video", int(sys.argv[3]))
+    eng.set_option("sub_batch", n)
 video = torch.from_numpy(synthetic.synthetic_echo_video(32 + n - 1, 112, 112, seed=0)).cuda()
 prob = torch.empty((n, 2, 32, 112, 112), dtype=torch.bfloat16, device="cuda")
 mot = torch.empty((n, 4, 32, 112, 112), dtype=torch.bfloat16, device="cuda")
