@@ -272,7 +272,7 @@ def main():
             "clip_frames_per_s": world * N_CLIPS * CLIP * args.steps / (ms_total / 1e3),
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()} | {"warp_fuse": fuse_ms},
             "e2e": {"value": world * T_VIDEO * args.steps / (e2e_ms / 1e3), "unit": "frames/s",
-                    "h2d_bytes_per_step": int(video_host.numel() * 4), "d2h_bytes_per_step": int(T_VIDEO * H * W)},
+                    "h2d_bytes_per_step": int(video_host.numel() * 4), "d2h_bytes_per_step": int(T_VIDEO * H * W * 8)},
             "gpu_launches": args.steps * launches_per_step,
             "roofline": {"kernel": "conv_umma_kernel (trunk: stem 3x1x1 + layer1-4)",
                          "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",

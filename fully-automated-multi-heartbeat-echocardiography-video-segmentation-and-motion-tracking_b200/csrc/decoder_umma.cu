@@ -42,6 +42,7 @@ constexpr int P1_WARPS = 10;
 constexpr int P1_THREADS = P1_WARPS * 32;
 constexpr int MAX_WT = 4;                 // w tiles of 128 voxels (W <= 512)
 constexpr int NRAW = 3;                   // raw corner-row stages in flight (2 when 3 do not fit shared memory)
+constexpr int NR = 3;                     // R stages (phase 1 runs up to two rows ahead of MMA 0; 2 when 3 do not fit)
 constexpr int KSLABS = 2;                 // K of MMA 0 is always 2 slabs of 64 (interpolation columns + 2 bias rows, zero padded)
 
 struct AxisTap { int i0, i1; float l0, l1; };
@@ -112,6 +113,7 @@ struct HeadGeom {                 // host-computed layout of the K axis of MMA 0
   int raw_stage_bytes;
   int total_rows;                 // n * t * h
   int nraw;                       // raw stages actually used (2 or NRAW)
+  int nr;                         // R stages actually used (2 or NR)
   int wt_vox;                     // voxels per w tile (128, or fewer when the tile's interpolation columns would exceed K)
 };
 
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   const uint32_t wa_bytes = (uint32_t)KSLABS * 16384u;
   const uint32_t r_stage_bytes = (uint32_t)g.nslab * 8192u;
   const uint32_t r_off = Smem::WA + wa_bytes;
-  const uint32_t raw_off0 = r_off + 2u * r_stage_bytes;
+  const uint32_t raw_off0 = r_off + (uint32_t)g.nr * r_stage_bytes;
 
   const int wt = blockIdx.x % g.w_tiles;
   const int row0 = blockIdx.x / g.w_tiles, row_step = gridDim.x / g.w_tiles;
@@ -165,8 +167,8 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   }
   if (tid == 0) {
     for (int s = 0; s < NRAW; ++s) { mbar_init(bar(RAW_FULL, s), 1); mbar_init(bar(RAW_EMPTY, s), P1_WARPS); }
+    for (int s = 0; s < NR; ++s) { mbar_init(bar(R_FULL, s), P1_WARPS); mbar_init(bar(R_EMPTY, s), 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar(R_FULL, s), P1_WARPS); mbar_init(bar(R_EMPTY, s), 1);
       mbar_init(bar(ACC0_FULL, s), 1); mbar_init(bar(ACC0_EMPTY, s), 4);
       mbar_init(bar(A1_FULL, s), 4); mbar_init(bar(A_EMPTY, s), 1);
       mbar_init(bar(ACC1_FULL, s), 1); mbar_init(bar(ACC1_EMPTY, s), 4);
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // zero the interpolation matrix and both R stages (unused K rows / columns must be exact zeros, not stale NaNs)
-  for (uint32_t i = (uint32_t)tid * 16u; i < wa_bytes + 2u * r_stage_bytes; i += HU_THREADS * 16u)
+  for (uint32_t i = (uint32_t)tid * 16u; i < wa_bytes + (uint32_t)g.nr * r_stage_bytes; i += HU_THREADS * 16u)
     *reinterpret_cast<uint4*>(sm + Smem::WA + i) = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 512) {
     // W2 (64 out x 64 in, bf16) into the K-major swizzled B tile: 512 chunks of 16 bytes
@@ -215,13 +217,15 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     }
     if (tid >= 512 && tid < 640) { put_w(tid - 512, g.ktot - 2, 1.f); put_w(tid - 512, g.ktot - 1, 1.f); }
     // the two constant rows of R: b1 = hi + lo (both stages)
-    if (tid >= 640 && tid < 640 + 2 * HC) {
-      const int c = (tid - 640) & 63, s = (tid - 640) >> 6;
+    if (tid >= 640 && tid < 640 + HC) {
+      const int c = tid - 640;
       const float b = __ldg(a.b1 + c);
       const __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
-      const uint32_t base = r_off + (uint32_t)s * r_stage_bytes;
-      *reinterpret_cast<__half*>(sm + base + sw128_offset((uint32_t)(g.ktot - 2), (uint32_t)(c >> 3)) + (uint32_t)(c & 7) * 2u) = hi;
-      *reinterpret_cast<__half*>(sm + base + sw128_offset((uint32_t)(g.ktot - 1), (uint32_t)(c >> 3)) + (uint32_t)(c & 7) * 2u) = lo;
+      for (int s = 0; s < g.nr; ++s) {
+        const uint32_t base = r_off + (uint32_t)s * r_stage_bytes;
+        *reinterpret_cast<__half*>(sm + base + sw128_offset((uint32_t)(g.ktot - 2), (uint32_t)(c >> 3)) + (uint32_t)(c & 7) * 2u) = hi;
+        *reinterpret_cast<__half*>(sm + base + sw128_offset((uint32_t)(g.ktot - 1), (uint32_t)(c >> 3)) + (uint32_t)(c & 7) * 2u) = lo;
+      }
     }
   }
   fence_async_smem();
@@ -285,19 +289,20 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     for (int k = 0; k < my_rows + 2; ++k) {
       if (k < my_rows) {
         const int s = k & 1; const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-        mbar_wait(bar(R_FULL, s), ph);
+        const int rs = k % g.nr; const uint32_t rph = (uint32_t)(k / g.nr) & 1u;
+        mbar_wait(bar(R_FULL, rs), rph);
         mbar_wait(bar(ACC0_EMPTY, s), ph ^ 1u);
         tc_fence_after();
         // K is always 2 slabs = 128 (zero rows / columns beyond ktot): 16 instructions with constant descriptor
         // offsets.  MN-major B: 16 K rows of 128 bytes per instruction = two 8-row swizzle atoms (SBO = 1024), so K
         // advances by 2048 bytes = 128 descriptor units.
-        const uint64_t db0 = desc_r + (uint64_t)(s * (int)(KSLABS * 8192 / 16));
+        const uint64_t db0 = desc_r + (uint64_t)(rs * (int)(KSLABS * 8192 / 16));
         const uint32_t d0 = acc0 + (uint32_t)(s * 64);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < KSLABS * 4; ++kk)
             tc_mma_bf16(d0, desc_wa + (uint64_t)((kk >> 2) * 1024 + 2 * (kk & 3)), db0 + (uint64_t)(kk * 128), idesc0, kk ? 1u : 0u);
-          tc_commit(bar(R_EMPTY, s));
+          tc_commit(bar(R_EMPTY, rs));
           tc_commit(bar(ACC0_FULL, s));
         }
         __syncwarp();
@@ -445,10 +450,10 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     // ================================================================ phase 1: R = (T,H)-interpolated rows, bf16, MN-major swizzled
     const int ptid = (warp < 4 ? warp - 2 : warp - 14) * 32 + lane;       // 0 .. P1_THREADS-1
     for (int i = 0; i < my_rows; ++i) {
-      const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      const int s = i % g.nr; const uint32_t ph = (uint32_t)(i / g.nr) & 1u;
       const int rs = i % g.nraw; const uint32_t rph = (uint32_t)(i / g.nraw) & 1u;
       mbar_wait_sleep(bar(RAW_FULL, rs), rph);
-      mbar_wait_sleep(bar(R_EMPTY, s), ph ^ 1u);          // MMA 0 of row i-2 has finished reading this R stage
+      mbar_wait_sleep(bar(R_EMPTY, s), ph ^ 1u);          // MMA 0 of row i-nr has finished reading this R stage
       const TilePlan& pl = plans[rs];
       const uint8_t* stage = sm + raw_off0 + (uint32_t)rs * (uint32_t)g.raw_stage_bytes;
       uint8_t* rst = sm + r_off + (uint32_t)s * r_stage_bytes;
@@ -525,9 +530,11 @@ int launch_head_umma(const HeadArgs& a, cudaStream_t stream) {
   const int64_t total = (int64_t)a.n * a.t * a.h;
   CLASFV_REQUIRE(total < (1ll << 31), "head_umma: too many rows");
   g.total_rows = (int)total;
-  const size_t fixed = 1024 + Smem::WA + (size_t)KSLABS * 16384 + (size_t)2 * KSLABS * 8192;
-  g.nraw = fixed + (size_t)NRAW * g.raw_stage_bytes <= 227 * 1024 ? NRAW : 2;
-  const size_t smem = fixed + (size_t)g.nraw * g.raw_stage_bytes;
+  // three R stages matter more than three raw stages (ncu: phase 1 otherwise idles a third of the time on R_EMPTY)
+  const size_t base_bytes = 1024 + Smem::WA + (size_t)KSLABS * 16384, r_stage = (size_t)KSLABS * 8192, limit = 227 * 1024;
+  g.nr = base_bytes + NR * r_stage + 2 * (size_t)g.raw_stage_bytes <= limit ? NR : 2;
+  g.nraw = base_bytes + g.nr * r_stage + (size_t)NRAW * g.raw_stage_bytes <= limit ? NRAW : 2;
+  const size_t smem = base_bytes + g.nr * r_stage + (size_t)g.nraw * g.raw_stage_bytes;
   CLASFV_REQUIRE(smem <= 227 * 1024, "head_umma: shared memory overflow (%zu bytes, W=%d)", smem, a.w);
   int dev = 0, sms = 0;
   CLASFV_CUDA(cudaGetDevice(&dev));

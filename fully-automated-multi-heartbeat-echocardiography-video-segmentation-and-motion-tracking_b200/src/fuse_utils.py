@@ -82,6 +82,17 @@ def _to_device_video(video, device):
     return v.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
 
 
+def _mask_to_host_int64(mask):
+    """(T,H,W) uint8 CUDA mask -> int64 numpy array (what the reference returns, fuse_utils.py:100-102).  The widening
+    runs on the device and the copy lands in pinned memory from torch's caching host allocator: a uint8 pageable copy
+    followed by a host-side ``astype`` costs ~2 ms per 200-frame video, more than the whole fusion kernel."""
+    wide = mask.to(torch.int64)
+    host = torch.empty(wide.shape, dtype=torch.int64, pin_memory=True)
+    host.copy_(wide, non_blocking=True)
+    torch.cuda.current_stream(mask.device).synchronize()
+    return host.numpy()
+
+
 def divide_to_consecutive_clips(video, clip_length=32, interpolate_last=False):
     """(3, L, H, W) array -> (n, 3, clip_length, H, W) float64 array, n = round(L / clip_length)."""
     eng = _default_engine()
@@ -129,7 +140,7 @@ def segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num
         # and layer1 between the overlapping windows (dense-video schedule, csrc/api.cu)
         eng.forward_windows(v, prob, mot, OUT_PROB, starts, CLIP, batch_clips)
         res = eng.warp_fuse(prob, mot, starts, num_frames, edge_hops=edge_hops)
-        fused = res["mask"].cpu().numpy().astype(np.int64)
+        fused = _mask_to_host_int64(res["mask"])
         if return_details:
             return fused, {"area": res["area"].cpu().numpy(), "cnt": res["cnt"].cpu().numpy(), "acc": res["acc"],
                            "clips": n, "prob": prob, "motion": mot, "starts": starts}
@@ -160,7 +171,7 @@ def segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num
         b1 = min(total, b0 + batch_clips)
         eng.forward_into(clips[b0:b1], prob[b0:b1], mot[:b1 - b0], OUT_PROB)
     mask, area = eng.fuse_shift_votes(prob, plan, num_frames, step)
-    fused = mask.cpu().numpy().astype(np.int64)
+    fused = _mask_to_host_int64(mask)
     keep = [0] + [i for i in range(1, num_frames) if step - 1 < i]   # reference skips frames 1..step-1 (:85)
     if len(keep) != num_frames:
         fused = fused[keep]
