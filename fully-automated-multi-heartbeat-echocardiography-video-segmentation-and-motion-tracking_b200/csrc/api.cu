@@ -247,7 +247,7 @@ struct Forward {
   int act; size_t es; bool tc_head; size_t gs;
   int T[5], H[5], W[5], C[5];
   char* ws = nullptr;
-  size_t o_s0, o_f[5], o_mid, o_ta, o_x1, o_ds, o_g[4];
+  size_t o_s0, o_f[5], o_mid, o_ta, o_x1, o_ds, o_g[4], o_gt[4];
   size_t total = 0;
   size_t region(size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; }
 
@@ -285,6 +285,8 @@ struct Forward {
     o_x1 = region(P[dense ? 2 : 1] * (dense ? 128 : 64) * es);
     o_ds = region(P[2] * 128 * es);
     for (int i = 0; i < 4; ++i) o_g[i] = region(P[i + 1] * DEC * gs);
+    // tensor-core head: lateral maps of levels 2-4 interpolated along T to the output's frame count
+    for (int i = 1; i < 4; ++i) o_gt[i] = tc_head ? region((int64_t)nb * t * H[i + 1] * W[i + 1] * DEC * gs) : 0;
   }
 
   // one residual block on a batch of nb clips
@@ -332,6 +334,11 @@ struct Forward {
     if ((rc = mark(2))) return rc;
     HeadArgs ha;
     for (int i = 0; i < 4; ++i) { ha.g[i] = ws + o_g[i]; ha.tl[i] = T[i + 1]; ha.hl[i] = H[i + 1]; ha.wl[i] = W[i + 1]; }
+    if (tc_head)
+      for (int i = 1; i < 4; ++i) {
+        if ((rc = launch_temporal_upsample_bf16(ws + o_g[i], ws + o_gt[i], nb, T[i + 1], t, H[i + 1], W[i + 1], stream))) return rc;
+        ha.g[i] = ws + o_gt[i]; ha.tl[i] = t;
+      }
     ha.g_dtype = tc_head ? CLASFV_BF16 : CLASFV_F32;
     ha.n = nb; ha.t = t; ha.h = height; ha.w = width;
     ha.b1 = h->b1; ha.w2 = h->w2; ha.w2_bf16 = h->w2_bf16; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;

@@ -20,8 +20,8 @@
 // Warp roles (768 threads, persistent, one CTA per SM); every hand-over is an mbarrier, every buffer is doubled:
 //   warp 0           producer: plans the row (corner indices / weights), bulk-copies its raw corner rows (bf16)
 //   warp 1           MMA issuer (one lane): per step MMA0(i), MMA1(i-1), MMA2(i-2)
-//   warps 4-7        epilogue 0: acc0 -> relu -> bf16 -> A tile            (one warp per TMEM lane quarter)
-//   warps 8-11       epilogue 1: acc1 + b2 -> relu -> bf16 -> A tile (in place: MMA 1 has finished reading it)
+//   warps 4-7        epilogue 0: acc0 -> relu -> bf16 -> tensor memory (A operand of MMA 1)   (one warp per lane quarter)
+//   warps 8-11       epilogue 1: acc1 + b2 -> relu -> bf16 -> tensor memory (A operand of MMA 2)
 //   warps 12-15      epilogue 2: acc2 + bh -> softmax / tanh -> global
 //   warps 2,3,16-23  phase 1: raw corner rows -> R
 #include "internal.h"
@@ -41,7 +41,7 @@ constexpr int HC = 64;
 constexpr int P1_WARPS = 10;
 constexpr int P1_THREADS = P1_WARPS * 32;
 constexpr int MAX_WT = 4;                 // w tiles of 128 voxels (W <= 512)
-constexpr int NRAW = 3;                   // raw corner-row stages in flight (2 when 3 do not fit shared memory)
+constexpr int NRAW = 4;                   // raw corner-row stages wanted (as many as fit shared memory, at least 2)
 constexpr int NR = 3;                     // R stages (phase 1 runs up to two rows ahead of MMA 0; 2 when 3 do not fit)
 constexpr int KSLABS = 2;                 // K of MMA 0 is always 2 slabs of 64 (interpolation columns + 2 bias rows, zero padded)
 
@@ -78,6 +78,20 @@ __device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {
   uint32_t d;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
   return d;
+}
+
+// tcgen05.mma with the A operand in tensor memory (lane = row, two 16-bit K elements per 32-bit column)
+__device__ __forceinline__ void tc_mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 
 // compiler-level fence: values produced by an asynchronous tcgen05.ld may not be consumed before tcgen05.wait::ld
@@ -125,18 +139,17 @@ struct Smem {                     // byte offsets from the 1024-aligned base
   static constexpr uint32_t B2 = WHB + 2048;              // [64] fp32
   static constexpr uint32_t BH = B2 + 256;                // [8] fp32
   static constexpr uint32_t PLAN = BH + 32;               // NRAW x TilePlan
-  static constexpr uint32_t BARS = PLAN + NRAW * 64;      // 13 groups of up to 4 mbarriers
-  static constexpr uint32_t TMEM = BARS + 8 * 52;
-  static constexpr uint32_t AT = 11264;                   // 2 x (128 x 128 B)  A tile of MMA 1 / MMA 2
-  static constexpr uint32_t WA = AT + 2 * 16384;          // interpolation matrix (fp16): KSLABS slabs of 16 KB
+  static constexpr uint32_t BARS = PLAN + NRAW * 64;      // 14 groups of up to 4 mbarriers
+  static constexpr uint32_t TMEM = BARS + 8 * 56;
+  static constexpr uint32_t WA = 12288;                   // interpolation matrix (fp16), staging only: KSLABS slabs of 16 KB
   // then: R (2 stages x nslab x 8 KB), raw (2 stages x raw_stage_bytes)
 };
-static_assert(Smem::TMEM + 4 <= Smem::AT, "head smem header overflow");
+static_assert(Smem::TMEM + 4 <= Smem::WA, "head smem header overflow");
 static_assert(sizeof(TilePlan) == 64, "plan slot size");
 
 enum Bar {  // index of the first mbarrier of each group (one per buffer stage, up to 4 stages)
-  RAW_FULL = 0, RAW_EMPTY = 4, R_FULL = 8, R_EMPTY = 12, ACC0_FULL = 16, ACC0_EMPTY = 20, A1_FULL = 24, A_EMPTY = 28,
-  ACC1_FULL = 32, ACC1_EMPTY = 36, A2_FULL = 40, ACC2_FULL = 44, ACC2_EMPTY = 48,
+  RAW_FULL = 0, RAW_EMPTY = 4, R_FULL = 8, R_EMPTY = 12, ACC0_FULL = 16, ACC0_EMPTY = 20, A1_FULL = 24, A1_EMPTY = 28,
+  ACC1_FULL = 32, ACC1_EMPTY = 36, A2_FULL = 40, ACC2_FULL = 44, ACC2_EMPTY = 48, A2_EMPTY = 52,
 };
 
 template <typename OutT>
@@ -170,14 +183,15 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     for (int s = 0; s < NR; ++s) { mbar_init(bar(R_FULL, s), P1_WARPS); mbar_init(bar(R_EMPTY, s), 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(ACC0_FULL, s), 1); mbar_init(bar(ACC0_EMPTY, s), 4);
-      mbar_init(bar(A1_FULL, s), 4); mbar_init(bar(A_EMPTY, s), 1);
+      mbar_init(bar(A1_FULL, s), 4); mbar_init(bar(A1_EMPTY, s), 1); mbar_init(bar(A2_EMPTY, s), 1);
       mbar_init(bar(ACC1_FULL, s), 1); mbar_init(bar(ACC1_EMPTY, s), 4);
       mbar_init(bar(A2_FULL, s), 4); mbar_init(bar(ACC2_FULL, s), 1); mbar_init(bar(ACC2_EMPTY, s), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // zero the interpolation matrix and both R stages (unused K rows / columns must be exact zeros, not stale NaNs)
-  for (uint32_t i = (uint32_t)tid * 16u; i < wa_bytes + (uint32_t)g.nr * r_stage_bytes; i += HU_THREADS * 16u)
+  // zero the interpolation matrix, the R stages (unused K rows / columns must be exact zeros, not stale NaNs) and the
+  // raw stages (phase 1 reads the slot of an unfetched corner with weight 0)
+  for (uint32_t i = (uint32_t)tid * 16u; i < wa_bytes + (uint32_t)g.nr * r_stage_bytes + (uint32_t)(g.nraw * g.raw_stage_bytes); i += HU_THREADS * 16u)
     *reinterpret_cast<uint4*>(sm + Smem::WA + i) = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 512) {
     // W2 (64 out x 64 in, bf16) into the K-major swizzled B tile: 512 chunks of 16 bytes
@@ -234,6 +248,27 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc0 = tmem_base, acc1 = tmem_base + 128u, acc2 = tmem_base + 256u;   // 2 x 64, 2 x 64, 2 x 16 columns
+  const uint32_t tmem_wa = tmem_base + 320u;                                           // 64 columns: the interpolation matrix
+  const uint32_t tmem_a1 = tmem_base + 384u, tmem_a2 = tmem_base + 448u;               // 2 x 32 columns each: relu(h1), relu(h2) in bf16
+  if (warp >= 4 && warp < 8) {
+    // The interpolation matrix is the A operand of every MMA 0 and never changes: it lives in tensor memory
+    // (128 lanes x 64 columns, two fp16 K elements per column), so MMA 0 reads no A bytes from shared memory.
+    const int v = (warp & 3) * 32 + lane;
+#pragma unroll
+    for (int c16 = 0; c16 < 4; ++c16) {
+      uint32_t r[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = 2 * (c16 * 16 + j);
+        r[j] = *reinterpret_cast<const uint32_t*>(sm + Smem::WA + (uint32_t)(k >> 6) * 16384u + sw128_offset((uint32_t)v, (uint32_t)((k & 63) >> 3)) + (uint32_t)(k & 7) * 2u);
+      }
+      tc_st16(tmem_wa + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c16 * 16), r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   // rows of this CTA: row0, row0 + row_step, ...; (n, t, h) advance by a fixed carry-propagated step (no divisions
   // in the per-row paths: the producer's planning latency is on the critical path of the whole pipeline)
@@ -285,7 +320,6 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     const uint32_t idesc1 = idesc_bf16_f32(128, 64), idesc2 = idesc_bf16_f32(128, 16);
     const uint64_t desc_w2 = smem_desc_sw128(sbase + Smem::W2B), desc_wh = smem_desc_sw128(sbase + Smem::WHB);
     const uint64_t desc_wa = smem_desc_sw128(sbase + Smem::WA), desc_r = smem_desc_sw128(sbase + r_off);
-    const uint64_t desc_at = smem_desc_sw128(sbase + Smem::AT);
     for (int k = 0; k < my_rows + 2; ++k) {
       if (k < my_rows) {
         const int s = k & 1; const uint32_t ph = (uint32_t)(k >> 1) & 1u;
@@ -301,7 +335,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < KSLABS * 4; ++kk)
-            tc_mma_bf16(d0, desc_wa + (uint64_t)((kk >> 2) * 1024 + 2 * (kk & 3)), db0 + (uint64_t)(kk * 128), idesc0, kk ? 1u : 0u);
+            tc_mma_ts_f16(d0, tmem_wa + (uint32_t)(kk * 8), db0 + (uint64_t)(kk * 128), idesc0, kk ? 1u : 0u);
           tc_commit(bar(R_EMPTY, rs));
           tc_commit(bar(ACC0_FULL, s));
         }
@@ -312,11 +346,12 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
         mbar_wait(bar(A1_FULL, s), ph);
         mbar_wait(bar(ACC1_EMPTY, s), ph ^ 1u);
         tc_fence_after();
-        const uint64_t da = desc_at + (uint64_t)(s * 1024);
+        const uint32_t ta = tmem_a1 + (uint32_t)(s * 32);
         const uint32_t d1 = acc1 + (uint32_t)(s * 64);
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(d1, da + (uint64_t)(2 * kk), desc_w2 + (uint64_t)(2 * kk), idesc1, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) tc_mma_ts_f16(d1, ta + (uint32_t)(8 * kk), desc_w2 + (uint64_t)(2 * kk), idesc1, kk > 0 ? 1u : 0u);
+          tc_commit(bar(A1_EMPTY, s));
           tc_commit(bar(ACC1_FULL, s));
         }
         __syncwarp();
@@ -326,12 +361,12 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
         mbar_wait(bar(A2_FULL, s), ph);
         mbar_wait(bar(ACC2_EMPTY, s), ph ^ 1u);
         tc_fence_after();
-        const uint64_t da = desc_at + (uint64_t)(s * 1024);
+        const uint32_t ta = tmem_a2 + (uint32_t)(s * 32);
         const uint32_t d2 = acc2 + (uint32_t)(s * 16);
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_bf16(d2, da + (uint64_t)(2 * kk), desc_wh + (uint64_t)(2 * kk), idesc2, kk > 0 ? 1u : 0u);
-          tc_commit(bar(A_EMPTY, s));
+          for (int kk = 0; kk < 4; ++kk) tc_mma_ts_f16(d2, ta + (uint32_t)(8 * kk), desc_wh + (uint64_t)(2 * kk), idesc2, kk > 0 ? 1u : 0u);
+          tc_commit(bar(A2_EMPTY, s));
           tc_commit(bar(ACC2_FULL, s));
         }
         __syncwarp();
@@ -346,10 +381,10 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
       for (int i = 0; i < my_rows; ++i) {
         const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
         mbar_wait_sleep(bar(ACC0_FULL, s), ph);
-        mbar_wait_sleep(bar(A_EMPTY, s), ph ^ 1u);        // MMA 2 of row i-2 has finished reading this A tile
+        mbar_wait_sleep(bar(A1_EMPTY, s), ph ^ 1u);       // MMA 1 of row i-2 has finished reading this A tile
         tc_fence_after();
         const uint32_t taddr = acc0 + lane_addr + (uint32_t)(s * 64);
-        uint8_t* arow = sm + Smem::AT + (uint32_t)s * 16384u;
+        const uint32_t aaddr = tmem_a1 + lane_addr + (uint32_t)(s * 32);
         uint32_t v0[16], v1[16];
         tc_ld16(taddr, v0);
         tc_ld16(taddr + 16u, v1);
@@ -363,22 +398,21 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
             pk[8 + j] = cvt_relu_bf16x2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
           }
           if (half == 0) { tc_ld16(taddr + 32u, v0); tc_ld16(taddr + 48u, v1); }
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(arow + sw128_offset((uint32_t)vrow, (uint32_t)(4 * half + c))) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          tc_st16(aaddr + (uint32_t)(16 * half), pk);       // 32 channels = 16 packed columns
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
-        fence_async_smem();
         __syncwarp();
         if (lane == 0) { mbar_arrive(bar(ACC0_EMPTY, s)); mbar_arrive(bar(A1_FULL, s)); }
       }
     } else if (role == 1) {
       for (int i = 0; i < my_rows; ++i) {
         const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-        mbar_wait_sleep(bar(ACC1_FULL, s), ph);           // MMA 1 done: acc1 complete AND the A tile may be overwritten
+        mbar_wait_sleep(bar(ACC1_FULL, s), ph);
+        mbar_wait_sleep(bar(A2_EMPTY, s), ph ^ 1u);       // MMA 2 of row i-2 has finished reading this A tile
         tc_fence_after();
         const uint32_t taddr = acc1 + lane_addr + (uint32_t)(s * 64);
-        uint8_t* arow = sm + Smem::AT + (uint32_t)s * 16384u;
+        const uint32_t aaddr = tmem_a2 + lane_addr + (uint32_t)(s * 32);
         uint32_t v0[16], v1[16];
         tc_ld16(taddr, v0);
         tc_ld16(taddr + 16u, v1);
@@ -394,12 +428,10 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
             pk[8 + j] = cvt_relu_bf16x2(__uint_as_float(v1[2 * j]) + bb.x, __uint_as_float(v1[2 * j + 1]) + bb.y);
           }
           if (half == 0) { tc_ld16(taddr + 32u, v0); tc_ld16(taddr + 48u, v1); }
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(arow + sw128_offset((uint32_t)vrow, (uint32_t)(4 * half + c))) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          tc_st16(aaddr + (uint32_t)(16 * half), pk);
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
-        fence_async_smem();
         __syncwarp();
         if (lane == 0) { mbar_arrive(bar(ACC1_EMPTY, s)); mbar_arrive(bar(A2_FULL, s)); }
       }
@@ -449,6 +481,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   } else {
     // ================================================================ phase 1: R = (T,H)-interpolated rows, bf16, MN-major swizzled
     const int ptid = (warp < 4 ? warp - 2 : warp - 14) * 32 + lane;       // 0 .. P1_THREADS-1
+    const int q1 = g.nx[wt][0] * 8, q2 = q1 + g.nx[wt][1] * 8, q3 = q2 + g.nx[wt][2] * 8, n_items = q3 + g.nx[wt][3] * 8;
     for (int i = 0; i < my_rows; ++i) {
       const int s = i % g.nr; const uint32_t ph = (uint32_t)(i / g.nr) & 1u;
       const int rs = i % g.nraw; const uint32_t rph = (uint32_t)(i / g.nraw) & 1u;
@@ -457,32 +490,50 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
       const TilePlan& pl = plans[rs];
       const uint8_t* stage = sm + raw_off0 + (uint32_t)rs * (uint32_t)g.raw_stage_bytes;
       uint8_t* rst = sm + r_off + (uint32_t)s * r_stage_bytes;
+      // One flat item list over the four levels (item = one low-resolution column x 8 channels), three items per thread
+      // processed together: this role's dependent-issue latency paces the whole pipeline (clock64 timeline), so the
+      // loads of all three items are issued before any arithmetic.  Corners 0/1 are read unconditionally (a corner
+      // that was not fetched has weight 0 and its slot holds finite stale data: the stages are zero-filled at start).
+      for (int q0 = ptid; q0 < n_items; q0 += 3 * P1_THREADS) {
+        uint4 ra[3], rb[3], rc[3], rd[3];
+        float4 wq[3];
+        int krow[3], itv[3];
+        bool on[3], four[3];
 #pragma unroll
-      for (int l = 0; l < 4; ++l) {
-        float wgt[4];
+        for (int u = 0; u < 3; ++u) {
+          const int q = q0 + u * P1_THREADS;
+          on[u] = q < n_items;
+          const int qq = on[u] ? q : 0;
+          const int l = (qq >= q1 ? 1 : 0) + (qq >= q2 ? 1 : 0) + (qq >= q3 ? 1 : 0);
+          const int it = qq - (l == 0 ? 0 : l == 1 ? q1 : l == 2 ? q2 : q3);
+          const uint32_t roff = (uint32_t)(l == 0 ? g.raw_off[0] : l == 1 ? g.raw_off[1] : l == 2 ? g.raw_off[2] : g.raw_off[3]);
+          const uint32_t cstride = (uint32_t)(l == 0 ? g.nxmax[0] : l == 1 ? g.nxmax[1] : l == 2 ? g.nxmax[2] : g.nxmax[3]) * 128u;
+          krow[u] = (l == 0 ? g.koff[0] : l == 1 ? g.koff[1] : l == 2 ? g.koff[2] : g.koff[3]) + (it >> 3);
+          itv[u] = it;
+          wq[u] = *reinterpret_cast<const float4*>(&pl.wgt[l][0]);
+          four[u] = (l == 0 ? a.tl[0] : l == 1 ? a.tl[1] : l == 2 ? a.tl[2] : a.tl[3]) != a.t;   // level has T corners
+          const uint8_t* src = stage + roff + (uint32_t)it * 16u;
+          ra[u] = *reinterpret_cast<const uint4*>(src);
+          rb[u] = *reinterpret_cast<const uint4*>(src + cstride);
+          rc[u] = rd[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (four[u]) { rc[u] = *reinterpret_cast<const uint4*>(src + 2u * cstride); rd[u] = *reinterpret_cast<const uint4*>(src + 3u * cstride); }
+        }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wgt[c] = pl.wgt[l][c];
-        const uint8_t* src = stage + g.raw_off[l];
-        const int items = g.nx[wt][l] * 8;
-        const uint32_t cstride = (uint32_t)g.nxmax[l] * 128u;
-        for (int it = ptid; it < items; it += P1_THREADS) {
-          const int x = it >> 3, j = it & 7;
-          float o[8];
+        for (int u = 0; u < 3; ++u) {
+          const uint32_t xa[4] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w}, xb[4] = {rb[u].x, rb[u].y, rb[u].z, rb[u].w};
+          const uint32_t xc[4] = {rc[u].x, rc[u].y, rc[u].z, rc[u].w}, xd[4] = {rd[u].x, rd[u].y, rd[u].z, rd[u].w};
+          uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = 0.f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (wgt[c] == 0.f) continue;
-            const uint4 r = *reinterpret_cast<const uint4*>(src + (uint32_t)c * cstride + (uint32_t)it * 16u);
-            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              o[2 * e] = fmaf(wgt[c], __uint_as_float(rr[e] << 16), o[2 * e]);
-              o[2 * e + 1] = fmaf(wgt[c], __uint_as_float(rr[e] & 0xffff0000u), o[2 * e + 1]);
+          for (int e = 0; e < 4; ++e) {
+            float lo = wq[u].x * __uint_as_float(xa[e] << 16), hi = wq[u].x * __uint_as_float(xa[e] & 0xffff0000u);
+            lo = fmaf(wq[u].y, __uint_as_float(xb[e] << 16), lo); hi = fmaf(wq[u].y, __uint_as_float(xb[e] & 0xffff0000u), hi);
+            if (four[u]) {
+              lo = fmaf(wq[u].z, __uint_as_float(xc[e] << 16), lo); hi = fmaf(wq[u].z, __uint_as_float(xc[e] & 0xffff0000u), hi);
+              lo = fmaf(wq[u].w, __uint_as_float(xd[e] << 16), lo); hi = fmaf(wq[u].w, __uint_as_float(xd[e] & 0xffff0000u), hi);
             }
+            pk[e] = cvt_f16x2_sat(lo, hi);
           }
-          const uint4 pk = make_uint4(cvt_f16x2_sat(o[0], o[1]), cvt_f16x2_sat(o[2], o[3]), cvt_f16x2_sat(o[4], o[5]), cvt_f16x2_sat(o[6], o[7]));
-          *reinterpret_cast<uint4*>(rst + sw128_offset((uint32_t)(g.koff[l] + x), (uint32_t)j)) = pk;
+          if (on[u]) *reinterpret_cast<uint4*>(rst + sw128_offset((uint32_t)krow[u], (uint32_t)(itv[u] & 7))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
       fence_async_smem();
@@ -499,7 +550,40 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   }
 }
 
+// Temporal pre-pass: levels at reduced temporal resolution are interpolated along T once per output frame
+// (trilinear is separable; align_corners=True), so that the head only ever needs the two H corner rows of a level.
+__global__ void __launch_bounds__(256) temporal_upsample_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int tl, int t,
+                                                                int64_t frame16) {
+  const int to = blockIdx.y; const int64_t n = blockIdx.z;
+  const AxisTap at = axis_tap(to, tl, t);
+  const uint4* a0 = in + (n * tl + at.i0) * frame16;
+  const uint4* a1 = in + (n * tl + at.i1) * frame16;
+  uint4* o = out + (n * t + to) * frame16;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < frame16; i += (int64_t)gridDim.x * 256) {
+    const uint4 x = __ldg(a0 + i);
+    if (at.l1 == 0.f) { o[i] = x; continue; }
+    const uint4 y = __ldg(a1 + i);
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float lo = at.l0 * __uint_as_float(xs[e] << 16) + at.l1 * __uint_as_float(ys[e] << 16);
+      const float hi = at.l0 * __uint_as_float(xs[e] & 0xffff0000u) + at.l1 * __uint_as_float(ys[e] & 0xffff0000u);
+      r[e] = cvt_bf16x2(lo, hi);
+    }
+    o[i] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
 }  // namespace
+
+int launch_temporal_upsample_bf16(const void* in, void* out, int n, int tl, int t, int hl, int wl, cudaStream_t stream) {
+  const int64_t frame16 = (int64_t)hl * wl * HC * 2 / 16;
+  const int bx = (int)std::min<int64_t>(cdiv(frame16, 256), 32);
+  temporal_upsample_kernel<<<dim3((unsigned)bx, (unsigned)t, (unsigned)n), 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), tl, t, frame16);
+  CLASFV_CUDA(cudaGetLastError());
+  return CLASFV_OK;
+}
 
 int launch_head_umma(const HeadArgs& a, cudaStream_t stream) {
   CLASFV_REQUIRE(a.g_dtype == CLASFV_BF16 && a.w2_bf16, "head_umma: bf16 lateral maps and bf16 W2 required");
@@ -532,8 +616,11 @@ int launch_head_umma(const HeadArgs& a, cudaStream_t stream) {
   g.total_rows = (int)total;
   // three R stages matter more than three raw stages (ncu: phase 1 otherwise idles a third of the time on R_EMPTY)
   const size_t base_bytes = 1024 + Smem::WA + (size_t)KSLABS * 16384, r_stage = (size_t)KSLABS * 8192, limit = 227 * 1024;
-  g.nr = base_bytes + NR * r_stage + 2 * (size_t)g.raw_stage_bytes <= limit ? NR : 2;
-  g.nraw = base_bytes + g.nr * r_stage + (size_t)NRAW * g.raw_stage_bytes <= limit ? NRAW : 2;
+  // The row rate is (bulk-copy latency + phase 1 + hand-offs) / raw stages (clock64 timeline): raw stages
+  // first, a third R stage only if it is free.
+  g.nr = 2;
+  for (g.nraw = NRAW; g.nraw > 2 && base_bytes + 2 * r_stage + (size_t)g.nraw * g.raw_stage_bytes > limit; --g.nraw) {}
+  if (base_bytes + NR * r_stage + (size_t)g.nraw * g.raw_stage_bytes <= limit) g.nr = NR;
   const size_t smem = base_bytes + g.nr * r_stage + (size_t)g.nraw * g.raw_stage_bytes;
   CLASFV_REQUIRE(smem <= 227 * 1024, "head_umma: shared memory overflow (%zu bytes, W=%d)", smem, a.w);
   int dev = 0, sms = 0;

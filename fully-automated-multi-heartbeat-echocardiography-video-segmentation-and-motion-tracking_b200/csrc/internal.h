@@ -115,6 +115,8 @@ struct HeadArgs {
 };
 int launch_head(const HeadArgs& a, cudaStream_t stream);        // CUDA-core head (fp32 g)
 int launch_head_umma(const HeadArgs& a, cudaStream_t stream);   // tcgen05 head (bf16 g), decoder_umma.cu
+// (n,tl,hl,wl,64) bf16 -> (n,t,hl,wl,64) bf16, linear along T, align_corners=True (pre-pass of the tcgen05 head)
+int launch_temporal_upsample_bf16(const void* in, void* out, int n, int tl, int t, int hl, int wl, cudaStream_t stream);
 
 // fusion.cu
 int launch_warp(const float* src, const float* flow, float* out, int n, int c, int h, int w, cudaStream_t s);
