@@ -481,60 +481,67 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   } else {
     // ================================================================ phase 1: R = (T,H)-interpolated rows, bf16, MN-major swizzled
     const int ptid = (warp < 4 ? warp - 2 : warp - 14) * 32 + lane;       // 0 .. P1_THREADS-1
+    // One flat item list over the four levels (item = one low-resolution column x 8 channels), P1_ITEMS per thread.
+    // The item -> (level, column, chunk) mapping is the same for every row, so everything but the loads and the
+    // arithmetic is hoisted out of the row loop: this role's instruction stream paces the pipeline (clock64 timeline).
+    constexpr int P1_ITEMS = 4;
     const int q1 = g.nx[wt][0] * 8, q2 = q1 + g.nx[wt][1] * 8, q3 = q2 + g.nx[wt][2] * 8, n_items = q3 + g.nx[wt][3] * 8;
+    uint32_t i_src[P1_ITEMS], i_cstride[P1_ITEMS], i_dst[P1_ITEMS], i_wgt[P1_ITEMS];
+    bool i_on[P1_ITEMS], i_four[P1_ITEMS];
+#pragma unroll
+    for (int u = 0; u < P1_ITEMS; ++u) {
+      const int q = ptid + u * P1_THREADS;
+      i_on[u] = q < n_items;
+      const int qq = i_on[u] ? q : 0;
+      const int l = (qq >= q1 ? 1 : 0) + (qq >= q2 ? 1 : 0) + (qq >= q3 ? 1 : 0);
+      const int it = qq - (l == 0 ? 0 : l == 1 ? q1 : l == 2 ? q2 : q3);
+      i_src[u] = (uint32_t)g.raw_off[l] + (uint32_t)it * 16u;
+      i_cstride[u] = (uint32_t)g.nxmax[l] * 128u;
+      i_dst[u] = sw128_offset((uint32_t)(g.koff[l] + (it >> 3)), (uint32_t)(it & 7));
+      i_wgt[u] = (uint32_t)l * 16u;
+      i_four[u] = a.tl[l] != a.t;                  // the level has T corners (4 slots); otherwise only its 2 H corners exist
+    }
     for (int i = 0; i < my_rows; ++i) {
       const int s = i % g.nr; const uint32_t ph = (uint32_t)(i / g.nr) & 1u;
       const int rs = i % g.nraw; const uint32_t rph = (uint32_t)(i / g.nraw) & 1u;
-      mbar_wait_sleep(bar(RAW_FULL, rs), rph);
-      mbar_wait_sleep(bar(R_EMPTY, s), ph ^ 1u);          // MMA 0 of row i-nr has finished reading this R stage
-      const TilePlan& pl = plans[rs];
+      mbar_wait(bar(RAW_FULL, rs), rph);
+      mbar_wait(bar(R_EMPTY, s), ph ^ 1u);               // MMA 0 of row i-nr has finished reading this R stage
+      const uint8_t* plw = reinterpret_cast<const uint8_t*>(&plans[rs]);
       const uint8_t* stage = sm + raw_off0 + (uint32_t)rs * (uint32_t)g.raw_stage_bytes;
       uint8_t* rst = sm + r_off + (uint32_t)s * r_stage_bytes;
-      // One flat item list over the four levels (item = one low-resolution column x 8 channels), three items per thread
-      // processed together: this role's dependent-issue latency paces the whole pipeline (clock64 timeline), so the
-      // loads of all three items are issued before any arithmetic.  Corners 0/1 are read unconditionally (a corner
-      // that was not fetched has weight 0 and its slot holds finite stale data: the stages are zero-filled at start).
-      for (int q0 = ptid; q0 < n_items; q0 += 3 * P1_THREADS) {
-        uint4 ra[3], rb[3], rc[3], rd[3];
-        float4 wq[3];
-        int krow[3], itv[3];
-        bool on[3], four[3];
+      // Corners 0/1 are read unconditionally (a corner that was not fetched has weight 0 and its slot holds finite
+      // stale data: the stages are zero-filled at start); all loads are issued before any arithmetic.
+      uint4 ra[P1_ITEMS], rb[P1_ITEMS];
+      float4 wq[P1_ITEMS];
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          const int q = q0 + u * P1_THREADS;
-          on[u] = q < n_items;
-          const int qq = on[u] ? q : 0;
-          const int l = (qq >= q1 ? 1 : 0) + (qq >= q2 ? 1 : 0) + (qq >= q3 ? 1 : 0);
-          const int it = qq - (l == 0 ? 0 : l == 1 ? q1 : l == 2 ? q2 : q3);
-          const uint32_t roff = (uint32_t)(l == 0 ? g.raw_off[0] : l == 1 ? g.raw_off[1] : l == 2 ? g.raw_off[2] : g.raw_off[3]);
-          const uint32_t cstride = (uint32_t)(l == 0 ? g.nxmax[0] : l == 1 ? g.nxmax[1] : l == 2 ? g.nxmax[2] : g.nxmax[3]) * 128u;
-          krow[u] = (l == 0 ? g.koff[0] : l == 1 ? g.koff[1] : l == 2 ? g.koff[2] : g.koff[3]) + (it >> 3);
-          itv[u] = it;
-          wq[u] = *reinterpret_cast<const float4*>(&pl.wgt[l][0]);
-          four[u] = (l == 0 ? a.tl[0] : l == 1 ? a.tl[1] : l == 2 ? a.tl[2] : a.tl[3]) != a.t;   // level has T corners
-          const uint8_t* src = stage + roff + (uint32_t)it * 16u;
-          ra[u] = *reinterpret_cast<const uint4*>(src);
-          rb[u] = *reinterpret_cast<const uint4*>(src + cstride);
-          rc[u] = rd[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (four[u]) { rc[u] = *reinterpret_cast<const uint4*>(src + 2u * cstride); rd[u] = *reinterpret_cast<const uint4*>(src + 3u * cstride); }
+      for (int u = 0; u < P1_ITEMS; ++u) {
+        if (!i_on[u]) continue;
+        wq[u] = *reinterpret_cast<const float4*>(plw + i_wgt[u]);
+        ra[u] = *reinterpret_cast<const uint4*>(stage + i_src[u]);
+        rb[u] = *reinterpret_cast<const uint4*>(stage + i_src[u] + i_cstride[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < P1_ITEMS; ++u) {
+        if (!i_on[u]) continue;
+        const uint32_t xa[4] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w}, xb[4] = {rb[u].x, rb[u].y, rb[u].z, rb[u].w};
+        float lo[4], hi[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          lo[e] = wq[u].x * __uint_as_float(xa[e] << 16); hi[e] = wq[u].x * __uint_as_float(xa[e] & 0xffff0000u);
+          lo[e] = fmaf(wq[u].y, __uint_as_float(xb[e] << 16), lo[e]); hi[e] = fmaf(wq[u].y, __uint_as_float(xb[e] & 0xffff0000u), hi[e]);
         }
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          const uint32_t xa[4] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w}, xb[4] = {rb[u].x, rb[u].y, rb[u].z, rb[u].w};
-          const uint32_t xc[4] = {rc[u].x, rc[u].y, rc[u].z, rc[u].w}, xd[4] = {rd[u].x, rd[u].y, rd[u].z, rd[u].w};
-          uint32_t pk[4];
+        if (i_four[u]) {
+          const uint4 rc = *reinterpret_cast<const uint4*>(stage + i_src[u] + 2u * i_cstride[u]);
+          const uint4 rd = *reinterpret_cast<const uint4*>(stage + i_src[u] + 3u * i_cstride[u]);
+          const uint32_t xc[4] = {rc.x, rc.y, rc.z, rc.w}, xd[4] = {rd.x, rd.y, rd.z, rd.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float lo = wq[u].x * __uint_as_float(xa[e] << 16), hi = wq[u].x * __uint_as_float(xa[e] & 0xffff0000u);
-            lo = fmaf(wq[u].y, __uint_as_float(xb[e] << 16), lo); hi = fmaf(wq[u].y, __uint_as_float(xb[e] & 0xffff0000u), hi);
-            if (four[u]) {
-              lo = fmaf(wq[u].z, __uint_as_float(xc[e] << 16), lo); hi = fmaf(wq[u].z, __uint_as_float(xc[e] & 0xffff0000u), hi);
-              lo = fmaf(wq[u].w, __uint_as_float(xd[e] << 16), lo); hi = fmaf(wq[u].w, __uint_as_float(xd[e] & 0xffff0000u), hi);
-            }
-            pk[e] = cvt_f16x2_sat(lo, hi);
+            lo[e] = fmaf(wq[u].z, __uint_as_float(xc[e] << 16), lo[e]); hi[e] = fmaf(wq[u].z, __uint_as_float(xc[e] & 0xffff0000u), hi[e]);
+            lo[e] = fmaf(wq[u].w, __uint_as_float(xd[e] << 16), lo[e]); hi[e] = fmaf(wq[u].w, __uint_as_float(xd[e] & 0xffff0000u), hi[e]);
           }
-          if (on[u]) *reinterpret_cast<uint4*>(rst + sw128_offset((uint32_t)krow[u], (uint32_t)(itv[u] & 7))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+        *reinterpret_cast<uint4*>(rst + i_dst[u]) =
+            make_uint4(cvt_f16x2_sat(lo[0], hi[0]), cvt_f16x2_sat(lo[1], hi[1]), cvt_f16x2_sat(lo[2], hi[2]), cvt_f16x2_sat(lo[3], hi[3]));
       }
       fence_async_smem();
       __syncwarp();
