@@ -177,10 +177,12 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
 // votes are read from global memory as coalesced pair loads, and the eight bilinear taps of a hop are LDS.  The
 // order of additions per pixel is exactly warp_fuse_kernel's (clip by clip: direct, forward hop, backward hop), so
 // both kernels give bit-identical sums.  No float atomics, no intermediate warped volume.
-constexpr int WS_THREADS = 1024;
-constexpr int WS_CONSUMERS = WS_THREADS - 32;       // warp 0 is the producer
-constexpr int WS_PAIRS = 4;                         // pixel pairs per consumer thread
 constexpr int WS_MAX_UNITS = 8;
+// CTA shape per element type (measured, config 3): fp32 runs best with 512 threads x 7 pixel pairs (128 registers, no
+// spills, more ILP per thread), bf16 with 1024 threads x 4 pairs (its 2-byte taps are latency-, not register-bound).
+template <typename T> struct WsShape;
+template <> struct WsShape<float> { static constexpr int THREADS = 512, PAIRS = 7; };
+template <> struct WsShape<__nv_bfloat16> { static constexpr int THREADS = 1024, PAIRS = 4; };
 
 template <typename T> struct Pair;
 template <> struct Pair<float> {
@@ -197,20 +199,44 @@ template <> __device__ __forceinline__ float lds_val<float>(const float* p) { re
 template <> __device__ __forceinline__ float lds_val<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(p)) << 16);
 }
+// Branch-free bilinear taps for the staged kernel.  grid_sample(padding_mode="border") clamps the source coordinate to
+// [0, S-1] BEFORE splitting it, so a corner that falls outside the plane always has weight exactly 0 (x0 == W-1 implies
+// ix == W-1): reading the clamped neighbour instead and adding 0 * finite gives the same sum as skipping the tap.
+struct Taps { int p, dx, dy; float nw, ne, sw, se; };
+__device__ __forceinline__ Taps taps_setup(float bx, float by, float fx, float fy, int h, int w) {
+  const float gx = bx + fx, gy = by + fy;
+  float ix = ((gx + 1.f) * (float)w - 1.f) * 0.5f;
+  float iy = ((gy + 1.f) * (float)h - 1.f) * 0.5f;
+  ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
+  iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const float x1 = fx0 + 1.f, y1 = fy0 + 1.f;
+  Taps t;
+  t.nw = (x1 - ix) * (y1 - iy);
+  t.ne = (ix - fx0) * (y1 - iy);
+  t.sw = (x1 - ix) * (iy - fy0);
+  t.se = (ix - fx0) * (iy - fy0);
+  t.p = y0 * w + x0;
+  t.dx = x0 + 1 < w ? 1 : 0;
+  t.dy = y0 + 1 < h ? w : 0;
+  return t;
+}
 template <typename T>
-__device__ __forceinline__ float bilinear_fetch_smem(const T* plane, const Bilinear& b, int w) {
-  const T* p = plane + b.y0 * w + b.x0;
-  float v = lds_val<T>(p) * b.nw;
-  if (b.x1ok) v += lds_val<T>(p + 1) * b.ne;
-  if (b.y1ok) v += lds_val<T>(p + w) * b.sw;
-  if (b.x1ok && b.y1ok) v += lds_val<T>(p + w + 1) * b.se;
+__device__ __forceinline__ float taps_fetch(const T* plane, const Taps& t) {
+  const T* p = plane + t.p;
+  float v = lds_val<T>(p) * t.nw;
+  v += lds_val<T>(p + t.dx) * t.ne;
+  v += lds_val<T>(p + t.dy) * t.sw;
+  v += lds_val<T>(p + t.dy + t.dx) * t.se;
   return v;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const WarpFuseArgs a, int n_units, int slice_pix) {
+__global__ void __launch_bounds__(WsShape<T>::THREADS, 1) warp_fuse_staged_kernel(const WarpFuseArgs a, int n_units, int slice_pix) {
   extern __shared__ __align__(128) uint8_t ws_smem[];
   using namespace ptx;
+  constexpr int WS_THREADS = WsShape<T>::THREADS, WS_PAIRS = WsShape<T>::PAIRS, WS_CONSUMERS = WS_THREADS - 32;   // warp 0 = producer
   const int g = blockIdx.y;
   const int hw = a.h * a.w;
   const int L = a.clip_len;
@@ -317,12 +343,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
 #pragma unroll
         for (int k = 0; k < WS_PAIRS; ++k) {
           if (px[k] < 0) continue;
-          const Bilinear ba = bilinear_setup_base(bx0[k], by[k], fx[k].x, fy[k].x, a.h, a.w);
-          s0[2 * k] += bilinear_fetch_smem<T>(u0, ba, a.w);
-          s1[2 * k] += bilinear_fetch_smem<T>(u1, ba, a.w);
-          const Bilinear bb = bilinear_setup_base(bx1[k], by[k], fx[k].y, fy[k].y, a.h, a.w);
-          s0[2 * k + 1] += bilinear_fetch_smem<T>(u0, bb, a.w);
-          s1[2 * k + 1] += bilinear_fetch_smem<T>(u1, bb, a.w);
+          const Taps ta = taps_setup(bx0[k], by[k], fx[k].x, fy[k].x, a.h, a.w);
+          s0[2 * k] += taps_fetch<T>(u0, ta);
+          s1[2 * k] += taps_fetch<T>(u1, ta);
+          const Taps tb = taps_setup(bx1[k], by[k], fx[k].y, fy[k].y, a.h, a.w);
+          s0[2 * k + 1] += taps_fetch<T>(u0, tb);
+          s1[2 * k + 1] += taps_fetch<T>(u1, tb);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + 8u * (n_units + u));
@@ -478,7 +504,8 @@ int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
     const bool aligned = (hw * es) % 16 == 0 && a.w % 2 == 0 && ((uintptr_t)a.prob % 16) == 0 && ((uintptr_t)a.acc % 8) == 0 &&
                          (!a.mask || ((uintptr_t)a.mask % 2) == 0);
     if (units >= 2 && aligned && !no_staged) {
-      const int per_cta = WS_CONSUMERS * 2 * WS_PAIRS;
+      const int per_cta = a.dtype == CLASFV_F32 ? (WsShape<float>::THREADS - 32) * 2 * WsShape<float>::PAIRS
+                                                : (WsShape<__nv_bfloat16>::THREADS - 32) * 2 * WsShape<__nv_bfloat16>::PAIRS;
       const int slices = (int)cdiv(hw, per_cta);
       int slice_pix = (int)cdiv(hw, slices);
       slice_pix += slice_pix & 1;                           // even: pixel pairs
@@ -486,10 +513,10 @@ int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
       dim3 grid((unsigned)slices, (unsigned)a.t_out);
       if (a.dtype == CLASFV_F32) {
         CLASFV_CUDA(cudaFuncSetAttribute(warp_fuse_staged_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        warp_fuse_staged_kernel<float><<<grid, WS_THREADS, smem, s>>>(a, units, slice_pix);
+        warp_fuse_staged_kernel<float><<<grid, WsShape<float>::THREADS, smem, s>>>(a, units, slice_pix);
       } else {
         CLASFV_CUDA(cudaFuncSetAttribute(warp_fuse_staged_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        warp_fuse_staged_kernel<__nv_bfloat16><<<grid, WS_THREADS, smem, s>>>(a, units, slice_pix);
+        warp_fuse_staged_kernel<__nv_bfloat16><<<grid, WsShape<__nv_bfloat16>::THREADS, smem, s>>>(a, units, slice_pix);
       }
       CLASFV_CUDA(cudaGetLastError());
       return CLASFV_OK;

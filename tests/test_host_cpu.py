@@ -96,3 +96,36 @@ def test_ef_from_synthetic_beating_masks():
     assert all(45 < ef < 70 for ef in efs), efs
     length, radii = get2dPucks(masks[0].astype(int), (1.0, 1.0))
     assert 55 < length < 65 and len(radii) == 10
+
+
+def test_forward_windows_groups_equally_spaced_runs_into_single_calls():
+    """Engine.forward_windows hands every maximal run of equally spaced windows to ONE clasfv_forward call (that is
+    what lets the library share the stem and layer1 between overlapping windows); host logic only, no GPU."""
+    import torch
+    from clasfv_b200.engine import Engine
+
+    class Recorder(Engine):
+        def __init__(self):
+            self.calls, self.options = [], {}
+
+        def set_option(self, name, value):
+            self.options[name] = value
+
+        def forward_into(self, x, seg, mot, out_kind, clip_starts=None, clip_len=None):
+            assert seg.shape[0] == len(clip_starts) == mot.shape[0]
+            self.calls.append(list(clip_starts))
+
+        def __del__(self):
+            pass
+
+    video = torch.zeros(3, 64, 4, 4)
+    for starts, expect in [
+        (list(range(0, 33)), [list(range(0, 33))]),                               # stride 1: one call
+        ([0, 2, 4, 6, 7], [[0, 2, 4, 6], [7]]),                                   # the appended tail window is off the grid
+        ([5], [[5]]),
+        ([0, 3, 6, 10, 14, 18], [[0, 3, 6], [10, 14, 18]]),
+    ]:
+        eng = Recorder()
+        seg = torch.zeros(len(starts), 2, 32, 4, 4); mot = torch.zeros(len(starts), 4, 32, 4, 4)
+        eng.forward_windows(video, seg, mot, 1, starts, 32, batch_clips=7)
+        assert eng.calls == expect and eng.options == {"sub_batch": 7}
