@@ -261,7 +261,9 @@ def main():
         algorithmic_tflops = TRUNK_GFLOP_PER_CLIP * N_CLIPS / trunk_ms_per_step
         achieved_tflops = performed_tflops
         n_batches = (N_CLIPS + bc - 1) // bc
-        launches_per_step = (n_batches * KERNELS_PER_FORWARD if args.per_clip else 10 + n_batches * (16 + 32)) + 1
+        # dense schedule: 10 video-level launches; per batch 14 edge convs + 2 gathers + 27 layer2-4 convs + 4 lateral + 3 temporal
+        # pre-pass + 1 head; + 1 fusion kernel per video (ncu launch list: profiles/r01y_launches_bench_steps1.csv)
+        launches_per_step = (n_batches * (KERNELS_PER_FORWARD + 3) if args.per_clip else 10 + n_batches * 51) + 1
         elt = 2 if args.precision == "bf16" else 4
         fuse_bytes = N_CLIPS * CLIP * H * W * 6 * elt + T_VIDEO * H * W * (8 + 1) + T_VIDEO * 8
         line = {
@@ -286,7 +288,9 @@ def main():
                                      "dense-video: stem+layer1 once per video frame, clip-edge frames per clip (bit-identical outputs)"},
             "roofline_warp_fuse": {"kernel": "warp_fuse_kernel", "bound": "hbm", "achieved": fuse_bytes / (fuse_ms * 1e6),
                                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fuse_bytes / (fuse_ms * 1e6) / peaks["hbm_gbs"],
-                                   "traffic": None, "algorithmic_bytes": fuse_bytes},
+                                   "traffic": None, "algorithmic_bytes": fuse_bytes,
+                                   "traffic_note": "ncu --set full of the same kernel on configs[2] (256 clips): DRAM read+write / algorithmic "
+                                                   "bytes = 1.00 fp32, 0.99 bf16 (profiles/r01y_wf_ncu.csv); instruction-bound, see DESIGN.md 4.5"},
             "clocks": clocks, "mean_abs_flow_px": flow_px,
         }
         if world == 1 and not args.no_cpu_baseline:
