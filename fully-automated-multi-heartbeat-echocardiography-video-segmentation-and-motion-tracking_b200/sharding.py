@@ -76,14 +76,18 @@ def touched_window(my_starts, num_frames, edge_hops=False):
     return (max(0, my_starts[0] - e), min(num_frames, my_starts[-1] + CLIP + e))
 
 
-def exchange_partials(acc, cnt, window, owners, group=None):
+def exchange_partials(acc, cnt, window, owners, group=None, windows=None):
     """acc (hi-lo, 2, H, W), cnt (hi-lo,) = this rank's partial sums over frames window=[lo,hi).
     Returns (acc_owned, cnt_owned) over this rank's owned frames with every rank's votes added.
-    The windows of all ranks are all-gathered as 2 integers each; the frame data moves point-to-point."""
+    ``windows`` = the [lo,hi) of every rank when the caller can derive them (the clip plan is deterministic), else they
+    are all-gathered as 2 integers each; the frame data moves point-to-point between neighbours."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi = window
-    wins = [None] * world
-    dist.all_gather_object(wins, (int(lo), int(hi)), group=group)
+    if windows is not None:
+        wins = [(int(a), int(b)) for a, b in windows]
+    else:
+        wins = [None] * world
+        dist.all_gather_object(wins, (int(lo), int(hi)), group=group)
     f0, f1 = owners[rank]
     h, w = acc.shape[-2:]
     acc_own = torch.zeros((f1 - f0, 2, h, w), dtype=acc.dtype, device=acc.device)
@@ -128,8 +132,9 @@ def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=32, gr
     net = _unwrap(model)
     eng = net.engine()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    v = _to_device_video(video, eng.device)
-    num_frames, h, w = int(v.shape[1]), int(v.shape[2]), int(v.shape[3])
+    if getattr(video, "ndim", None) != 4 or video.shape[0] != 3:
+        raise ValueError(f"expected a video of shape (3,T,H,W), got {tuple(video.shape)}")
+    num_frames, h, w = int(video.shape[1]), int(video.shape[2]), int(video.shape[3])
     starts = clip_starts_for_video(num_frames, step)
     ranges = partition_clips(len(starts), world)
     owners = frame_owners(starts, ranges, num_frames)
@@ -137,26 +142,34 @@ def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=32, gr
     mine = starts[c0:c1]
     lo, hi = touched_window(mine, num_frames, edge_hops)
     out_dtype = torch.float32 if eng.precision == 0 else torch.bfloat16
+    dev = eng.device
     if mine:
-        prob = torch.empty((len(mine), 2, CLIP, h, w), dtype=out_dtype, device=v.device)
-        mot = torch.empty((len(mine), 4, CLIP, h, w), dtype=out_dtype, device=v.device)
-        eng.forward_windows(v, prob, mot, OUT_PROB, mine, CLIP, batch_clips)
+        # only the frames this rank's clips read go to its GPU (a 2000-frame 224x224 video is 1.2 GB as fp32)
+        fa, fb = mine[0], mine[-1] + CLIP
+        v = _to_device_video(video[:, fa:fb], dev)
+        prob = torch.empty((len(mine), 2, CLIP, h, w), dtype=out_dtype, device=dev)
+        mot = torch.empty((len(mine), 4, CLIP, h, w), dtype=out_dtype, device=dev)
+        eng.forward_windows(v, prob, mot, OUT_PROB, [s - fa for s in mine], CLIP, batch_clips)
         res = eng.warp_fuse(prob, mot, [s - lo for s in mine], hi - lo, edge_hops=edge_hops, want_mask=False, want_area=False)
         acc, cnt = res["acc"], res["cnt"]
     else:
-        acc = torch.zeros((0, 2, h, w), dtype=torch.float32, device=v.device)
-        cnt = torch.zeros((0,), dtype=torch.int32, device=v.device)
-    acc_own, cnt_own = exchange_partials(acc, cnt, (lo, hi), owners, group)
+        acc = torch.zeros((0, 2, h, w), dtype=torch.float32, device=dev)
+        cnt = torch.zeros((0,), dtype=torch.int32, device=dev)
+    windows = [touched_window(starts[a:b], num_frames, edge_hops) for a, b in ranges]
+    acc_own, cnt_own = exchange_partials(acc, cnt, (lo, hi), owners, group, windows=windows)
     f0, f1 = owners[rank]
     if f1 > f0:
         mask, _area = _engine.finalize_mask(acc_own.contiguous())
     else:
-        mask = torch.zeros((0, h, w), dtype=torch.uint8, device=v.device)
+        mask = torch.zeros((0, h, w), dtype=torch.uint8, device=dev)
     if not gather:
         return mask.cpu().numpy().astype(np.int64), (f0, f1)
-    parts = [None] * world
-    dist.all_gather_object(parts, (f0, mask.cpu().numpy()), group=group)
-    full = np.zeros((num_frames, h, w), dtype=np.int64)
-    for pf0, pm in parts:
-        full[pf0:pf0 + pm.shape[0]] = pm
-    return full
+    # device-side gather of the owned masks (padded to the largest owned range), one host copy at the end
+    most = max(b - a for a, b in owners)
+    padded = torch.zeros((most, h, w), dtype=torch.uint8, device=dev)
+    padded[:f1 - f0] = mask
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    full = torch.cat([p[:b - a] for p, (a, b) in zip(parts, owners)], 0)
+    assert full.shape[0] == num_frames
+    return full.to(torch.int64).cpu().numpy()
