@@ -17,13 +17,14 @@
 // its B operand is R, built per row in shared memory directly in the MN-major SWIZZLE_128B layout (K rows of 64
 // channels = 128 bytes).  ReLU + bf16 conversion of an accumulator is one cvt.rn.relu.bf16x2.f32 per two values.
 //
-// Warp roles (768 threads, persistent, one CTA per SM); every hand-over is an mbarrier, every buffer is doubled:
+// Warp roles (768 threads, persistent, one CTA per SM); every hand-over is an mbarrier, every buffer is at least doubled.
+// Phase 1 is the throughput-limiting role (clock64 timeline), so it gets every warp the epilogues can spare:
 //   warp 0           producer: plans the row (corner indices / weights), bulk-copies its raw corner rows (bf16)
 //   warp 1           MMA issuer (one lane): per step MMA0(i), MMA1(i-1), MMA2(i-2)
-//   warps 4-7        epilogue 0: acc0 -> relu -> bf16 -> tensor memory (A operand of MMA 1)   (one warp per lane quarter)
-//   warps 8-11       epilogue 1: acc1 + b2 -> relu -> bf16 -> tensor memory (A operand of MMA 2)
-//   warps 12-15      epilogue 2: acc2 + bh -> softmax / tanh -> global
-//   warps 2,3,16-23  phase 1: raw corner rows -> R
+//   warps 4-7        epilogue 0 of row i (acc0 -> relu -> bf16 -> tensor memory = A of MMA 1) and epilogue 2 of row i-2
+//                    (acc2 + bh -> softmax / tanh -> global); one warp per TMEM lane quarter
+//   warps 8-11       epilogue 1 (acc1 -> relu -> bf16 -> tensor memory = A of MMA 2; comb_2's bias rides in K)
+//   warps 2,3,12-23  phase 1: raw corner rows -> R (two groups of 7 warps on alternate rows)
 #include "internal.h"
 #include "umma_ptx.cuh"
 
@@ -38,7 +39,7 @@ using namespace ptx;
 
 constexpr int HU_THREADS = 768;
 constexpr int HC = 64;
-constexpr int P1_WARPS = 10;
+constexpr int P1_WARPS = 14;
 constexpr int P1_THREADS = P1_WARPS * 32;
 constexpr int MAX_WT = 4;                 // w tiles of 128 voxels (W <= 512)
 constexpr int NRAW = 4;                   // raw corner-row stages wanted (as many as fit shared memory, at least 2)
@@ -134,15 +135,14 @@ struct HeadGeom {                 // host-computed layout of the K axis of MMA 0
 struct TilePlan { float wgt[4][4]; };   // weight of each (T,H) corner per level, [level][2*tc + hc]; 0 = corner not fetched
 
 struct Smem {                     // byte offsets from the 1024-aligned base
-  static constexpr uint32_t W2B = 0;                      // 64 x 128 B   W2, K-major
-  static constexpr uint32_t WHB = W2B + 8192;             // 16 x 128 B   heads, K-major (rows 6..15 zero)
-  static constexpr uint32_t B2 = WHB + 2048;              // [64] fp32
-  static constexpr uint32_t BH = B2 + 256;                // [8] fp32
+  static constexpr uint32_t W2B = 0;                      // 2 slabs of 64 x 128 B: W2 (K 0..63), then K 64..79 = {b2 hi, b2 lo, 0...}
+  static constexpr uint32_t WHB = W2B + 16384;            // 16 x 128 B   heads, K-major (rows 6..15 zero)
+  static constexpr uint32_t BH = WHB + 2048;              // [8] fp32
   static constexpr uint32_t PLAN = BH + 32;               // NRAW x TilePlan
   static constexpr uint32_t BARS = PLAN + NRAW * 64;      // 14 groups of up to 4 mbarriers
   static constexpr uint32_t TMEM = BARS + 8 * 56;
-  static constexpr uint32_t WA = 12288;                   // interpolation matrix (fp16), staging only: KSLABS slabs of 16 KB
-  // then: R (2 stages x nslab x 8 KB), raw (2 stages x raw_stage_bytes)
+  static constexpr uint32_t WA = 20480;                   // interpolation matrix (fp16), staging only: KSLABS slabs of 16 KB
+  // then: R (nr stages x KSLABS x 8 KB), raw (nraw stages x raw_stage_bytes)
 };
 static_assert(Smem::TMEM + 4 <= Smem::WA, "head smem header overflow");
 static_assert(sizeof(TilePlan) == 64, "plan slot size");
@@ -158,7 +158,6 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(sm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* b2s = reinterpret_cast<float*>(sm + Smem::B2);
   float* bhs = reinterpret_cast<float*>(sm + Smem::BH);
   TilePlan* plans = reinterpret_cast<TilePlan*>(sm + Smem::PLAN);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + Smem::TMEM);
@@ -179,8 +178,8 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < NRAW; ++s) { mbar_init(bar(RAW_FULL, s), 1); mbar_init(bar(RAW_EMPTY, s), P1_WARPS); }
-    for (int s = 0; s < NR; ++s) { mbar_init(bar(R_FULL, s), P1_WARPS); mbar_init(bar(R_EMPTY, s), 1); }
+    for (int s = 0; s < NRAW; ++s) { mbar_init(bar(RAW_FULL, s), 1); mbar_init(bar(RAW_EMPTY, s), P1_WARPS / 2); }
+    for (int s = 0; s < NR; ++s) { mbar_init(bar(R_FULL, s), P1_WARPS / 2); mbar_init(bar(R_EMPTY, s), 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(ACC0_FULL, s), 1); mbar_init(bar(ACC0_EMPTY, s), 4);
       mbar_init(bar(A1_FULL, s), 4); mbar_init(bar(A1_EMPTY, s), 1); mbar_init(bar(A2_EMPTY, s), 1);
@@ -198,6 +197,15 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     const int row = tid >> 3, chunk = tid & 7;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.w2_bf16 + row * HC) + chunk);
     *reinterpret_cast<uint4*>(sm + Smem::W2B + sw128_offset(row, chunk)) = v;
+    // second K slab of W2: K 64, 65 carry the folded comb_2 bias (hi + lo bf16), picked up by two columns of ones in the
+    // A tile, so that epilogue 1 is a pure ReLU + convert like epilogue 0
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+    if (chunk == 0) {
+      const float b = __ldg(a.b2 + row);
+      const __nv_bfloat16 hi = __float2bfloat16_rn(b), lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+      x.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+    }
+    *reinterpret_cast<uint4*>(sm + Smem::W2B + 8192u + sw128_offset(row, chunk)) = x;
   } else if (tid < 640) {
     // heads (6 x 64 fp32 -> bf16) into the K-major swizzled tile, rows 6..15 zero
     const int i = tid - 512, row = i >> 3, chunk = i & 7;
@@ -208,10 +216,8 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
       v.z = cvt_bf16x2(__ldg(src + 4), __ldg(src + 5)); v.w = cvt_bf16x2(__ldg(src + 6), __ldg(src + 7));
     }
     *reinterpret_cast<uint4*>(sm + Smem::WHB + sw128_offset(row, chunk)) = v;
-  } else if (tid < 640 + HC) {
-    b2s[tid - 640] = __ldg(a.b2 + tid - 640);
-  } else if (tid < 640 + HC + 6) {
-    bhs[tid - 704] = __ldg(a.bh + tid - 704);
+  } else if (tid < 646) {
+    bhs[tid - 640] = __ldg(a.bh + tid - 640);
   }
   __syncthreads();
   {
@@ -248,8 +254,9 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc0 = tmem_base, acc1 = tmem_base + 128u, acc2 = tmem_base + 256u;   // 2 x 64, 2 x 64, 2 x 16 columns
-  const uint32_t tmem_wa = tmem_base + 320u;                                           // 64 columns: the interpolation matrix
-  const uint32_t tmem_a1 = tmem_base + 384u, tmem_a2 = tmem_base + 448u;               // 2 x 32 columns each: relu(h1), relu(h2) in bf16
+  const uint32_t tmem_wa = tmem_base + 288u;                                           // 64 columns: the interpolation matrix
+  // relu(h1): 2 stages x 40 columns (32 of data + 8 for K 64..79 = {1, 1, 0, ...}: the bias columns); relu(h2): 2 x 32
+  const uint32_t tmem_a1 = tmem_base + 352u, tmem_a2 = tmem_base + 432u;
   if (warp >= 4 && warp < 8) {
     // The interpolation matrix is the A operand of every MMA 0 and never changes: it lives in tensor memory
     // (128 lanes x 64 columns, two fp16 K elements per column), so MMA 0 reads no A bytes from shared memory.
@@ -264,6 +271,11 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
       }
       tc_st16(tmem_wa + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c16 * 16), r);
     }
+    // constant bias columns of both relu(h1) stages: K 64 and 65 = 1.0 (bf16 0x3F80), K 66..79 = 0
+#pragma unroll
+    for (int st = 0; st < 2; ++st)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %2, %2, %2, %2, %2, %2};"
+                   ::"r"(tmem_a1 + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(st * 40 + 32)), "r"(0x3F803F80u), "r"(0u) : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -346,11 +358,12 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
         mbar_wait(bar(A1_FULL, s), ph);
         mbar_wait(bar(ACC1_EMPTY, s), ph ^ 1u);
         tc_fence_after();
-        const uint32_t ta = tmem_a1 + (uint32_t)(s * 32);
+        const uint32_t ta = tmem_a1 + (uint32_t)(s * 40);
         const uint32_t d1 = acc1 + (uint32_t)(s * 64);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) tc_mma_ts_f16(d1, ta + (uint32_t)(8 * kk), desc_w2 + (uint64_t)(2 * kk), idesc1, kk > 0 ? 1u : 0u);
+          tc_mma_ts_f16(d1, ta + 32u, desc_w2 + (uint64_t)(8192 / 16), idesc1, 1u);      // + b2 (bias slab)
           tc_commit(bar(A1_EMPTY, s));
           tc_commit(bar(ACC1_FULL, s));
         }
@@ -372,75 +385,41 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
         __syncwarp();
       }
     }
-  } else if (warp >= 4 && warp < 16) {
+  } else if (warp >= 4 && warp < 12) {
     // ================================================================ epilogues (warp % 4 = TMEM lane quarter)
+    // Two groups of four warps: warps 4-7 run epilogue 0 of row i and epilogue 2 of row i-2, warps 8-11 epilogue 1
+    // (measured: one group for all three is slower, three groups leave phase 1 four warps short).  Epilogues 0 and 1 are
+    // the same code: accumulator -> ReLU -> bf16 -> the tensor-memory A tile of the next GEMM (biases ride in K).
     const int role = (warp - 4) >> 2, q = warp & 3;
     const int vrow = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    if (role == 0) {
-      for (int i = 0; i < my_rows; ++i) {
-        const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-        mbar_wait_sleep(bar(ACC0_FULL, s), ph);
-        mbar_wait_sleep(bar(A1_EMPTY, s), ph ^ 1u);       // MMA 1 of row i-2 has finished reading this A tile
-        tc_fence_after();
-        const uint32_t taddr = acc0 + lane_addr + (uint32_t)(s * 64);
-        const uint32_t aaddr = tmem_a1 + lane_addr + (uint32_t)(s * 32);
-        uint32_t v0[16], v1[16];
-        tc_ld16(taddr, v0);
-        tc_ld16(taddr + 16u, v1);
+    auto relu_to_tmem = [&](uint32_t taddr, uint32_t aaddr) {
+      uint32_t v0[16], v1[16];
+      tc_ld16(taddr, v0);
+      tc_ld16(taddr + 16u, v1);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          tc_wait_ld(); reg_fence16(v0); reg_fence16(v1);
-          uint32_t pk[16];
+      for (int half = 0; half < 2; ++half) {
+        tc_wait_ld(); reg_fence16(v0); reg_fence16(v1);
+        uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            pk[j] = cvt_relu_bf16x2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
-            pk[8 + j] = cvt_relu_bf16x2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
-          }
-          if (half == 0) { tc_ld16(taddr + 32u, v0); tc_ld16(taddr + 48u, v1); }
-          tc_st16(aaddr + (uint32_t)(16 * half), pk);       // 32 channels = 16 packed columns
+        for (int j = 0; j < 8; ++j) {
+          pk[j] = cvt_relu_bf16x2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+          pk[8 + j] = cvt_relu_bf16x2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(bar(ACC0_EMPTY, s)); mbar_arrive(bar(A1_FULL, s)); }
+        if (half == 0) { tc_ld16(taddr + 32u, v0); tc_ld16(taddr + 48u, v1); }
+        tc_st16(aaddr + (uint32_t)(16 * half), pk);       // 32 channels = 16 packed columns
       }
-    } else if (role == 1) {
-      for (int i = 0; i < my_rows; ++i) {
-        const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-        mbar_wait_sleep(bar(ACC1_FULL, s), ph);
-        mbar_wait_sleep(bar(A2_EMPTY, s), ph ^ 1u);       // MMA 2 of row i-2 has finished reading this A tile
-        tc_fence_after();
-        const uint32_t taddr = acc1 + lane_addr + (uint32_t)(s * 64);
-        const uint32_t aaddr = tmem_a2 + lane_addr + (uint32_t)(s * 32);
-        uint32_t v0[16], v1[16];
-        tc_ld16(taddr, v0);
-        tc_ld16(taddr + 16u, v1);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          tc_wait_ld(); reg_fence16(v0); reg_fence16(v1);
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 ba = *reinterpret_cast<const float2*>(b2s + 32 * half + 2 * j);
-            const float2 bb = *reinterpret_cast<const float2*>(b2s + 32 * half + 16 + 2 * j);
-            pk[j] = cvt_relu_bf16x2(__uint_as_float(v0[2 * j]) + ba.x, __uint_as_float(v0[2 * j + 1]) + ba.y);
-            pk[8 + j] = cvt_relu_bf16x2(__uint_as_float(v1[2 * j]) + bb.x, __uint_as_float(v1[2 * j + 1]) + bb.y);
-          }
-          if (half == 0) { tc_ld16(taddr + 32u, v0); tc_ld16(taddr + 48u, v1); }
-          tc_st16(aaddr + (uint32_t)(16 * half), pk);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(bar(ACC1_EMPTY, s)); mbar_arrive(bar(A2_FULL, s)); }
-      }
-    } else {
-      const int64_t plane = (int64_t)a.h * a.w;
-      const int w = w_base + vrow;
-      RowIter it = it0;
-      for (int i = 0; i < my_rows; ++i, it.next()) {
-        const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+    };
+    const int64_t plane = (int64_t)a.h * a.w;
+    const int w = w_base + vrow;
+    RowIter it2 = it0;
+    // epilogue 2 of row i (rows are visited in order; it2 follows)
+    auto epilogue2 = [&](int i) {
+      RowIter& it = it2;
+      const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
         const int n = it.n, t = it.t, h = it.h;
         mbar_wait_sleep(bar(ACC2_FULL, s), ph);
         tc_fence_after();
@@ -476,32 +455,43 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
             put<OutT>(mot + (int64_t)k * a.t * plane, th);
           }
         }
+      it.next();
+    };
+    if (role == 0) {
+      for (int k = 0; k < my_rows + 2; ++k) {
+        if (k < my_rows) {
+          const int s = k & 1; const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+          mbar_wait_sleep(bar(ACC0_FULL, s), ph);
+          mbar_wait_sleep(bar(A1_EMPTY, s), ph ^ 1u);     // MMA 1 of row k-2 has finished reading this A tile
+          tc_fence_after();
+          relu_to_tmem(acc0 + lane_addr + (uint32_t)(s * 64), tmem_a1 + lane_addr + (uint32_t)(s * 40));
+          if (lane == 0) { mbar_arrive(bar(ACC0_EMPTY, s)); mbar_arrive(bar(A1_FULL, s)); }
+        }
+        if (k >= 2) epilogue2(k - 2);                     // the same warps drain the head accumulators two rows behind
+      }
+    } else {
+      for (int j = 0; j < my_rows; ++j) {
+        const int s = j & 1; const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        mbar_wait_sleep(bar(ACC1_FULL, s), ph);
+        mbar_wait_sleep(bar(A2_EMPTY, s), ph ^ 1u);       // MMA 2 of row j-2 has finished reading this A tile
+        tc_fence_after();
+        relu_to_tmem(acc1 + lane_addr + (uint32_t)(s * 64), tmem_a2 + lane_addr + (uint32_t)(s * 32));
+        if (lane == 0) { mbar_arrive(bar(ACC1_EMPTY, s)); mbar_arrive(bar(A2_FULL, s)); }
       }
     }
   } else {
     // ================================================================ phase 1: R = (T,H)-interpolated rows, bf16, MN-major swizzled
-    const int ptid = (warp < 4 ? warp - 2 : warp - 14) * 32 + lane;       // 0 .. P1_THREADS-1
-    // One flat item list over the four levels (item = one low-resolution column x 8 channels), P1_ITEMS per thread.
-    // The item -> (level, column, chunk) mapping is the same for every row, so everything but the loads and the
-    // arithmetic is hoisted out of the row loop: this role's instruction stream paces the pipeline (clock64 timeline).
-    constexpr int P1_ITEMS = 4;
+    const int ptid = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;       // warps 2,3,12..23 -> 0 .. P1_THREADS-1
+    // Two groups of 7 warps take alternate rows: the role is latency-bound (wait -> loads -> FMAs -> stores -> proxy fence
+    // -> arrive is one dependent chain per row, ~3 000 clk in the clock64 timeline, at < 2 of 4 issue slots used), so two
+    // rows' chains in flight beat ten warps on one row.  One flat item list over the four levels (item = one low-resolution
+    // column x 8 channels), P1_ITEMS per thread and pass; all loads of a pass are issued before any arithmetic.  Corners 0/1
+    // are read unconditionally (a corner that was not fetched has weight 0 and its slot holds finite stale data: the
+    // stages are zero-filled at start).
+    constexpr int P1_ITEMS = 4, GT = P1_THREADS / 2;
+    const int grp = ptid / GT, gtid = ptid % GT;
     const int q1 = g.nx[wt][0] * 8, q2 = q1 + g.nx[wt][1] * 8, q3 = q2 + g.nx[wt][2] * 8, n_items = q3 + g.nx[wt][3] * 8;
-    uint32_t i_src[P1_ITEMS], i_cstride[P1_ITEMS], i_dst[P1_ITEMS], i_wgt[P1_ITEMS];
-    bool i_on[P1_ITEMS], i_four[P1_ITEMS];
-#pragma unroll
-    for (int u = 0; u < P1_ITEMS; ++u) {
-      const int q = ptid + u * P1_THREADS;
-      i_on[u] = q < n_items;
-      const int qq = i_on[u] ? q : 0;
-      const int l = (qq >= q1 ? 1 : 0) + (qq >= q2 ? 1 : 0) + (qq >= q3 ? 1 : 0);
-      const int it = qq - (l == 0 ? 0 : l == 1 ? q1 : l == 2 ? q2 : q3);
-      i_src[u] = (uint32_t)g.raw_off[l] + (uint32_t)it * 16u;
-      i_cstride[u] = (uint32_t)g.nxmax[l] * 128u;
-      i_dst[u] = sw128_offset((uint32_t)(g.koff[l] + (it >> 3)), (uint32_t)(it & 7));
-      i_wgt[u] = (uint32_t)l * 16u;
-      i_four[u] = a.tl[l] != a.t;                  // the level has T corners (4 slots); otherwise only its 2 H corners exist
-    }
-    for (int i = 0; i < my_rows; ++i) {
+    for (int i = grp; i < my_rows; i += 2) {
       const int s = i % g.nr; const uint32_t ph = (uint32_t)(i / g.nr) & 1u;
       const int rs = i % g.nraw; const uint32_t rph = (uint32_t)(i / g.nraw) & 1u;
       mbar_wait(bar(RAW_FULL, rs), rph);
@@ -509,39 +499,49 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
       const uint8_t* plw = reinterpret_cast<const uint8_t*>(&plans[rs]);
       const uint8_t* stage = sm + raw_off0 + (uint32_t)rs * (uint32_t)g.raw_stage_bytes;
       uint8_t* rst = sm + r_off + (uint32_t)s * r_stage_bytes;
-      // Corners 0/1 are read unconditionally (a corner that was not fetched has weight 0 and its slot holds finite
-      // stale data: the stages are zero-filled at start); all loads are issued before any arithmetic.
-      uint4 ra[P1_ITEMS], rb[P1_ITEMS];
-      float4 wq[P1_ITEMS];
+      for (int q0 = gtid; q0 < n_items; q0 += P1_ITEMS * GT) {
+        uint4 ra[P1_ITEMS], rb[P1_ITEMS];
+        float4 wq[P1_ITEMS];
+        uint32_t i_src[P1_ITEMS], i_cs[P1_ITEMS], i_dst[P1_ITEMS];
+        bool i_on[P1_ITEMS], i_four[P1_ITEMS];
 #pragma unroll
-      for (int u = 0; u < P1_ITEMS; ++u) {
-        if (!i_on[u]) continue;
-        wq[u] = *reinterpret_cast<const float4*>(plw + i_wgt[u]);
-        ra[u] = *reinterpret_cast<const uint4*>(stage + i_src[u]);
-        rb[u] = *reinterpret_cast<const uint4*>(stage + i_src[u] + i_cstride[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < P1_ITEMS; ++u) {
-        if (!i_on[u]) continue;
-        const uint32_t xa[4] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w}, xb[4] = {rb[u].x, rb[u].y, rb[u].z, rb[u].w};
-        float lo[4], hi[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          lo[e] = wq[u].x * __uint_as_float(xa[e] << 16); hi[e] = wq[u].x * __uint_as_float(xa[e] & 0xffff0000u);
-          lo[e] = fmaf(wq[u].y, __uint_as_float(xb[e] << 16), lo[e]); hi[e] = fmaf(wq[u].y, __uint_as_float(xb[e] & 0xffff0000u), hi[e]);
+        for (int u = 0; u < P1_ITEMS; ++u) {
+          const int q = q0 + u * GT;
+          i_on[u] = q < n_items;
+          const int qq = i_on[u] ? q : 0;
+          const int l = (qq >= q1 ? 1 : 0) + (qq >= q2 ? 1 : 0) + (qq >= q3 ? 1 : 0);
+          const int it = qq - (l == 0 ? 0 : l == 1 ? q1 : l == 2 ? q2 : q3);
+          i_src[u] = (uint32_t)(l == 0 ? g.raw_off[0] : l == 1 ? g.raw_off[1] : l == 2 ? g.raw_off[2] : g.raw_off[3]) + (uint32_t)it * 16u;
+          i_cs[u] = (uint32_t)(l == 0 ? g.nxmax[0] : l == 1 ? g.nxmax[1] : l == 2 ? g.nxmax[2] : g.nxmax[3]) * 128u;
+          i_dst[u] = sw128_offset((uint32_t)((l == 0 ? g.koff[0] : l == 1 ? g.koff[1] : l == 2 ? g.koff[2] : g.koff[3]) + (it >> 3)), (uint32_t)(it & 7));
+          i_four[u] = (l == 0 ? a.tl[0] : l == 1 ? a.tl[1] : l == 2 ? a.tl[2] : a.tl[3]) != a.t;   // the level has T corners
+          wq[u] = *reinterpret_cast<const float4*>(plw + (uint32_t)l * 16u);
+          ra[u] = *reinterpret_cast<const uint4*>(stage + i_src[u]);
+          rb[u] = *reinterpret_cast<const uint4*>(stage + i_src[u] + i_cs[u]);
         }
-        if (i_four[u]) {
-          const uint4 rc = *reinterpret_cast<const uint4*>(stage + i_src[u] + 2u * i_cstride[u]);
-          const uint4 rd = *reinterpret_cast<const uint4*>(stage + i_src[u] + 3u * i_cstride[u]);
-          const uint32_t xc[4] = {rc.x, rc.y, rc.z, rc.w}, xd[4] = {rd.x, rd.y, rd.z, rd.w};
+#pragma unroll
+        for (int u = 0; u < P1_ITEMS; ++u) {
+          if (!i_on[u]) continue;
+          const uint32_t xa[4] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w}, xb[4] = {rb[u].x, rb[u].y, rb[u].z, rb[u].w};
+          float lo[4], hi[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            lo[e] = fmaf(wq[u].z, __uint_as_float(xc[e] << 16), lo[e]); hi[e] = fmaf(wq[u].z, __uint_as_float(xc[e] & 0xffff0000u), hi[e]);
-            lo[e] = fmaf(wq[u].w, __uint_as_float(xd[e] << 16), lo[e]); hi[e] = fmaf(wq[u].w, __uint_as_float(xd[e] & 0xffff0000u), hi[e]);
+            lo[e] = wq[u].x * __uint_as_float(xa[e] << 16); hi[e] = wq[u].x * __uint_as_float(xa[e] & 0xffff0000u);
+            lo[e] = fmaf(wq[u].y, __uint_as_float(xb[e] << 16), lo[e]); hi[e] = fmaf(wq[u].y, __uint_as_float(xb[e] & 0xffff0000u), hi[e]);
           }
+          if (i_four[u]) {
+            const uint4 rc = *reinterpret_cast<const uint4*>(stage + i_src[u] + 2u * i_cs[u]);
+            const uint4 rd = *reinterpret_cast<const uint4*>(stage + i_src[u] + 3u * i_cs[u]);
+            const uint32_t xc[4] = {rc.x, rc.y, rc.z, rc.w}, xd[4] = {rd.x, rd.y, rd.z, rd.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              lo[e] = fmaf(wq[u].z, __uint_as_float(xc[e] << 16), lo[e]); hi[e] = fmaf(wq[u].z, __uint_as_float(xc[e] & 0xffff0000u), hi[e]);
+              lo[e] = fmaf(wq[u].w, __uint_as_float(xd[e] << 16), lo[e]); hi[e] = fmaf(wq[u].w, __uint_as_float(xd[e] & 0xffff0000u), hi[e]);
+            }
+          }
+          *reinterpret_cast<uint4*>(rst + i_dst[u]) =
+              make_uint4(cvt_f16x2_sat(lo[0], hi[0]), cvt_f16x2_sat(lo[1], hi[1]), cvt_f16x2_sat(lo[2], hi[2]), cvt_f16x2_sat(lo[3], hi[3]));
         }
-        *reinterpret_cast<uint4*>(rst + i_dst[u]) =
-            make_uint4(cvt_f16x2_sat(lo[0], hi[0]), cvt_f16x2_sat(lo[1], hi[1]), cvt_f16x2_sat(lo[2], hi[2]), cvt_f16x2_sat(lo[3], hi[3]));
       }
       fence_async_smem();
       __syncwarp();
