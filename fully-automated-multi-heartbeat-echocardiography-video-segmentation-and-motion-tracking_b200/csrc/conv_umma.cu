@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
         mbar_arrive_expect_tx(wres_bar, (uint32_t)(p.ntaps * kslabs * b_slab_bytes));
         for (int tap = 0; tap < p.ntaps; ++tap)
           for (int ks = 0; ks < kslabs; ++ks)
-            tma_load_3d(b_base + (uint32_t)((tap * kslabs + ks) * b_slab_bytes), &p.tmap_b, wres_bar, ks * SLAB_K, 0, p.tap_widx[tap]);
+            tma_load_3d(b_base + (uint32_t)((tap * kslabs + ks) * b_slab_bytes), &p.tmap_b, wres_bar, ks * SLAB_K,
+                        (int)(blockIdx.x % (unsigned)tiles_n) * bn, p.tap_widx[tap]);
       }
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -504,6 +505,18 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
     mode = SHARE_NONE;
   }
   CLASFV_REQUIRE(p.nstages >= 2, "conv_umma: tile does not fit shared memory");
+  // Few-tap layers whose whole filter bank does not fit shared memory but half of it does (layer2's 3x1x1 convolutions,
+  // 128 output channels): split N in two tiles and keep each half RESIDENT in the CTAs that own that N tile (the grid is a
+  // multiple of the N tiling, so a persistent CTA only ever sees one N tile).  The weights are then read once per CTA instead
+  // of once per 128-row tile (192 KB per tile against 72 KB of activations); the A slabs are read twice.
+  static const bool no_split = getenv("CLASFV_UMMA_NO_NSPLIT") != nullptr;
+  if (!p.resident && p.tiles_n == 1 && ntaps <= 3 && s.cout % 32 == 0 && !no_split) {
+    const int bn2 = s.cout / 2, b_slab2 = bn2 * SLAB_K * 2, res2 = ntaps * p.kslabs * b_slab2;
+    if (res2 + 4 * p.a_slab_bytes + bar_bytes + 1024 <= SMEM_BUDGET) {
+      bn = bn2; p.bn = bn2; p.tiles_n = 2; p.b_slab_bytes = b_slab2; p.resident = 1;
+      p.nstages = std::min(8, (SMEM_BUDGET - 1024 - bar_bytes - res2) / p.a_slab_bytes);
+    }
+  }
   CLASFV_REQUIRE(!a.seg.on || mode == SHARE_T, "conv_umma: a time-segmented input needs a 3x1x1 stride-1 pad-1 convolution whose frame is whole swizzle atoms");
   CLASFV_REQUIRE(!a.seg.on || (a.seg.b && a.seg.a_t >= 1 && a.seg.b_t >= 1 && a.seg.to == s.to), "conv_umma: bad time-segment description");
   p.tiles_w = (int)cdiv(s.wo, p.bw); p.tiles_h = (int)cdiv(s.ho, p.bh); p.tiles_t = (int)cdiv(s.to, p.bt); p.tiles_b = (int)cdiv(s.n, p.bb);
@@ -611,7 +624,8 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   CLASFV_REQUIRE(smem <= 227 * 1024, "conv_umma: shared memory overflow (%zu bytes)", smem);
   CLASFV_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_b * p.tiles_n;
-  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  if (p.resident && p.tiles_n > 1) grid = std::max(grid / p.tiles_n, 1) * p.tiles_n;     // a CTA keeps one N tile: tile % tiles_n == blockIdx.x % tiles_n
   conv_umma_kernel<<<grid, UMMA_THREADS, smem, stream>>>(p);
   CLASFV_CUDA(cudaGetLastError());
   return CLASFV_OK;
