@@ -8,10 +8,25 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <utility>
 
 namespace clasfv {
 
 static thread_local char g_error[1024] = "";
+
+cudaError_t allow_max_dynamic_smem_impl(const void* kernel) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& kd : done) if (kd.first == kernel && kd.second == dev) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) done.emplace_back(kernel, dev);
+  return e;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -622,7 +622,7 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)p.nstages * p.a_slab_bytes +
                       (p.resident ? (size_t)ntaps * p.kslabs * p.b_slab_bytes : (size_t)p.nstages * p.b_stage_slabs * p.b_slab_bytes) + bar_bytes;
   CLASFV_REQUIRE(smem <= 227 * 1024, "conv_umma: shared memory overflow (%zu bytes)", smem);
-  CLASFV_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+  CLASFV_CUDA(allow_max_dynamic_smem(conv_umma_kernel));
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_b * p.tiles_n;
   int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (p.resident && p.tiles_n > 1) grid = std::max(grid / p.tiles_n, 1) * p.tiles_n;     // a CTA keeps one N tile: tile % tiles_n == blockIdx.x % tiles_n

@@ -149,10 +149,10 @@ int launch_head(const HeadArgs& a, cudaStream_t stream) {
   CLASFV_REQUIRE(smem <= 200 * 1024, "head: frame too wide for the row buffers (W=%d)", a.w);
   dim3 grid((unsigned)a.h, (unsigned)a.t, (unsigned)a.n);
   if (a.out_dtype == CLASFV_F32) {
-    CLASFV_CUDA(cudaFuncSetAttribute(head_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CLASFV_CUDA(allow_max_dynamic_smem(head_kernel<float>));
     head_kernel<float><<<grid, HEAD_THREADS, smem, stream>>>(a, rowbuf);
   } else {
-    CLASFV_CUDA(cudaFuncSetAttribute(head_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CLASFV_CUDA(allow_max_dynamic_smem(head_kernel<__nv_bfloat16>));
     head_kernel<__nv_bfloat16><<<grid, HEAD_THREADS, smem, stream>>>(a, rowbuf);
   }
   CLASFV_CUDA(cudaGetLastError());

@@ -636,10 +636,10 @@ int launch_head_umma(const HeadArgs& a, cudaStream_t stream) {
   int grid = (int)std::min<int64_t>(total * g.w_tiles, (int64_t)(sms / g.w_tiles) * g.w_tiles);
   grid = std::max(grid / g.w_tiles, 1) * g.w_tiles;
   if (a.out_dtype == CLASFV_F32) {
-    CLASFV_CUDA(cudaFuncSetAttribute(head_umma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CLASFV_CUDA(allow_max_dynamic_smem(head_umma_kernel<float>));
     head_umma_kernel<float><<<grid, HU_THREADS, smem, stream>>>(a, g);
   } else {
-    CLASFV_CUDA(cudaFuncSetAttribute(head_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CLASFV_CUDA(allow_max_dynamic_smem(head_umma_kernel<__nv_bfloat16>));
     head_umma_kernel<__nv_bfloat16><<<grid, HU_THREADS, smem, stream>>>(a, g);
   }
   CLASFV_CUDA(cudaGetLastError());

@@ -512,10 +512,10 @@ int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
       const size_t smem = (size_t)units * unit + 16 * (size_t)units;
       dim3 grid((unsigned)slices, (unsigned)a.t_out);
       if (a.dtype == CLASFV_F32) {
-        CLASFV_CUDA(cudaFuncSetAttribute(warp_fuse_staged_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CLASFV_CUDA(allow_max_dynamic_smem(warp_fuse_staged_kernel<float>));
         warp_fuse_staged_kernel<float><<<grid, WsShape<float>::THREADS, smem, s>>>(a, units, slice_pix);
       } else {
-        CLASFV_CUDA(cudaFuncSetAttribute(warp_fuse_staged_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CLASFV_CUDA(allow_max_dynamic_smem(warp_fuse_staged_kernel<__nv_bfloat16>));
         warp_fuse_staged_kernel<__nv_bfloat16><<<grid, WsShape<__nv_bfloat16>::THREADS, smem, s>>>(a, units, slice_pix);
       }
       CLASFV_CUDA(cudaGetLastError());

@@ -29,6 +29,12 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Opt a kernel in to the full 227 KB of dynamic shared memory once per device (the attribute is a maximum, so one value
+// serves every launch); a driver call per launch is ~170 calls per video step otherwise.
+cudaError_t allow_max_dynamic_smem_impl(const void* kernel);     // api.cu: once per (kernel, device)
+template <typename Kernel>
+inline cudaError_t allow_max_dynamic_smem(Kernel kernel) { return allow_max_dynamic_smem_impl(reinterpret_cast<const void*>(kernel)); }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------
