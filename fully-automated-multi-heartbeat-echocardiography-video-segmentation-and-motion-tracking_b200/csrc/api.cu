@@ -763,7 +763,13 @@ int clasfv_profile_gflop(clasfv_handle* h, double* stage_gflop_host) {
 
 int clasfv_warp(const float* src_dev, const float* flow_dev, float* out_dev, int n, int c, int height, int width, void* stream) {
   CLASFV_REQUIRE(src_dev && flow_dev && out_dev && n >= 1 && c >= 1 && height >= 1 && width >= 1, "clasfv_warp: bad argument");
-  return launch_warp(src_dev, flow_dev, out_dev, n, c, height, width, static_cast<cudaStream_t>(stream));
+  return launch_warp(src_dev, flow_dev, out_dev, n, c, height, width, 0, static_cast<cudaStream_t>(stream));
+}
+
+int clasfv_warp_mode(const float* src_dev, const float* flow_dev, float* out_dev, int n, int c, int height, int width, int mode, void* stream) {
+  CLASFV_REQUIRE(src_dev && flow_dev && out_dev && n >= 1 && c >= 1 && height >= 1 && width >= 1, "clasfv_warp_mode: bad argument");
+  CLASFV_REQUIRE(mode == CLASFV_WARP_BILINEAR || mode == CLASFV_WARP_NEAREST, "clasfv_warp_mode: mode must be CLASFV_WARP_BILINEAR or CLASFV_WARP_NEAREST");
+  return launch_warp(src_dev, flow_dev, out_dev, n, c, height, width, mode == CLASFV_WARP_NEAREST ? 1 : 0, static_cast<cudaStream_t>(stream));
 }
 
 int clasfv_motion_field(const float* flow_dev, float* grid_dev, int n, int height, int width, void* stream) {

@@ -85,13 +85,23 @@ __device__ __forceinline__ float bilinear_fetch(const T* __restrict__ plane, con
 }
 
 __global__ void warp_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ out,
-                            int c, int h, int w) {
+                            int c, int h, int w, int nearest) {
   const int n = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= h * w) return;
   const int i = pix / w, j = pix % w;
   const int64_t hw = (int64_t)h * w;
   const float fx = __ldg(flow + (int64_t)n * 2 * hw + pix), fy = __ldg(flow + ((int64_t)n * 2 + 1) * hw + pix);
+  if (nearest) {
+    // grid_sample(mode="nearest", padding_mode="border", align_corners=False): clamp, then round half to even (nearbyint)
+    const float gx = linspace_pm1(j, w) + fx, gy = linspace_pm1(i, h) + fy;
+    float ix = ((gx + 1.f) * (float)w - 1.f) * 0.5f, iy = ((gy + 1.f) * (float)h - 1.f) * 0.5f;
+    ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
+    iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
+    const int xs = (int)rintf(ix), ys = (int)rintf(iy);
+    for (int k = 0; k < c; ++k) out[((int64_t)n * c + k) * hw + pix] = __ldg(src + ((int64_t)n * c + k) * hw + (int64_t)ys * w + xs);
+    return;
+  }
   const Bilinear b = bilinear_setup(i, j, fx, fy, h, w);
   for (int k = 0; k < c; ++k) out[((int64_t)n * c + k) * hw + pix] = bilinear_fetch<float>(src + ((int64_t)n * c + k) * hw, b, w);
 }
@@ -476,9 +486,9 @@ __global__ void temporal_resample_kernel(const float* __restrict__ in, float* __
 
 }  // namespace
 
-int launch_warp(const float* src, const float* flow, float* out, int n, int c, int h, int w, cudaStream_t s) {
+int launch_warp(const float* src, const float* flow, float* out, int n, int c, int h, int w, int nearest, cudaStream_t s) {
   dim3 grid((unsigned)cdiv((int64_t)h * w, 256), (unsigned)n);
-  warp_kernel<<<grid, 256, 0, s>>>(src, flow, out, c, h, w);
+  warp_kernel<<<grid, 256, 0, s>>>(src, flow, out, c, h, w, nearest);
   CLASFV_CUDA(cudaGetLastError());
   return CLASFV_OK;
 }

@@ -230,17 +230,19 @@ class Engine:
         return out
 
 
-def warp(src, flow):
-    """W1 + its grid_sample call site on fp32 CUDA tensors: src (N,C,H,W), flow (N,2,H,W)."""
+def warp(src, flow, mode="bilinear"):
+    """W1 + its grid_sample call site on fp32 CUDA tensors: src (N,C,H,W), flow (N,2,H,W); mode "bilinear" | "nearest"."""
     _lib.require_cuda(src, "src"); _lib.require_cuda(flow, "flow")
     if src.dtype != torch.float32 or flow.dtype != torch.float32:
         raise ClasfvError("warp: float32 tensors only")
     n, c, h, w = src.shape
     if tuple(flow.shape) != (n, 2, h, w):
         raise ClasfvError("warp: flow must be (N,2,H,W)")
+    if mode not in ("bilinear", "nearest"):
+        raise ClasfvError(f"warp: mode must be 'bilinear' or 'nearest', got {mode!r}")
     out = torch.empty_like(src)
-    check(_lib.lib().clasfv_warp(src.data_ptr(), flow.data_ptr(), out.data_ptr(), n, c, h, w,
-                                 _lib.current_stream_ptr(src.device)), "clasfv_warp")
+    check(_lib.lib().clasfv_warp_mode(src.data_ptr(), flow.data_ptr(), out.data_ptr(), n, c, h, w, 1 if mode == "nearest" else 0,
+                                      _lib.current_stream_ptr(src.device)), "clasfv_warp_mode")
     return out
 
 

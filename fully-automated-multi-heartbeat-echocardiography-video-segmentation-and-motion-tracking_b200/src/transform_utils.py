@@ -11,7 +11,7 @@ def generate_2dmotion_field(x, offset):
     return _engine.motion_field(offset.contiguous().float(), int(x.shape[2]), int(x.shape[3]))
 
 
-def warp(x, offset):
-    """``F.grid_sample(x, generate_2dmotion_field(x, offset), align_corners=False, mode='bilinear',
-    padding_mode='border')`` (clasfv_losses.py:86-87) in one kernel."""
-    return _engine.warp(x.contiguous().float(), offset.contiguous().float())
+def warp(x, offset, mode="bilinear"):
+    """``F.grid_sample(x, generate_2dmotion_field(x, offset), align_corners=False, mode=mode,
+    padding_mode='border')`` (clasfv_losses.py:86-87, visualization_utils.py:123-126) in one kernel."""
+    return _engine.warp(x.contiguous().float(), offset.contiguous().float(), mode)

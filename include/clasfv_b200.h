@@ -115,6 +115,13 @@ int64_t clasfv_workspace_bytes(const clasfv_handle* h);
  *   out(i,j) = bilinear src( clamp(i*H/(H-1) - 1/2 + flow_y*H/2), clamp(j*W/(W-1) - 1/2 + flow_x*W/2) ) */
 int clasfv_warp(const float* src_dev, const float* flow_dev, float* out_dev, int n, int c, int height, int width,
                 void* stream);
+/* The same with the interpolation mode of the call site selectable: the reference's label / image propagation
+ * (apply_sequence_deformation, src/visualization_utils.py:106-128) calls grid_sample with mode="nearest" for labels
+ * (clamp to the border, then round half to even) and "bilinear" for images. */
+#define CLASFV_WARP_BILINEAR 0
+#define CLASFV_WARP_NEAREST  1
+int clasfv_warp_mode(const float* src_dev, const float* flow_dev, float* out_dev, int n, int c, int height, int width,
+                     int mode, void* stream);
 /* The sampling grid itself, (N,H,W,2) fp32 = what generate_2dmotion_field returns. */
 int clasfv_motion_field(const float* flow_dev, float* grid_dev, int n, int height, int width, void* stream);
 

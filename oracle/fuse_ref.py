@@ -175,6 +175,19 @@ def warp(src, flow):
 
 
 # --------------------------------------------------------------------------- F2
+def apply_sequence_deformation(flow_source_image, motion_output, start_index, end_index, grid_mode="bilinear", forward=True):
+    """Reference ``src/visualization_utils.py:106-128`` restated on the pinned primitives (``generate_2dmotion_field`` +
+    ``F.grid_sample(align_corners=False, mode=grid_mode, padding_mode='border')``): chained warps of one frame's image /
+    label along the forward (channels 0:2) or backward (2:4) motion of frames range(start_index, end_index, +-1)."""
+    step = 1 if forward else -1
+    for frame_index in range(start_index, end_index, step):
+        field = motion_output[:, :2, frame_index] if forward else motion_output[:, 2:, frame_index]
+        grid = generate_2dmotion_field(flow_source_image, field)
+        new_image = F.grid_sample(flow_source_image, grid, align_corners=False, mode=grid_mode, padding_mode="border")
+        flow_source_image = new_image
+    return new_image
+
+
 def warp_fuse(prob, motion, clip_starts, num_frames, edge_hops=False, accumulate=torch.float64):
     """North-star warp-and-fuse operator (not in the reference; composition of S1 + W1).
 

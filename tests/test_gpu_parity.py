@@ -90,6 +90,33 @@ def test_warp_primitive_matches_oracle_and_golden(golden_dir):
 
 
 # ------------------------------------------------------------------------------------------ C1
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+@pytest.mark.parametrize("forward", [True, False])
+def test_apply_sequence_deformation_matches_oracle(mode, forward):
+    """Motion-tracking product (reference src/visualization_utils.py:106-128): a label / image carried through a run of
+    motion fields by chained warps.  Bilinear: <= 1e-5 after 6 chained warps; nearest: the same pixels picked (exact)."""
+    from clasfv_b200.src.visualization_utils import apply_sequence_deformation
+    g = torch.Generator().manual_seed(11)
+    n, t, h, w = 2, 10, 40, 56
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    label = (((yy - 20) / 12) ** 2 + ((xx - 28) / 9) ** 2 <= 1).float().expand(n, 1, h, w).contiguous()
+    image = torch.rand(n, 1, h, w, generator=g)
+    src = label if mode == "nearest" else image
+    # smooth flows of a few pixels (white noise would make every nearest pick a coin flip between fp32 rounding orders)
+    motion = torch.tanh(F.interpolate(torch.randn(n, 4, t, 5, 7, generator=g), size=(t, h, w), mode="trilinear", align_corners=True) * 0.08)
+    a, b = (1, 7) if forward else (8, 2)
+    ref = fuse_ref.apply_sequence_deformation(src, motion, a, b, grid_mode=mode, forward=forward)
+    out = apply_sequence_deformation(src.cuda(), motion.cuda(), a, b, grid_mode=mode, forward=forward).cpu()
+    assert out.shape == ref.shape
+    if mode == "bilinear":
+        assert float((out - ref).abs().max()) <= 1e-5
+    else:
+        assert float((out != ref).float().mean()) <= 1e-3          # ties at exactly .5 may round differently after fp32 reassociation
+        assert set(out.unique().tolist()) <= {0.0, 1.0}
+    with pytest.raises(UnboundLocalError):
+        apply_sequence_deformation(src.cuda(), motion.cuda(), 3, 3, grid_mode=mode, forward=forward)
+
+
 @pytest.mark.parametrize("length", [75, 48, 64, 80])
 def test_divide_to_consecutive_clips_matches_golden(golden_dir, length):
     g = np.load(os.path.join(golden_dir, "divide_clips.npz"))

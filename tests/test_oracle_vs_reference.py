@@ -50,3 +50,22 @@ def test_warp_matches_reference_function(ref):
     with ref_import.cuda_is_noop():
         grid = ref.transform_utils.generate_2dmotion_field(src, flow)
     assert torch.equal(grid, fuse_ref.generate_2dmotion_field(src, flow))
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+@pytest.mark.parametrize("forward", [True, False])
+def test_apply_sequence_deformation_matches_reference_function(ref, mode, forward):
+    """The motion-tracking product (src/visualization_utils.py:106-128), unmodified reference function with ``.cuda()``
+    patched to a no-op, against the oracle's restatement: bit-identical."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from src import visualization_utils as ref_vis
+    g = torch.Generator().manual_seed(4)
+    src = torch.rand(2, 1, 24, 32, generator=g)
+    motion = torch.tanh(0.1 * torch.randn(2, 4, 10, 24, 32, generator=g))
+    a, b = (1, 6) if forward else (8, 3)
+    with ref_import.cuda_is_noop():
+        want = ref_vis.apply_sequence_deformation(src, motion, a, b, grid_mode=mode, forward=forward)
+    got = fuse_ref.apply_sequence_deformation(src, motion, a, b, grid_mode=mode, forward=forward)
+    assert torch.equal(want, got)
