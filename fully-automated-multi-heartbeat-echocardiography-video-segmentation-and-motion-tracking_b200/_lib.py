@@ -23,7 +23,7 @@ EXPORTS = (
     "clasfv_finalize", "clasfv_forward", "clasfv_workspace_bytes", "clasfv_warp", "clasfv_motion_field",
     "clasfv_warp_fuse", "clasfv_build_shift_clips", "clasfv_fuse_shift_votes", "clasfv_temporal_resample",
     "clasfv_conv3d", "clasfv_profile_begin", "clasfv_profile_end", "clasfv_finalize_mask",
-    "clasfv_set_option", "clasfv_profile_gflop", "clasfv_warp_mode",
+    "clasfv_set_option", "clasfv_profile_gflop", "clasfv_warp_mode", "clasfv_ingest_u8",
 )
 
 
@@ -69,6 +69,7 @@ def lib():
         l.clasfv_workspace_bytes.argtypes = [vp]
         l.clasfv_workspace_bytes.restype = i64
         l.clasfv_warp.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+        l.clasfv_ingest_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]
         l.clasfv_warp_mode.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
         l.clasfv_motion_field.argtypes = [vp, vp, i32, i32, i32, vp]
         l.clasfv_warp_fuse.argtypes = [vp, vp, vp, i32, C.POINTER(C.c_int32), i32, i32, i32, i32, i32, i32, i32,

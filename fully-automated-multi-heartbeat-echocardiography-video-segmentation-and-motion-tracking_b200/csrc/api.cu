@@ -106,6 +106,7 @@ struct clasfv_handle {
   __nv_bfloat16* w2_bf16 = nullptr;
   // workspace
   void* ws = nullptr; size_t ws_bytes = 0;
+  uint32_t* minmax = nullptr;          // per-channel {min, max} bit patterns of clasfv_ingest_u8
   TableRing ring;
   // optional stage profiler: an event after every stage of every (sub-)batch; the time since the previous event
   // of the same call is attributed to that stage.  prof_gflop counts the MACs the convolutions really performed.
@@ -568,6 +569,7 @@ void clasfv_destroy(clasfv_handle* h) {
   cudaDeviceSynchronize();
   free_packed(h);
   if (h->ws) cudaFree(h->ws);
+  if (h->minmax) cudaFree(h->minmax);
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
   h->ring.destroy();
   delete h;
@@ -759,6 +761,15 @@ int clasfv_profile_gflop(clasfv_handle* h, double* stage_gflop_host) {
   CLASFV_REQUIRE(h && stage_gflop_host, "clasfv_profile_gflop: null argument");
   for (int s = 0; s < 4; ++s) stage_gflop_host[s] = h->prof_gflop[s];
   return CLASFV_OK;
+}
+
+int clasfv_ingest_u8(clasfv_handle* h, const uint8_t* frames_dev, int t, int height0, int width0, int bgr,
+                     float* video_dev, int height, int width, void* stream_v) {
+  CLASFV_REQUIRE(h && frames_dev && video_dev, "clasfv_ingest_u8: null argument");
+  CLASFV_REQUIRE(t >= 1 && height0 >= 1 && width0 >= 1 && height >= 1 && width >= 1, "clasfv_ingest_u8: bad extent");
+  DeviceGuard guard(h->device);
+  if (!h->minmax) CLASFV_CUDA(cudaMalloc(&h->minmax, 6 * sizeof(uint32_t)));
+  return launch_ingest_u8(frames_dev, t, height0, width0, bgr ? 1 : 0, video_dev, height, width, h->minmax, static_cast<cudaStream_t>(stream_v));
 }
 
 int clasfv_warp(const float* src_dev, const float* flow_dev, float* out_dev, int n, int c, int height, int width, void* stream) {

@@ -118,6 +118,64 @@ __global__ void motion_field_kernel(const float* __restrict__ flow, float* __res
   reinterpret_cast<float2*>(grid)[(int64_t)n * hw + pix] = g;
 }
 
+// ------------------------------------------------------------------------------------------- ingest
+// motion_segment.py:80-106 after the cv2 decode: uint8 frames (T,H0,W0,3) -> float, F.interpolate(size=(T,h,w),
+// mode="trilinear", align_corners=True) (the frame count is unchanged, so this is a per-frame bilinear resize) ->
+// zeroone_normalizer (echonet_dataset.py:38-50): per channel x -= min; x /= max-after-the-shift.
+// Pass 1 resizes, writes the planar (3,T,h,w) fp32 video and reduces min / max per channel; pass 2 normalises in place.
+// Values are >= 0, so the unsigned bit pattern of a float orders like the float: atomicMin / atomicMax on uint32.
+struct LerpAC { int i0, i1; float l0, l1; };
+__device__ __forceinline__ LerpAC lerp_align_corners(int dst, int in_size, int out_size) {
+  LerpAC r;
+  const float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  const float src = scale * (float)dst;
+  r.i0 = min((int)src, in_size - 1);
+  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+__global__ void __launch_bounds__(256) ingest_resize_kernel(const uint8_t* __restrict__ frames, int t, int h0, int w0, int bgr,
+                                                            float* __restrict__ out, int h, int w, uint32_t* __restrict__ minmax) {
+  const int ti = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  const bool valid = pix < h * w;
+  float v[3] = {0.f, 0.f, 0.f};
+  if (valid) {
+    const int i = pix / w, j = pix % w;
+    const LerpAC ly = lerp_align_corners(i, h0, h), lx = lerp_align_corners(j, w0, w);
+    const uint8_t* f = frames + (int64_t)ti * h0 * w0 * 3;
+    const uint8_t* p00 = f + ((int64_t)ly.i0 * w0 + lx.i0) * 3; const uint8_t* p01 = f + ((int64_t)ly.i0 * w0 + lx.i1) * 3;
+    const uint8_t* p10 = f + ((int64_t)ly.i1 * w0 + lx.i0) * 3; const uint8_t* p11 = f + ((int64_t)ly.i1 * w0 + lx.i1) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int cs = bgr ? 2 - c : c;         // output channel c reads byte cs of the pixel
+      // the nesting and rounding of ATen's linear upsampling: h0*(w0*a + w1*b) + h1*(w0*c + w1*d), no fused multiply-add
+      const float top = __fadd_rn(__fmul_rn(lx.l0, (float)p00[cs]), __fmul_rn(lx.l1, (float)p01[cs]));
+      const float bot = __fadd_rn(__fmul_rn(lx.l0, (float)p10[cs]), __fmul_rn(lx.l1, (float)p11[cs]));
+      v[c] = __fadd_rn(__fmul_rn(ly.l0, top), __fmul_rn(ly.l1, bot));
+      out[((int64_t)c * t + ti) * h * w + pix] = v[c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float lo = valid ? v[c] : 3.0e38f, hi = valid ? v[c] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(minmax + 2 * c, __float_as_uint(lo)); atomicMax(minmax + 2 * c + 1, __float_as_uint(hi)); }
+  }
+}
+
+__global__ void __launch_bounds__(256) ingest_normalize_kernel(float* __restrict__ out, int64_t per_channel, const uint32_t* __restrict__ minmax) {
+  const int c = blockIdx.y;
+  const float lo = __uint_as_float(minmax[2 * c]);
+  const float range = __fsub_rn(__uint_as_float(minmax[2 * c + 1]), lo);       // the max after the shift
+  float* o = out + (int64_t)c * per_channel;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < per_channel; i += (int64_t)gridDim.x * 256)
+    o[i] = __fdiv_rn(__fsub_rn(o[i], lo), range);
+}
+
 // ------------------------------------------------------------------------------------------- F2
 constexpr int WF_THREADS = 256;
 
@@ -485,6 +543,17 @@ __global__ void temporal_resample_kernel(const float* __restrict__ in, float* __
 }
 
 }  // namespace
+
+int launch_ingest_u8(const uint8_t* frames, int t, int h0, int w0, int bgr, float* out, int h, int w, uint32_t* minmax_dev, cudaStream_t s) {
+  static const uint32_t init[6] = {0x7f7fffffu, 0u, 0x7f7fffffu, 0u, 0x7f7fffffu, 0u};      // {+FLT_MAX, 0} per channel
+  CLASFV_CUDA(cudaMemcpyAsync(minmax_dev, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  ingest_resize_kernel<<<dim3((unsigned)cdiv((int64_t)h * w, 256), (unsigned)t), 256, 0, s>>>(frames, t, h0, w0, bgr, out, h, w, minmax_dev);
+  CLASFV_CUDA(cudaGetLastError());
+  const int64_t per_channel = (int64_t)t * h * w;
+  ingest_normalize_kernel<<<dim3((unsigned)std::min<int64_t>(cdiv(per_channel, 256), 1184), 3u), 256, 0, s>>>(out, per_channel, minmax_dev);
+  CLASFV_CUDA(cudaGetLastError());
+  return CLASFV_OK;
+}
 
 int launch_warp(const float* src, const float* flow, float* out, int n, int c, int h, int w, int nearest, cudaStream_t s) {
   dim3 grid((unsigned)cdiv((int64_t)h * w, 256), (unsigned)n);

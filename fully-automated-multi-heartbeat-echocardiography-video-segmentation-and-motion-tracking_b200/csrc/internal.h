@@ -125,6 +125,7 @@ int launch_head_umma(const HeadArgs& a, cudaStream_t stream);   // tcgen05 head 
 int launch_temporal_upsample_bf16(const void* in, void* out, int n, int tl, int t, int hl, int wl, cudaStream_t stream);
 
 // fusion.cu
+int launch_ingest_u8(const uint8_t* frames, int t, int h0, int w0, int bgr, float* out, int h, int w, uint32_t* minmax_dev, cudaStream_t s);
 int launch_warp(const float* src, const float* flow, float* out, int n, int c, int h, int w, int nearest, cudaStream_t s);
 int launch_motion_field(const float* flow, float* grid, int n, int h, int w, cudaStream_t s);
 struct WarpFuseArgs {

@@ -129,6 +129,21 @@ class Engine:
             self.forward_into(video, seg[i:j], mot[i:j], out_kind, clip_starts=starts[i:j], clip_len=clip_len)
             i = j
 
+    def ingest_u8(self, frames, height, width, bgr=False):
+        """frames (T,H0,W0,3) uint8 (host or CUDA) -> (3,T,height,width) fp32 CUDA video: the reference's pre-resize
+        (trilinear, align_corners=True) + zero-one normalisation (motion_segment.py:96-106) on the device."""
+        f = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames))
+        if f.dtype != torch.uint8 or f.dim() != 4 or f.shape[3] != 3:
+            raise ClasfvError(f"ingest_u8: expected uint8 frames of shape (T,H,W,3), got {f.dtype} {tuple(f.shape)}")
+        if not f.is_cuda:
+            f = f.pin_memory().to(self.device, non_blocking=True)
+        f = f.contiguous()
+        t, h0, w0, _ = f.shape
+        out = torch.empty((3, t, int(height), int(width)), dtype=torch.float32, device=f.device)
+        check(self.lib.clasfv_ingest_u8(self._h, f.data_ptr(), t, h0, w0, 1 if bgr else 0, out.data_ptr(), int(height), int(width),
+                                        _lib.current_stream_ptr(f.device)), "clasfv_ingest_u8")
+        return out
+
     def set_option(self, name, value):
         """``sub_batch`` (clips per internal batch of a forward call, default 16) or ``dense_video`` (0/1: share
         the stem and layer1 between overlapping windows of one resident video, default on)."""

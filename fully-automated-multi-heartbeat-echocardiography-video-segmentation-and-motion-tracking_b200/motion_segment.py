@@ -44,6 +44,23 @@ def build_parser():
     return ap
 
 
+def load_frames(path):
+    """cv2 decode -> (T, H, W, 3) uint8 frames in cv2's B,G,R byte order (motion_segment.py:80-92 without the per-frame
+    cvtColor: the channel swap happens in the device ingest)."""
+    import cv2
+    capture = cv2.VideoCapture(path)
+    frame_count = int(capture.get(cv2.CAP_PROP_FRAME_COUNT))
+    frame_width = int(capture.get(cv2.CAP_PROP_FRAME_WIDTH))
+    frame_height = int(capture.get(cv2.CAP_PROP_FRAME_HEIGHT))
+    video = np.zeros((frame_count, frame_height, frame_width, 3), np.uint8)
+    for count in range(frame_count):
+        ret, frame = capture.read()
+        if not ret:
+            raise ValueError("Failed to load frame #{} of {}.".format(count, path))
+        video[count, :, :] = frame
+    return video
+
+
 def load_video(path):
     """cv2 decode -> (3, T, H, W) float32 RGB, as motion_segment.py:80-96."""
     import cv2
@@ -79,7 +96,10 @@ def main(argv=None):
         print(f'R2+1D MotionNet has {sum(p.numel() for p in model.parameters() if p.requires_grad)} parameters.')
     model.eval()
 
-    video = preprocess(load_video(args.path), args.height, args.width)
+    # decode on the host, everything after it on the device: channel swap, trilinear pre-resize (align_corners=True)
+    # and zero-one normalisation are one ingest call (clasfv_ingest_u8); the (3,T,h,w) video never exists on the host
+    eng = (model.module if isinstance(model, torch.nn.DataParallel) else model).engine()
+    video = eng.ingest_u8(load_frames(args.path), args.height, args.width, bgr=True)
     class_list = [0, 1]
     segmentations = segment_a_video_with_fusion(video, model=model, interpolate_last=True, step=args.step,
                                                 num_clips=args.fuse, fuse_method=args.fuse_method, class_list=class_list)
@@ -101,7 +121,7 @@ def main(argv=None):
     if "gif" in content or "all" in content:
         try:
             from clasfv_b200.src.visualization_utils import make_annotated_gif
-            make_annotated_gif(segmentations, video, filename=os.path.join(args.output, filename + "_annotated.gif"))
+            make_annotated_gif(segmentations, video.cpu().numpy(), filename=os.path.join(args.output, filename + "_annotated.gif"))
         except ImportError as e:      # matplotlib is optional presentation tooling
             print("skipping the annotated gif:", e)
     if "binary" in content or "all" in content:

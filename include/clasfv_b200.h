@@ -107,6 +107,14 @@ int clasfv_profile_gflop(clasfv_handle* h, double* stage_gflop_host /* [4] */);
 /* Largest workspace (bytes) the handle currently holds; informational. */
 int64_t clasfv_workspace_bytes(const clasfv_handle* h);
 
+/* ---- video ingest -----------------------------------------------------------------------------
+ * Replaces the float pipeline of motion_segment.py:96-106 after the cv2 decode: frames_dev (T,H0,W0,3) uint8 (bgr != 0:
+ * bytes are B,G,R as cv2 delivers them, else R,G,B) -> video_dev (3,T,height,width) fp32 =
+ * zeroone_normalizer(F.interpolate(float(video), size=(T,height,width), mode="trilinear", align_corners=True))
+ * (src/echonet_dataset.py:38-50: per channel x -= min; x /= max after the shift). */
+int clasfv_ingest_u8(clasfv_handle* h, const uint8_t* frames_dev, int t, int height0, int width0, int bgr,
+                     float* video_dev, int height, int width, void* stream);
+
 /* ---- warp primitive ---------------------------------------------------------------------------
  * Replaces generate_2dmotion_field (src/transform_utils.py:14-34) + its call site
  * F.grid_sample(src, grid, align_corners=False, mode="bilinear", padding_mode="border")

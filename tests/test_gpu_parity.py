@@ -90,6 +90,28 @@ def test_warp_primitive_matches_oracle_and_golden(golden_dir):
 
 
 # ------------------------------------------------------------------------------------------ C1
+@pytest.mark.parametrize("shape,size,bgr", [((12, 60, 80), (112, 112), False), ((9, 150, 130), (112, 112), True),
+                                            ((5, 112, 112), (112, 112), True), ((4, 33, 47), (48, 64), False)])
+def test_video_ingest_matches_host_pipeline(eng, shape, size, bgr):
+    """clasfv_ingest_u8 against the reference's host pipeline (motion_segment.py:96-106): float32 cast, F.interpolate(
+    trilinear, align_corners=True) to (T,h,w), zeroone_normalizer.  fp32 tolerance 2e-6 on [0,1] values."""
+    from clasfv_b200.src.echonet_dataset import zeroone_normalizer
+    rng = np.random.RandomState(3)
+    t, h0, w0 = shape
+    frames = rng.randint(0, 256, size=(t, h0, w0, 3)).astype(np.uint8)
+    frames[..., 2] = (frames[..., 2] * 0.6).astype(np.uint8)                    # channels with different ranges
+    rgb = frames[..., ::-1] if bgr else frames
+    video = np.ascontiguousarray(rgb.transpose((3, 0, 1, 2))).astype(np.float32)
+    v = torch.Tensor(video).unsqueeze(0)
+    v = F.interpolate(v, size=(v.shape[2], size[0], size[1]), mode="trilinear", align_corners=True)
+    want = zeroone_normalizer(v.squeeze(0).numpy().copy())
+    got = eng.ingest_u8(frames, size[0], size[1], bgr=bgr)
+    assert got.is_cuda and tuple(got.shape) == (3, t, size[0], size[1]) and got.dtype == torch.float32
+    got = got.cpu().numpy()
+    assert float(np.abs(got - want).max()) <= 2e-6
+    assert got.min() == 0.0 and got.reshape(3, -1).max(axis=1).tolist() == [1.0, 1.0, 1.0]
+
+
 @pytest.mark.parametrize("mode", ["bilinear", "nearest"])
 @pytest.mark.parametrize("forward", [True, False])
 def test_apply_sequence_deformation_matches_oracle(mode, forward):
