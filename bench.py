@@ -41,6 +41,16 @@ ENCODER_GFLOP_PER_CLIP = 2 * 81.038
 KERNELS_PER_FORWARD = 42                           # stem + 40 convolutions + head
 
 
+def ncu_traffic():
+    """DRAM bytes per bench step and kernel, from the committed ncu launch list of this workload
+    (profiles/r01_final_dram_traffic_per_step.json, written by tools/launch_list.sh + the aggregation in its header)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_final_dram_traffic_per_step.json")) as f:
+            return json.load(f)["per_kernel"]
+    except Exception:
+        return {}
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -266,6 +276,10 @@ def main():
         algorithmic_tflops = TRUNK_GFLOP_PER_CLIP * N_CLIPS / trunk_ms_per_step
         achieved_tflops = performed_tflops
         n_batches = (N_CLIPS + bc - 1) // bc
+        tr = ncu_traffic() if (not args.per_clip and bc == 64 and args.precision == "bf16") else {}
+        conv_traffic = (tr["conv_umma_kernel"]["dram_read_bytes"] + tr["conv_umma_kernel"]["dram_write_bytes"]) if "conv_umma_kernel" in tr else None
+        wf_key = next((k for k in tr if k.startswith("warp_fuse_staged")), None)
+        fuse_traffic = (tr[wf_key]["dram_read_bytes"] + tr[wf_key]["dram_write_bytes"]) if wf_key else None
         # dense schedule: 10 video-level launches; per batch 14 edge convs + 2 gathers + 27 layer2-4 convs + 4 lateral + 3 temporal
         # pre-pass + 1 head; + 1 fusion kernel per video (ncu launch list: profiles/r01y_launches_bench_steps1.csv)
         launches_per_step = (n_batches * (KERNELS_PER_FORWARD + 3) if args.per_clip else 10 + n_batches * 51) + 1
@@ -284,7 +298,9 @@ def main():
             "gpu_launches": args.steps * launches_per_step,
             "roofline": {"kernel": "conv_umma_kernel (trunk: stem 3x1x1 + layer1-4)",
                          "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peaks["bf16_tflops"], "traffic": None,
+                         "frac": achieved_tflops / peaks["bf16_tflops"], "traffic": conv_traffic,
+                         "traffic_is": "DRAM read+write bytes of all conv_umma_kernel launches of one step (ncu, profiles/"
+                                       "r01_final_dram_traffic_per_step.json); null with --per-clip or another batch size",
                          "peak_source": peaks["source"] + " (sustained; burst %.1f)" % peaks["bf16_tflops_burst"],
                          "achieved_is": "performed FLOPs (2 x true MACs executed by the kernel) / trunk time",
                          "performed_gflop_per_step": stage_gflop["trunk"] / args.steps,
@@ -294,7 +310,7 @@ def main():
                                      "dense-video: stem+layer1 once per video frame, clip-edge frames per clip (bit-identical outputs)"},
             "roofline_warp_fuse": {"kernel": "warp_fuse_kernel", "bound": "hbm", "achieved": fuse_bytes / (fuse_ms * 1e6),
                                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fuse_bytes / (fuse_ms * 1e6) / peaks["hbm_gbs"],
-                                   "traffic": None, "algorithmic_bytes": fuse_bytes,
+                                   "traffic": fuse_traffic, "algorithmic_bytes": fuse_bytes,
                                    "traffic_note": "ncu --set full of the same kernel on configs[2] (256 clips): DRAM read+write / algorithmic "
                                                    "bytes = 1.00 fp32, 0.99 bf16 (profiles/r01y_wf_ncu.csv); instruction-bound, see DESIGN.md 4.5"},
             "clocks": clocks, "mean_abs_flow_px": flow_px,
