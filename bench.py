@@ -218,9 +218,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # warm-up keeps the previous step's result alive while the next one is produced, exactly like the timed loop below:
+    # otherwise the second set of output buffers (acc 20 MB, mask, ...) is cudaMalloc'ed by torch's caching allocator inside
+    # the SECOND TIMED step, and that cudaMalloc stalls the stream for 20-60 ms in one run out of five (found with
+    # tools/bench_repeat.sh: the gap always sat in front of step 1's fusion kernel)
+    res = None
     for _ in range(args.warmup):
-        step_resident()
+        res = step_resident()
     barrier()
+    # Python's cyclic garbage collector is switched off inside the timed regions (as timeit does).
+    import gc
+    gc.collect()
+    gc.disable()
     sampler = ClockSampler(local_rank)
     sampler.start()
     eng.profile_begin()
@@ -258,6 +267,7 @@ def main():
         torch.cuda.synchronize()
         brackets.append(time.perf_counter() - t0)
     e2e_s = min(brackets)
+    gc.enable()
     assert mask.shape == (T_VIDEO, H, W)
 
     times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -292,6 +302,7 @@ def main():
             "config": dict(workload_config(), batch_clips=bc, parallelism=f"video-sharded x{world}, no collective"),
             "clip_frames_per_s": world * N_CLIPS * CLIP * args.steps / (ms_total / 1e3),
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()} | {"warp_fuse": fuse_ms},
+            "warp_fuse_ms_each_step": [round(a.elapsed_time(b), 3) for a, b in fuse_events],
             "e2e": {"value": world * T_VIDEO * args.steps / (e2e_ms / 1e3), "unit": "frames/s",
                     "h2d_bytes_per_step": int(video_host.numel() * 4), "d2h_bytes_per_step": int(T_VIDEO * H * W * 8),
                     "brackets_ms_per_step": [1e3 * t / args.steps for t in brackets], "reported": "faster of two K-step brackets (rank-local; max over ranks)"},

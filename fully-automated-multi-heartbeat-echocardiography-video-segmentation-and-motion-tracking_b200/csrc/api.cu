@@ -734,6 +734,17 @@ int clasfv_set_option(clasfv_handle* h, const char* name, int value) {
 
 int clasfv_profile_begin(clasfv_handle* h) {
   CLASFV_REQUIRE(h, "clasfv_profile_begin: handle is NULL");
+  // The event pool is created here, outside any timed region (no driver object creation between kernel launches);
+  // 1024 events cover ~70 internal batches, more are created on demand.
+  {
+    DeviceGuard guard(h->device);
+    while (h->prof_events.size() < 1024) {
+      cudaEvent_t ev;
+      CLASFV_CUDA(cudaEventCreate(&ev));
+      h->prof_events.push_back(ev);
+    }
+    h->prof_stage.reserve(1024);
+  }
   h->profiling = true; h->prof_calls = 0; h->prof_used = 0; h->prof_stage.clear();
   for (int s = 0; s < 4; ++s) h->prof_gflop[s] = 0.0;
   return CLASFV_OK;
