@@ -488,9 +488,25 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     // column x 8 channels), P1_ITEMS per thread and pass; all loads of a pass are issued before any arithmetic.  Corners 0/1
     // are read unconditionally (a corner that was not fetched has weight 0 and its slot holds finite stale data: the
     // stages are zero-filled at start).
-    constexpr int P1_ITEMS = 4, GT = P1_THREADS / 2;
+    constexpr int P1_ITEMS = 2, P1_PASSES = 3, P1_SLOTS = P1_ITEMS * P1_PASSES, GT = P1_THREADS / 2;
     const int grp = ptid / GT, gtid = ptid % GT;
     const int q1 = g.nx[wt][0] * 8, q2 = q1 + g.nx[wt][1] * 8, q3 = q2 + g.nx[wt][2] * 8, n_items = q3 + g.nx[wt][3] * 8;
+    // item -> (level, column, chunk) is the same for every row: source / destination offsets are computed once
+    uint32_t i_src[P1_SLOTS], i_cs[P1_SLOTS], i_dst[P1_SLOTS], i_woff[P1_SLOTS];
+    bool i_on[P1_SLOTS], i_four[P1_SLOTS];
+#pragma unroll
+    for (int u = 0; u < P1_SLOTS; ++u) {
+      const int q = gtid + u * GT;
+      i_on[u] = q < n_items;
+      const int qq = i_on[u] ? q : 0;
+      const int l = (qq >= q1 ? 1 : 0) + (qq >= q2 ? 1 : 0) + (qq >= q3 ? 1 : 0);
+      const int it = qq - (l == 0 ? 0 : l == 1 ? q1 : l == 2 ? q2 : q3);
+      i_src[u] = (uint32_t)(l == 0 ? g.raw_off[0] : l == 1 ? g.raw_off[1] : l == 2 ? g.raw_off[2] : g.raw_off[3]) + (uint32_t)it * 16u;
+      i_cs[u] = (uint32_t)(l == 0 ? g.nxmax[0] : l == 1 ? g.nxmax[1] : l == 2 ? g.nxmax[2] : g.nxmax[3]) * 128u;
+      i_dst[u] = sw128_offset((uint32_t)((l == 0 ? g.koff[0] : l == 1 ? g.koff[1] : l == 2 ? g.koff[2] : g.koff[3]) + (it >> 3)), (uint32_t)(it & 7));
+      i_woff[u] = (uint32_t)l * 16u;
+      i_four[u] = (l == 0 ? a.tl[0] : l == 1 ? a.tl[1] : l == 2 ? a.tl[2] : a.tl[3]) != a.t;   // the level has T corners
+    }
     for (int i = grp; i < my_rows; i += 2) {
       const int s = i % g.nr; const uint32_t ph = (uint32_t)(i / g.nr) & 1u;
       const int rs = i % g.nraw; const uint32_t rph = (uint32_t)(i / g.nraw) & 1u;
@@ -499,35 +515,28 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
       const uint8_t* plw = reinterpret_cast<const uint8_t*>(&plans[rs]);
       const uint8_t* stage = sm + raw_off0 + (uint32_t)rs * (uint32_t)g.raw_stage_bytes;
       uint8_t* rst = sm + r_off + (uint32_t)s * r_stage_bytes;
-      for (int q0 = gtid; q0 < n_items; q0 += P1_ITEMS * GT) {
+#pragma unroll
+      for (int pass = 0; pass < P1_PASSES; ++pass) {
         uint4 ra[P1_ITEMS], rb[P1_ITEMS];
         float4 wq[P1_ITEMS];
-        uint32_t i_src[P1_ITEMS], i_cs[P1_ITEMS], i_dst[P1_ITEMS];
-        bool i_on[P1_ITEMS], i_four[P1_ITEMS];
 #pragma unroll
-        for (int u = 0; u < P1_ITEMS; ++u) {
-          const int q = q0 + u * GT;
-          i_on[u] = q < n_items;
-          const int qq = i_on[u] ? q : 0;
-          const int l = (qq >= q1 ? 1 : 0) + (qq >= q2 ? 1 : 0) + (qq >= q3 ? 1 : 0);
-          const int it = qq - (l == 0 ? 0 : l == 1 ? q1 : l == 2 ? q2 : q3);
-          i_src[u] = (uint32_t)(l == 0 ? g.raw_off[0] : l == 1 ? g.raw_off[1] : l == 2 ? g.raw_off[2] : g.raw_off[3]) + (uint32_t)it * 16u;
-          i_cs[u] = (uint32_t)(l == 0 ? g.nxmax[0] : l == 1 ? g.nxmax[1] : l == 2 ? g.nxmax[2] : g.nxmax[3]) * 128u;
-          i_dst[u] = sw128_offset((uint32_t)((l == 0 ? g.koff[0] : l == 1 ? g.koff[1] : l == 2 ? g.koff[2] : g.koff[3]) + (it >> 3)), (uint32_t)(it & 7));
-          i_four[u] = (l == 0 ? a.tl[0] : l == 1 ? a.tl[1] : l == 2 ? a.tl[2] : a.tl[3]) != a.t;   // the level has T corners
-          wq[u] = *reinterpret_cast<const float4*>(plw + (uint32_t)l * 16u);
-          ra[u] = *reinterpret_cast<const uint4*>(stage + i_src[u]);
-          rb[u] = *reinterpret_cast<const uint4*>(stage + i_src[u] + i_cs[u]);
+        for (int v = 0; v < P1_ITEMS; ++v) {
+          const int u = pass * P1_ITEMS + v;
+          if (!i_on[u]) continue;
+          wq[v] = *reinterpret_cast<const float4*>(plw + i_woff[u]);
+          ra[v] = *reinterpret_cast<const uint4*>(stage + i_src[u]);
+          rb[v] = *reinterpret_cast<const uint4*>(stage + i_src[u] + i_cs[u]);
         }
 #pragma unroll
-        for (int u = 0; u < P1_ITEMS; ++u) {
+        for (int v = 0; v < P1_ITEMS; ++v) {
+          const int u = pass * P1_ITEMS + v;
           if (!i_on[u]) continue;
-          const uint32_t xa[4] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w}, xb[4] = {rb[u].x, rb[u].y, rb[u].z, rb[u].w};
+          const uint32_t xa[4] = {ra[v].x, ra[v].y, ra[v].z, ra[v].w}, xb[4] = {rb[v].x, rb[v].y, rb[v].z, rb[v].w};
           float lo[4], hi[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            lo[e] = wq[u].x * __uint_as_float(xa[e] << 16); hi[e] = wq[u].x * __uint_as_float(xa[e] & 0xffff0000u);
-            lo[e] = fmaf(wq[u].y, __uint_as_float(xb[e] << 16), lo[e]); hi[e] = fmaf(wq[u].y, __uint_as_float(xb[e] & 0xffff0000u), hi[e]);
+            lo[e] = wq[v].x * __uint_as_float(xa[e] << 16); hi[e] = wq[v].x * __uint_as_float(xa[e] & 0xffff0000u);
+            lo[e] = fmaf(wq[v].y, __uint_as_float(xb[e] << 16), lo[e]); hi[e] = fmaf(wq[v].y, __uint_as_float(xb[e] & 0xffff0000u), hi[e]);
           }
           if (i_four[u]) {
             const uint4 rc = *reinterpret_cast<const uint4*>(stage + i_src[u] + 2u * i_cs[u]);
@@ -535,8 +544,8 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
             const uint32_t xc[4] = {rc.x, rc.y, rc.z, rc.w}, xd[4] = {rd.x, rd.y, rd.z, rd.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              lo[e] = fmaf(wq[u].z, __uint_as_float(xc[e] << 16), lo[e]); hi[e] = fmaf(wq[u].z, __uint_as_float(xc[e] & 0xffff0000u), hi[e]);
-              lo[e] = fmaf(wq[u].w, __uint_as_float(xd[e] << 16), lo[e]); hi[e] = fmaf(wq[u].w, __uint_as_float(xd[e] & 0xffff0000u), hi[e]);
+              lo[e] = fmaf(wq[v].z, __uint_as_float(xc[e] << 16), lo[e]); hi[e] = fmaf(wq[v].z, __uint_as_float(xc[e] & 0xffff0000u), hi[e]);
+              lo[e] = fmaf(wq[v].w, __uint_as_float(xd[e] << 16), lo[e]); hi[e] = fmaf(wq[v].w, __uint_as_float(xd[e] & 0xffff0000u), hi[e]);
             }
           }
           *reinterpret_cast<uint4*>(rst + i_dst[u]) =
