@@ -161,12 +161,12 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
             mbar_arrive_expect_tx(full_bar(stage), tx);
             const uint32_t a_dst = a_base + (uint32_t)(stage * a_slab_bytes);
             if (framewise) {
-              for (int f = 0; f < bt + 2; ++f) {
-                const int v = ct + f;           // frame of the virtual clip (ct = t0 - 1)
-                const bool from_a = v < fw_split;
-                tma_load_5d(a_dst + (uint32_t)(f * frame_bytes), &p.tmap_a[from_a ? 0 : 1], full_bar(stage),
-                            ks * SLAB_K, cw, ch, v + (from_a ? fw_a_toff : fw_b_toff), b0);
-              }
+              // the tile spans the whole virtual clip (bt == to, ct == -1): frames [-1, split) come from source A and
+              // [split, to] from source B, each contiguous in its source, so two box loads (map 0: split+1 frames,
+              // map 1: the rest) fill the slab; a frame outside its source's extent is zero-filled by TMA
+              const int na = fw_split - ct;
+              tma_load_5d(a_dst, &p.tmap_a[0], full_bar(stage), ks * SLAB_K, cw, ch, ct + fw_a_toff, b0);
+              tma_load_5d(a_dst + (uint32_t)(na * frame_bytes), &p.tmap_a[1], full_bar(stage), ks * SLAB_K, cw, ch, ct + na + fw_b_toff, b0);
             } else {
               tma_load_5d(a_dst, map, full_bar(stage), ks * SLAB_K, cw, ch, ct, b0);
             }
@@ -400,11 +400,12 @@ bool g_unaligned_taps = true;       // tap starts inside a swizzle atom are fine
 
 // Choose the (bw,bh,bt,bb) box of <= 128 output positions that wastes the fewest MMA rows, under the
 // layout constraints of the sharing mode (see UmmaParams).  Returns false if no box satisfies them.
-bool choose_box(int wo, int ho, int to, int n, ShareMode mode, int* bw, int* bh, int* bt, int* bb, double* eff_out = nullptr) {
+bool choose_box(int wo, int ho, int to, int n, ShareMode mode, int* bw, int* bh, int* bt, int* bb, double* eff_out = nullptr, int force_t = 0) {
   double best = -1.0; int best_rows = 0, best_halo = 1 << 30; bool found = false;
   for (int w = 1; w <= wo && w <= TILE_M; ++w)
     for (int h = 1; h <= ho && w * h <= TILE_M; ++h)
       for (int t = 1; t <= to && w * h * t <= TILE_M; ++t) {
+        if (force_t && t != force_t) continue;
         int b = TILE_M / (w * h * t);
         if (b > n) b = n;
         if (b < 1) continue;
@@ -481,7 +482,7 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   for (int attempt = 0; attempt < 2; ++attempt) {
     mode = attempt == 0 ? want : SHARE_NONE;
     double eff = 0.0;
-    if (!choose_box(s.wo, s.ho, s.to, s.n, mode, &p.bw, &p.bh, &p.bt, &p.bb, &eff)) continue;
+    if (!choose_box(s.wo, s.ho, s.to, s.n, mode, &p.bw, &p.bh, &p.bt, &p.bb, &eff, a.seg.on ? s.to : 0)) continue;
     if (mode != SHARE_NONE && !a.seg.on && eff < 0.8 * eff_none) continue;
     const int rows_out = p.bw * p.bh * p.bt * p.bb;
     int slab_rows = rows_out, taps_per_group = 1;
@@ -571,7 +572,8 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
     // frame-wise loads: map 0 = source A, map 1 = source B, one frame per box
     p.framewise = 1; p.fw_split = a.seg.split; p.fw_a_toff = a.seg.a_toff; p.fw_b_toff = a.seg.b_toff;
     p.frame_bytes = p.bw * p.bh * SLAB_K * 2;
-    const uint32_t boxf[5] = {(uint32_t)SLAB_K, (uint32_t)p.bw, (uint32_t)p.bh, 1u, 1u};
+    CLASFV_REQUIRE(p.bt == s.to && a.seg.split >= 0 && a.seg.split <= s.to, "conv_umma: a time-segmented tile must span the virtual clip");
+    const int na = a.seg.split + 1, nb = s.to + 2 - na;          // frames [-1, split) from A, [split, to] from B
     const uint64_t e = 2, frame = (uint64_t)s.hi * s.wi * s.cin;
     for (int v = 0; v < MAX_VIEWS; ++v) {
       const bool is_b = v == 1;
@@ -579,6 +581,7 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
       const uint64_t bstride = is_b ? (uint64_t)a.seg.b_batch_stride : (a.in_batch_stride ? (uint64_t)a.in_batch_stride : frame * tt);
       const uint64_t dims[5] = {(uint64_t)s.cin, (uint64_t)s.wi, (uint64_t)s.hi, (uint64_t)tt, (uint64_t)s.n};
       const uint64_t strides[4] = {(uint64_t)s.cin * e, (uint64_t)s.wi * s.cin * e, frame * e, bstride * e};
+      const uint32_t boxf[5] = {(uint32_t)SLAB_K, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)(is_b ? nb : na), 1u};
       int rc = encode_map(&p.tmap_a[v], const_cast<void*>(is_b ? a.seg.b : a.in), 5, dims, strides, boxf);
       if (rc) return rc;
     }
