@@ -192,6 +192,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL announces its version on STDOUT when NCCL_DEBUG is VERSION (this image's default): keep stdout to the one
+        # JSON line the contract asks for; an explicit NCCL_DEBUG=INFO / TRACE from the caller is left alone
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     net = R2plus1D_18_MotionNet(pretrained=False, precision=args.precision)
