@@ -29,6 +29,12 @@ import sys
 import threading
 import time
 
+# The contract is ONE JSON line on stdout.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+# version banner there when a torchrun job creates its first communicator), so fd 1 is pointed at stderr for the whole
+# run and the JSON line goes to a private duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -147,7 +153,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     return 0
 
 
@@ -192,10 +198,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL announces its version on STDOUT when NCCL_DEBUG is VERSION (this image's default): keep stdout to the one
-        # JSON line the contract asks for; an explicit NCCL_DEBUG=INFO / TRACE from the caller is left alone
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     net = R2plus1D_18_MotionNet(pretrained=False, precision=args.precision)
@@ -336,7 +338,7 @@ def main():
             line["cpu_baseline"] = {"value": cb["frames_per_s"], "unit": "frames/s", "cores": cb["threads"], "kind": "port",
                                     "sample": "4 of 169 stride-1 clips (reference network restated on PyTorch CPU, "
                                               f"{cb['sec_per_clip_model']:.2f} s/clip) + oracle warp-fuse, scaled to the whole video"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -129,3 +129,24 @@ def test_forward_windows_groups_equally_spaced_runs_into_single_calls():
         seg = torch.zeros(len(starts), 2, 32, 4, 4); mot = torch.zeros(len(starts), 4, 32, 4, 4)
         eng.forward_windows(video, seg, mot, 1, starts, 32, batch_clips=7)
         assert eng.calls == expect and eng.options == {"sub_batch": 7}
+
+
+def test_config4_lengths_and_video_assignment():
+    """BASELINE config 4: 1 277 lengths ~N(175,55) in [64,400]; every video lands on exactly one rank and
+    the longest-first assignment keeps the per-rank clip counts within 0.1 % of each other (round-robin: several %)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "config4_many_videos", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "config4_many_videos.py"))
+    c4 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(c4)
+    lengths = c4.config4_lengths()
+    assert len(lengths) == 1277 and lengths.min() >= 64 and lengths.max() <= 400
+    assert abs(float(lengths.mean()) - 175.0) < 5.0
+    assert (lengths == c4.config4_lengths()).all()                      # seeded
+    for world in (1, 2, 4, 8):
+        for how in ("lpt", "round_robin"):
+            seen = sorted(i for r in range(world) for i in c4.assign(lengths, r, world, how))
+            assert seen == list(range(1277))
+        loads = c4.rank_loads(lengths, world, "lpt")
+        assert max(loads) / (sum(loads) / world) < 1.001
