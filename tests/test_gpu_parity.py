@@ -516,3 +516,53 @@ def test_long_video_split_single_rank_equals_direct(net_fp32):
         assert a.dtype == np.int64 and np.array_equal(a, b)
     finally:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ GPU yardstick
+def test_faster_than_pytorch_eager_of_the_reference_algorithm_on_the_same_gpu(net_bf16, sd):
+    """SURVEY.md 8(d) "GPU reference point": the reference ships no Blackwell code, so the kernel to beat on this GPU is
+    stock PyTorch eager (cuDNN / cuBLAS, bf16 autocast) of the reference's forward pass.  Same 16 independent clips, model
+    forward only (per-clip schedule: no sharing between windows), CUDA events, the better of two rounds each."""
+    n, shape = 16, (32, 112, 112)
+    x = fixtures.synthetic_clip(*shape, seed=21, batch=n).cuda()
+    sd_dev = {k: v.cuda() for k, v in model_ref.strip_module_prefix(sd).items()}
+
+    def timed(fn):
+        times = []
+        for _ in range(3):                                   # first round is the warm-up (cuDNN heuristics, workspace)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        return min(times[1:]), out
+
+    def eager():
+        outs = []
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            for i in range(0, n, 4):                          # 4 clips per call: the 1 024-channel concat is 3.3 GB in bf16
+                outs.append(model_ref.forward(sd_dev, x[i:i + 4]))
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+
+    eng_ = net_bf16.engine()
+    eng_.set_option("dense_video", 0)
+    try:
+        ms_ours, (seg, _mot) = timed(lambda: net_bf16(x))
+    finally:
+        eng_.set_option("dense_video", 1)
+    ms_eager, (seg_e, _mot_e) = timed(eager)
+    agree = float(((seg[:, 1] > seg[:, 0]) == (seg_e[:, 1] > seg_e[:, 0])).float().mean())
+    fps_ours, fps_eager = n * 32 / ms_ours * 1e3, n * 32 / ms_eager * 1e3
+    print(f"\n[eager yardstick] ours {ms_ours:.2f} ms ({fps_ours:.0f} clip-frames/s) | PyTorch eager bf16 autocast {ms_eager:.2f} ms "
+          f"({fps_eager:.0f} clip-frames/s) | ratio {ms_eager / ms_ours:.1f}x | mask agreement {agree * 100:.2f}%")
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        import json
+        with open(os.path.join(out_dir, "eager_yardstick.json"), "w") as f:
+            json.dump({"clips": n, "shape": list(shape), "ours_ms": ms_ours, "eager_bf16_autocast_ms": ms_eager,
+                       "ours_clip_frames_per_s": fps_ours, "eager_clip_frames_per_s": fps_eager,
+                       "speedup": ms_eager / ms_ours, "mask_agreement": agree, "schedule": "per-clip (no window sharing)"}, f)
+    assert ms_ours * 2 < ms_eager            # at least twice as fast as the library path on the same GPU
+    assert agree > 0.97                      # two bf16 evaluations of the same fp32 network (see the autocast yardstick test above)
