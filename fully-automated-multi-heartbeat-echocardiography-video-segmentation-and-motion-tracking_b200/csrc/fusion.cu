@@ -241,25 +241,44 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
 // L1/LSU pipe (16 scattered global loads per clip and pixel); here a CTA owns one output frame g and one slice of
 // its pixels, and for every hop (clip c, source frame ts) landing on g a producer warp bulk-copies the two class
 // planes prob[c, :, ts] (contiguous H*W elements each) into a ring of shared-memory units (mbarrier full / empty).
-// Consumer threads own fixed pixel pairs for the whole CTA lifetime: running sums live in registers, flow and direct
-// votes are read from global memory as coalesced pair loads, and the eight bilinear taps of a hop are LDS.  The
+// Consumer threads own fixed pixels for the whole CTA lifetime: running sums live in registers, flow and direct
+// votes are read from global memory as coalesced loads, and the eight bilinear taps of a hop are LDS.  The
 // order of additions per pixel is exactly warp_fuse_kernel's (clip by clip: direct, forward hop, backward hop), so
 // both kernels give bit-identical sums.  No float atomics, no intermediate warped volume.
 constexpr int WS_MAX_UNITS = 8;
-// CTA shape per element type (measured, config 3): fp32 runs best with 512 threads x 7 pixel pairs (128 registers, no
-// spills, more ILP per thread), bf16 with 1024 threads x 4 pairs (its 2-byte taps are latency-, not register-bound).
+// CTA shape per element type (measured, config 3).  An item is a pair of adjacent pixels, loaded with one instruction
+// (8 bytes fp32, 4 bytes bf16).  fp32: 512 threads x 7 pairs (128 registers, more ILP per thread); bf16: 1024 threads x
+// 4 pairs (its 2-byte taps are latency-, not register-bound).  Measured and rejected for fp32: single pixels per item, so
+// that the lanes' taps are one word apart instead of two (no 2-way bank conflict under a smooth flow): twice the global
+// load instructions cost more than the conflicts (1.05-1.18 ms against 0.96-1.05 ms for config 3).
 template <typename T> struct WsShape;
-template <> struct WsShape<float> { static constexpr int THREADS = 512, PAIRS = 7; };
-template <> struct WsShape<__nv_bfloat16> { static constexpr int THREADS = 1024, PAIRS = 4; };
+template <> struct WsShape<float> { static constexpr int THREADS = 512, ITEMS = 7, PP = 2; };
+template <> struct WsShape<__nv_bfloat16> { static constexpr int THREADS = 1024, ITEMS = 4, PP = 2; };
 
-template <typename T> struct Pair;
-template <> struct Pair<float> {
-  static __device__ __forceinline__ float2 ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+template <typename T> struct Item;
+template <> struct Item<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) {
+    const float2 o = __ldg(reinterpret_cast<const float2*>(p)); v[0] = o.x; v[1] = o.y;
+  }
+  static __device__ __forceinline__ void ld_acc(const float* p, float (&v)[2]) {
+    const float2 o = *reinterpret_cast<const float2*>(p); v[0] = o.x; v[1] = o.y;
+  }
+  static __device__ __forceinline__ void st_acc(float* p, const float (&v)[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+  static __device__ __forceinline__ void st_mask(uint8_t* p, const int (&m)[2]) {
+    *reinterpret_cast<uchar2*>(p) = make_uchar2((unsigned char)m[0], (unsigned char)m[1]);
+  }
 };
-template <> struct Pair<__nv_bfloat16> {
-  static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) {
+template <> struct Item<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[2]) {
     const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(p));
-    return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
+    v[0] = __uint_as_float(r << 16); v[1] = __uint_as_float(r & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void ld_acc(const float* p, float (&v)[2]) {
+    const float2 o = *reinterpret_cast<const float2*>(p); v[0] = o.x; v[1] = o.y;
+  }
+  static __device__ __forceinline__ void st_acc(float* p, const float (&v)[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+  static __device__ __forceinline__ void st_mask(uint8_t* p, const int (&m)[2]) {
+    *reinterpret_cast<uchar2*>(p) = make_uchar2((unsigned char)m[0], (unsigned char)m[1]);
   }
 };
 template <typename T> __device__ __forceinline__ float lds_val(const T* p);
@@ -269,34 +288,42 @@ template <> __device__ __forceinline__ float lds_val<__nv_bfloat16>(const __nv_b
 }
 // Branch-free bilinear taps for the staged kernel.  grid_sample(padding_mode="border") clamps the source coordinate to
 // [0, S-1] BEFORE splitting it, so a corner that falls outside the plane always has weight exactly 0 (x0 == W-1 implies
-// ix == W-1): reading the clamped neighbour instead and adding 0 * finite gives the same sum as skipping the tap.
-struct Taps { int p, dx, dy; float nw, ne, sw, se; };
-__device__ __forceinline__ Taps taps_setup(float bx, float by, float fx, float fy, int h, int w) {
+// ix == W-1).  Instead of skipping that corner the north-west corner is clamped to (H-2, W-2): at ix == W-1 the pair
+// (W-2, W-1) then gets the weights (0, 1) where grid_sample uses (W-1, -) with (1, 0).  The four-term sum
+// nw*a + ne*b + sw*c + se*d keeps its order, a zero-weight term adds exactly 0, and the non-zero products are the same
+// two numbers in the same order, so the result is bit-identical to warp_fuse_kernel's conditional taps - with no
+// select, no per-corner offset and the +1 neighbours at immediate offsets.  (x0+1) - ix is written 1 - (ix - x0): ix - x0
+// is exact, so both are one rounding of the same real number.
+struct Taps { int p; float nw, ne, sw, se; };
+struct TapGeom {                      // loop invariants of taps_setup, converted once per thread
+  float wf, hf, wm1, hm1, wm2, hm2;
+  __device__ __forceinline__ TapGeom(int h, int w)
+      : wf((float)w), hf((float)h), wm1((float)(w - 1)), hm1((float)(h - 1)), wm2((float)(w - 2)), hm2((float)(h - 2)) {}
+};
+__device__ __forceinline__ Taps taps_setup(float bx, float by, float fx, float fy, const TapGeom& g) {
   const float gx = bx + fx, gy = by + fy;
-  float ix = ((gx + 1.f) * (float)w - 1.f) * 0.5f;
-  float iy = ((gy + 1.f) * (float)h - 1.f) * 0.5f;
-  ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
-  iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
-  const float fx0 = floorf(ix), fy0 = floorf(iy);
-  const int x0 = (int)fx0, y0 = (int)fy0;
-  const float x1 = fx0 + 1.f, y1 = fy0 + 1.f;
+  float ix = ((gx + 1.f) * g.wf - 1.f) * 0.5f;
+  float iy = ((gy + 1.f) * g.hf - 1.f) * 0.5f;
+  ix = fminf(g.wm1, fmaxf(ix, 0.f));
+  iy = fminf(g.hm1, fmaxf(iy, 0.f));
+  const float fx0 = fminf(floorf(ix), g.wm2), fy0 = fminf(floorf(iy), g.hm2);
+  const float wx1 = ix - fx0, wy1 = iy - fy0;
+  const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
   Taps t;
-  t.nw = (x1 - ix) * (y1 - iy);
-  t.ne = (ix - fx0) * (y1 - iy);
-  t.sw = (x1 - ix) * (iy - fy0);
-  t.se = (ix - fx0) * (iy - fy0);
-  t.p = y0 * w + x0;
-  t.dx = x0 + 1 < w ? 1 : 0;
-  t.dy = y0 + 1 < h ? w : 0;
+  t.nw = wx0 * wy0;
+  t.ne = wx1 * wy0;
+  t.sw = wx0 * wy1;
+  t.se = wx1 * wy1;
+  t.p = (int)fmaf(fy0, g.wf, fx0);            // y0*W + x0: small integers, exact in fp32
   return t;
 }
 template <typename T>
-__device__ __forceinline__ float taps_fetch(const T* plane, const Taps& t) {
+__device__ __forceinline__ float taps_fetch(const T* plane, const Taps& t, int w) {
   const T* p = plane + t.p;
   float v = lds_val<T>(p) * t.nw;
-  v += lds_val<T>(p + t.dx) * t.ne;
-  v += lds_val<T>(p + t.dy) * t.sw;
-  v += lds_val<T>(p + t.dy + t.dx) * t.se;
+  v += lds_val<T>(p + 1) * t.ne;
+  v += lds_val<T>(p + w) * t.sw;
+  v += lds_val<T>(p + w + 1) * t.se;
   return v;
 }
 
@@ -304,7 +331,7 @@ template <typename T>
 __global__ void __launch_bounds__(WsShape<T>::THREADS, 1) warp_fuse_staged_kernel(const WarpFuseArgs a, int n_units, int slice_pix) {
   extern __shared__ __align__(128) uint8_t ws_smem[];
   using namespace ptx;
-  constexpr int WS_THREADS = WsShape<T>::THREADS, WS_PAIRS = WsShape<T>::PAIRS, WS_CONSUMERS = WS_THREADS - 32;   // warp 0 = producer
+  constexpr int WS_THREADS = WsShape<T>::THREADS, ITEMS = WsShape<T>::ITEMS, PP = WsShape<T>::PP, WS_CONSUMERS = WS_THREADS - 32;   // warp 0 = producer
   const int g = blockIdx.y;
   const int hw = a.h * a.w;
   const int L = a.clip_len;
@@ -360,37 +387,43 @@ __global__ void __launch_bounds__(WsShape<T>::THREADS, 1) warp_fuse_staged_kerne
       a.cnt[g] = (a.accumulate ? a.cnt[g] : 0) + votes;
     }
   } else {
-    // ---------------------------------------------------------------- consumers: fixed pixel pairs, sums in registers
+    // ---------------------------------------------------------------- consumers: fixed items (pixels / pixel pairs), sums in registers
     const int ctid = threadIdx.x - 32;
     const int pix0 = blockIdx.x * slice_pix;
     const int pix_end = min(hw, pix0 + slice_pix);
-    int px[WS_PAIRS];
-    float bx0[WS_PAIRS], bx1[WS_PAIRS], by[WS_PAIRS];
-    float s0[2 * WS_PAIRS], s1[2 * WS_PAIRS];
+    const int p0 = pix0 + PP * ctid;                       // item k of this thread starts at pixel p0 + k * PP * WS_CONSUMERS
+    constexpr int ITEM_STEP = PP * WS_CONSUMERS;
+    // items past the slice end are simply not there: n_items is the same for all but the last lanes of a slice
+    const int n_items = p0 < pix_end ? min(ITEMS, (pix_end - p0 + ITEM_STEP - 1) / ITEM_STEP) : 0;
+    float bx[ITEMS][PP], by[ITEMS];
+    float s0[ITEMS][PP], s1[ITEMS][PP];
     float* acc = a.acc + (int64_t)g * 2 * hw;
 #pragma unroll
-    for (int k = 0; k < WS_PAIRS; ++k) {
-      const int p = pix0 + 2 * (ctid + k * WS_CONSUMERS);
-      px[k] = p < pix_end ? p : -1;
-      const int i = p < pix_end ? p / a.w : 0, j = p < pix_end ? p % a.w : 0;     // W is even: a pair never straddles rows
-      bx0[k] = linspace_pm1(j, a.w); bx1[k] = linspace_pm1(j + 1 < a.w ? j + 1 : j, a.w); by[k] = linspace_pm1(i, a.h);
-      s0[2 * k] = s0[2 * k + 1] = s1[2 * k] = s1[2 * k + 1] = 0.f;
-      if (a.accumulate && px[k] >= 0) {
-        const float2 o0 = *reinterpret_cast<const float2*>(acc + p), o1 = *reinterpret_cast<const float2*>(acc + hw + p);
-        s0[2 * k] = o0.x; s0[2 * k + 1] = o0.y; s1[2 * k] = o1.x; s1[2 * k + 1] = o1.y;
-      }
+    for (int k = 0; k < ITEMS; ++k) {
+      const int p = p0 + k * ITEM_STEP;
+      const bool on = k < n_items;
+      const int i = on ? p / a.w : 0, j = on ? p % a.w : 0;     // PP == 2: W is even, a pair never straddles rows
+      by[k] = linspace_pm1(i, a.h);
+#pragma unroll
+      for (int q = 0; q < PP; ++q) { bx[k][q] = linspace_pm1(j + q < a.w ? j + q : j, a.w); s0[k][q] = 0.f; s1[k][q] = 0.f; }
+      if (a.accumulate && on) { Item<T>::ld_acc(acc + p, s0[k]); Item<T>::ld_acc(acc + hw + p, s1[k]); }
     }
+    const TapGeom geom(a.h, a.w);
     int item = 0;
     for (int c = lo; c < hi; ++c) {
       const int t = g - __ldg(a.clip_start + c);
-      const T* pc = prob + (int64_t)c * 2 * L * hw;
-      const T* mc = mot + (int64_t)c * 4 * L * hw;
+      const T* pc = prob + (int64_t)c * 2 * L * hw + p0;
+      const T* mc = mot + (int64_t)c * 4 * L * hw + p0;
       if (t >= 0 && t < L) {                                   // direct vote
+        const T* d0 = pc + (int64_t)t * hw;
+        const T* d1 = pc + (int64_t)(L + t) * hw;
 #pragma unroll
-        for (int k = 0; k < WS_PAIRS; ++k) {
-          if (px[k] < 0) continue;
-          const float2 v0 = Pair<T>::ld(pc + (int64_t)t * hw + px[k]), v1 = Pair<T>::ld(pc + (int64_t)(L + t) * hw + px[k]);
-          s0[2 * k] += v0.x; s0[2 * k + 1] += v0.y; s1[2 * k] += v1.x; s1[2 * k + 1] += v1.y;
+        for (int k = 0; k < ITEMS; ++k) {
+          if (k >= n_items) break;
+          float v0[PP], v1[PP];
+          Item<T>::ld(d0 + k * ITEM_STEP, v0); Item<T>::ld(d1 + k * ITEM_STEP, v1);
+#pragma unroll
+          for (int q = 0; q < PP; ++q) { s0[k][q] += v0[q]; s1[k][q] += v1[q]; }
         }
       }
 #pragma unroll
@@ -400,23 +433,23 @@ __global__ void __launch_bounds__(WsShape<T>::THREADS, 1) warp_fuse_staged_kerne
         if (!on) continue;
         const T* fxp = mc + (int64_t)((hop == 0 ? 0 : 2 * L) + ts) * hw;
         const T* fyp = mc + (int64_t)((hop == 0 ? L : 3 * L) + ts) * hw;
-        float2 fx[WS_PAIRS], fy[WS_PAIRS];
+        float fx[ITEMS][PP], fy[ITEMS][PP];
 #pragma unroll
-        for (int k = 0; k < WS_PAIRS; ++k)
-          if (px[k] >= 0) { fx[k] = Pair<T>::ld(fxp + px[k]); fy[k] = Pair<T>::ld(fyp + px[k]); }
+        for (int k = 0; k < ITEMS; ++k)
+          if (k < n_items) { Item<T>::ld(fxp + k * ITEM_STEP, fx[k]); Item<T>::ld(fyp + k * ITEM_STEP, fy[k]); }
         const int u = item % n_units; const uint32_t ph = (uint32_t)(item / n_units) & 1u;
         mbar_wait(bar0 + 8u * u, ph);
         const T* u0 = reinterpret_cast<const T*>(ws_smem + (size_t)u * unit_bytes);
         const T* u1 = u0 + hw;
 #pragma unroll
-        for (int k = 0; k < WS_PAIRS; ++k) {
-          if (px[k] < 0) continue;
-          const Taps ta = taps_setup(bx0[k], by[k], fx[k].x, fy[k].x, a.h, a.w);
-          s0[2 * k] += taps_fetch<T>(u0, ta);
-          s1[2 * k] += taps_fetch<T>(u1, ta);
-          const Taps tb = taps_setup(bx1[k], by[k], fx[k].y, fy[k].y, a.h, a.w);
-          s0[2 * k + 1] += taps_fetch<T>(u0, tb);
-          s1[2 * k + 1] += taps_fetch<T>(u1, tb);
+        for (int k = 0; k < ITEMS; ++k) {
+          if (k >= n_items) break;
+#pragma unroll
+          for (int q = 0; q < PP; ++q) {
+            const Taps ta = taps_setup(bx[k][q], by[k], fx[k][q], fy[k][q], geom);
+            s0[k][q] += taps_fetch<T>(u0, ta, a.w);
+            s1[k][q] += taps_fetch<T>(u1, ta, a.w);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + 8u * (n_units + u));
@@ -425,14 +458,15 @@ __global__ void __launch_bounds__(WsShape<T>::THREADS, 1) warp_fuse_staged_kerne
     }
     int lv_count = 0;
 #pragma unroll
-    for (int k = 0; k < WS_PAIRS; ++k) {
-      if (px[k] < 0) continue;
-      const int p = px[k];
-      *reinterpret_cast<float2*>(acc + p) = make_float2(s0[2 * k], s0[2 * k + 1]);
-      *reinterpret_cast<float2*>(acc + hw + p) = make_float2(s1[2 * k], s1[2 * k + 1]);
-      const int m0 = s1[2 * k] > s0[2 * k] ? 1 : 0, m1 = s1[2 * k + 1] > s0[2 * k + 1] ? 1 : 0;
-      lv_count += m0 + m1;
-      if (a.mask) *reinterpret_cast<uchar2*>(a.mask + (int64_t)g * hw + p) = make_uchar2((unsigned char)m0, (unsigned char)m1);
+    for (int k = 0; k < ITEMS; ++k) {
+      if (k >= n_items) break;
+      const int p = p0 + k * ITEM_STEP;
+      Item<T>::st_acc(acc + p, s0[k]);
+      Item<T>::st_acc(acc + hw + p, s1[k]);
+      int m[PP];
+#pragma unroll
+      for (int q = 0; q < PP; ++q) { m[q] = s1[k][q] > s0[k][q] ? 1 : 0; lv_count += m[q]; }
+      if (a.mask) Item<T>::st_mask(a.mask + (int64_t)g * hw + p, m);
     }
     if (a.area) {
       lv_count = __reduce_add_sync(0xffffffffu, lv_count);
@@ -582,9 +616,9 @@ int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
     static const bool no_staged = getenv("CLASFV_WARP_FUSE_DIRECT") != nullptr;
     const bool aligned = (hw * es) % 16 == 0 && a.w % 2 == 0 && ((uintptr_t)a.prob % 16) == 0 && ((uintptr_t)a.acc % 8) == 0 &&
                          (!a.mask || ((uintptr_t)a.mask % 2) == 0);
-    if (units >= 2 && aligned && !no_staged) {
-      const int per_cta = a.dtype == CLASFV_F32 ? (WsShape<float>::THREADS - 32) * 2 * WsShape<float>::PAIRS
-                                                : (WsShape<__nv_bfloat16>::THREADS - 32) * 2 * WsShape<__nv_bfloat16>::PAIRS;
+    if (units >= 2 && aligned && a.h >= 2 && !no_staged) {        // (w >= 2 follows from the even width)
+      const int per_cta = a.dtype == CLASFV_F32 ? (WsShape<float>::THREADS - 32) * WsShape<float>::PP * WsShape<float>::ITEMS
+                                                : (WsShape<__nv_bfloat16>::THREADS - 32) * WsShape<__nv_bfloat16>::PP * WsShape<__nv_bfloat16>::ITEMS;
       const int slices = (int)cdiv(hw, per_cta);
       int slice_pix = (int)cdiv(hw, slices);
       slice_pix += slice_pix & 1;                           // even: pixel pairs
