@@ -246,14 +246,16 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
 // order of additions per pixel is exactly warp_fuse_kernel's (clip by clip: direct, forward hop, backward hop), so
 // both kernels give bit-identical sums.  No float atomics, no intermediate warped volume.
 constexpr int WS_MAX_UNITS = 8;
-// CTA shape per element type (measured, config 3).  An item is a pair of adjacent pixels, loaded with one instruction
-// (8 bytes fp32, 4 bytes bf16).  fp32: 512 threads x 7 pairs (128 registers, more ILP per thread); bf16: 1024 threads x
-// 4 pairs (its 2-byte taps are latency-, not register-bound).  Measured and rejected for fp32: single pixels per item, so
-// that the lanes' taps are one word apart instead of two (no 2-way bank conflict under a smooth flow): twice the global
-// load instructions cost more than the conflicts (1.05-1.18 ms against 0.96-1.05 ms for config 3).
-template <typename T> struct WsShape;
-template <> struct WsShape<float> { static constexpr int THREADS = 512, ITEMS = 7, PP = 2; };
-template <> struct WsShape<__nv_bfloat16> { static constexpr int THREADS = 1024, ITEMS = 4, PP = 2; };
+// CTA shape (measured, config 3, 256 clips, ms at zero / 4 px flow).  An item is a pair of adjacent pixels, loaded with one
+// instruction (8 bytes fp32, 4 bytes bf16).  512 threads x 7 pairs (128 registers, no spills worth the name, 14 independent
+// tap chains per thread) is the best shape for both element types:
+//   fp32   512x7 0.80 / 0.96    384x9 0.85 / 0.98    768x5 0.94 / 1.09
+//   bf16   512x7 0.82 / 0.92    768x5 1.10 / 1.17    1024x4 1.14 / 1.22 (64-register cap: spills and constant reloads)
+// Also measured and rejected for fp32: single pixels per item, so that the lanes' taps are one word apart instead of two
+// (no 2-way bank conflict under a smooth flow): twice the global load instructions cost more than the conflicts
+// (1.05-1.18 ms).
+constexpr int WS_THREADS_PER_CTA = 512, WS_ITEMS = 7;
+constexpr int WS_PP = 2;
 
 template <typename T> struct Item;
 template <> struct Item<float> {
@@ -327,11 +329,11 @@ __device__ __forceinline__ float taps_fetch(const T* plane, const Taps& t, int w
   return v;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(WsShape<T>::THREADS, 1) warp_fuse_staged_kernel(const WarpFuseArgs a, int n_units, int slice_pix) {
+template <typename T, int WS_THREADS, int ITEMS>
+__global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const WarpFuseArgs a, int n_units, int slice_pix) {
   extern __shared__ __align__(128) uint8_t ws_smem[];
   using namespace ptx;
-  constexpr int WS_THREADS = WsShape<T>::THREADS, ITEMS = WsShape<T>::ITEMS, PP = WsShape<T>::PP, WS_CONSUMERS = WS_THREADS - 32;   // warp 0 = producer
+  constexpr int PP = WS_PP, WS_CONSUMERS = WS_THREADS - 32;   // warp 0 = producer
   const int g = blockIdx.y;
   const int hw = a.h * a.w;
   const int L = a.clip_len;
@@ -603,6 +605,19 @@ int launch_motion_field(const float* flow, float* grid_out, int n, int h, int w,
   return CLASFV_OK;
 }
 
+template <typename T, int THREADS, int ITEMS>
+static cudaError_t launch_staged(const WarpFuseArgs& a, int units, size_t smem, cudaStream_t s) {
+  const int64_t hw = (int64_t)a.h * a.w;
+  const int per_cta = (THREADS - 32) * WS_PP * ITEMS;
+  const int slices = (int)cdiv(hw, per_cta);
+  int slice_pix = (int)cdiv(hw, slices);
+  slice_pix += slice_pix & 1;                           // even: pixel pairs
+  cudaError_t e = allow_max_dynamic_smem(warp_fuse_staged_kernel<T, THREADS, ITEMS>);
+  if (e != cudaSuccess) return e;
+  warp_fuse_staged_kernel<T, THREADS, ITEMS><<<dim3((unsigned)slices, (unsigned)a.t_out), THREADS, smem, s>>>(a, units, slice_pix);
+  return cudaSuccess;
+}
+
 int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
   if (a.area) CLASFV_CUDA(cudaMemsetAsync(a.area, 0, sizeof(int32_t) * a.t_out, s));
   // staged kernel: needs at least two ring units of two class planes in shared memory, an even width (pixel pairs)
@@ -617,20 +632,10 @@ int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
     const bool aligned = (hw * es) % 16 == 0 && a.w % 2 == 0 && ((uintptr_t)a.prob % 16) == 0 && ((uintptr_t)a.acc % 8) == 0 &&
                          (!a.mask || ((uintptr_t)a.mask % 2) == 0);
     if (units >= 2 && aligned && a.h >= 2 && !no_staged) {        // (w >= 2 follows from the even width)
-      const int per_cta = a.dtype == CLASFV_F32 ? (WsShape<float>::THREADS - 32) * WsShape<float>::PP * WsShape<float>::ITEMS
-                                                : (WsShape<__nv_bfloat16>::THREADS - 32) * WsShape<__nv_bfloat16>::PP * WsShape<__nv_bfloat16>::ITEMS;
-      const int slices = (int)cdiv(hw, per_cta);
-      int slice_pix = (int)cdiv(hw, slices);
-      slice_pix += slice_pix & 1;                           // even: pixel pairs
       const size_t smem = (size_t)units * unit + 16 * (size_t)units;
-      dim3 grid((unsigned)slices, (unsigned)a.t_out);
-      if (a.dtype == CLASFV_F32) {
-        CLASFV_CUDA(allow_max_dynamic_smem(warp_fuse_staged_kernel<float>));
-        warp_fuse_staged_kernel<float><<<grid, WsShape<float>::THREADS, smem, s>>>(a, units, slice_pix);
-      } else {
-        CLASFV_CUDA(allow_max_dynamic_smem(warp_fuse_staged_kernel<__nv_bfloat16>));
-        warp_fuse_staged_kernel<__nv_bfloat16><<<grid, WsShape<__nv_bfloat16>::THREADS, smem, s>>>(a, units, slice_pix);
-      }
+      const cudaError_t e = a.dtype == CLASFV_F32 ? launch_staged<float, WS_THREADS_PER_CTA, WS_ITEMS>(a, units, smem, s)
+                                                  : launch_staged<__nv_bfloat16, WS_THREADS_PER_CTA, WS_ITEMS>(a, units, smem, s);
+      CLASFV_CUDA(e);
       CLASFV_CUDA(cudaGetLastError());
       return CLASFV_OK;
     }
