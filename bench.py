@@ -109,8 +109,9 @@ def cpu_reference_sample(sample_clips, threads=None):
     import torch
     from clasfv_b200 import synthetic
     from oracle import fuse_ref, model_ref
-    if threads:
-        torch.set_num_threads(threads)
+    # every host core this process may run on - torchrun exports OMP_NUM_THREADS=1, which would otherwise leave the
+    # reference arm of an N>1 launch on a single thread
+    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
     sd = synthetic.random_state_dict(0)
     video = synthetic.synthetic_echo_video(CLIP + sample_clips - 1, H, W, seed=0)
     starts = list(range(sample_clips))
