@@ -49,7 +49,7 @@ KERNELS_PER_FORWARD = 42                           # stem + 40 convolutions + he
 
 def ncu_traffic():
     """DRAM bytes per bench step and kernel, from the committed ncu launch list of this workload
-    (profiles/r01_final_dram_traffic_per_step.json, written by tools/launch_list.sh + the aggregation in its header)."""
+    (profiles/r01_final_dram_traffic_per_step.json, written by tools/launch_list.sh + tools/launch_list_aggregate.py)."""
     try:
         with open(os.path.join(ROOT, "profiles", "r01_final_dram_traffic_per_step.json")) as f:
             return json.load(f)["per_kernel"]
