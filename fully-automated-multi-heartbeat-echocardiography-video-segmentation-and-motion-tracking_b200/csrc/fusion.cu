@@ -26,7 +26,19 @@ template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloa
 __device__ __forceinline__ float linspace_pm1(int idx, int steps) {
   if (steps <= 1) return -1.f;
   const float step = 2.f / (float)(steps - 1);
-  return idx < steps / 2 ? -1.f + step * (float)idx : 1.f - step * (float)(steps - idx - 1);
+  return idx < steps / 2 ? __fmaf_rn(step, (float)idx, -1.f) : __fmaf_rn(-step, (float)(steps - idx - 1), 1.f);
+}
+
+// Every kernel in this file evaluates the sampling arithmetic through the helpers below with explicit rounding intrinsics.
+// Left to the compiler, `a*b + c*d` may be contracted into fma(a, b, rn(c*d)) or fma(c, d, rn(a*b)) - it chose differently
+// in different kernels, which made the direct-gather and the staged warp-fuse kernels disagree in the last bit.
+// grid_sample's unnormalise for align_corners=False: ((g + 1) * size - 1) / 2
+__device__ __forceinline__ float unnormalize(float g, float size) {
+  return __fmul_rn(__fmaf_rn(__fadd_rn(g, 1.f), size, -1.f), 0.5f);
+}
+// nw*a + ne*b + sw*c + se*d, accumulated left to right, one rounding per step
+__device__ __forceinline__ float tap_sum(float a, float nw, float b, float ne, float c, float sw, float d, float se) {
+  return __fmaf_rn(d, se, __fmaf_rn(c, sw, __fmaf_rn(b, ne, __fmul_rn(a, nw))));
 }
 
 struct Bilinear {
@@ -39,18 +51,18 @@ struct Bilinear {
 // output pixel (i, j) displaced by the normalised flow (fx, fy).
 __device__ __forceinline__ Bilinear bilinear_setup(int i, int j, float fx, float fy, int h, int w) {
   const float gx = linspace_pm1(j, w) + fx, gy = linspace_pm1(i, h) + fy;
-  float ix = ((gx + 1.f) * (float)w - 1.f) * 0.5f;
-  float iy = ((gy + 1.f) * (float)h - 1.f) * 0.5f;
+  float ix = unnormalize(gx, (float)w);
+  float iy = unnormalize(gy, (float)h);
   ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
   iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
   const float fx0 = floorf(ix), fy0 = floorf(iy);
   Bilinear b;
   b.x0 = (int)fx0; b.y0 = (int)fy0;
   const float x1 = fx0 + 1.f, y1 = fy0 + 1.f;
-  b.nw = (x1 - ix) * (y1 - iy);
-  b.ne = (ix - fx0) * (y1 - iy);
-  b.sw = (x1 - ix) * (iy - fy0);
-  b.se = (ix - fx0) * (iy - fy0);
+  b.nw = __fmul_rn(x1 - ix, y1 - iy);
+  b.ne = __fmul_rn(ix - fx0, y1 - iy);
+  b.sw = __fmul_rn(x1 - ix, iy - fy0);
+  b.se = __fmul_rn(ix - fx0, iy - fy0);
   b.x1ok = b.x0 + 1 < w; b.y1ok = b.y0 + 1 < h;
   return b;
 }
@@ -58,18 +70,18 @@ __device__ __forceinline__ Bilinear bilinear_setup(int i, int j, float fx, float
 // same, with the base grid coordinates (linspace values of the pixel) already known
 __device__ __forceinline__ Bilinear bilinear_setup_base(float bx, float by, float fx, float fy, int h, int w) {
   const float gx = bx + fx, gy = by + fy;
-  float ix = ((gx + 1.f) * (float)w - 1.f) * 0.5f;
-  float iy = ((gy + 1.f) * (float)h - 1.f) * 0.5f;
+  float ix = unnormalize(gx, (float)w);
+  float iy = unnormalize(gy, (float)h);
   ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
   iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
   const float fx0 = floorf(ix), fy0 = floorf(iy);
   Bilinear b;
   b.x0 = (int)fx0; b.y0 = (int)fy0;
   const float x1 = fx0 + 1.f, y1 = fy0 + 1.f;
-  b.nw = (x1 - ix) * (y1 - iy);
-  b.ne = (ix - fx0) * (y1 - iy);
-  b.sw = (x1 - ix) * (iy - fy0);
-  b.se = (ix - fx0) * (iy - fy0);
+  b.nw = __fmul_rn(x1 - ix, y1 - iy);
+  b.ne = __fmul_rn(ix - fx0, y1 - iy);
+  b.sw = __fmul_rn(x1 - ix, iy - fy0);
+  b.se = __fmul_rn(ix - fx0, iy - fy0);
   b.x1ok = b.x0 + 1 < w; b.y1ok = b.y0 + 1 < h;
   return b;
 }
@@ -77,10 +89,10 @@ __device__ __forceinline__ Bilinear bilinear_setup_base(float bx, float by, floa
 template <typename T>
 __device__ __forceinline__ float bilinear_fetch(const T* __restrict__ plane, const Bilinear& b, int w) {
   const T* p = plane + (int64_t)b.y0 * w + b.x0;
-  float v = ldf<T>(p) * b.nw;
-  if (b.x1ok) v += ldf<T>(p + 1) * b.ne;
-  if (b.y1ok) v += ldf<T>(p + w) * b.sw;
-  if (b.x1ok && b.y1ok) v += ldf<T>(p + w + 1) * b.se;
+  float v = __fmul_rn(ldf<T>(p), b.nw);
+  if (b.x1ok) v = __fmaf_rn(ldf<T>(p + 1), b.ne, v);
+  if (b.y1ok) v = __fmaf_rn(ldf<T>(p + w), b.sw, v);
+  if (b.x1ok && b.y1ok) v = __fmaf_rn(ldf<T>(p + w + 1), b.se, v);
   return v;
 }
 
@@ -95,7 +107,7 @@ __global__ void warp_kernel(const float* __restrict__ src, const float* __restri
   if (nearest) {
     // grid_sample(mode="nearest", padding_mode="border", align_corners=False): clamp, then round half to even (nearbyint)
     const float gx = linspace_pm1(j, w) + fx, gy = linspace_pm1(i, h) + fy;
-    float ix = ((gx + 1.f) * (float)w - 1.f) * 0.5f, iy = ((gy + 1.f) * (float)h - 1.f) * 0.5f;
+    float ix = unnormalize(gx, (float)w), iy = unnormalize(gy, (float)h);
     ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
     iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
     const int xs = (int)rintf(ix), ys = (int)rintf(iy);
@@ -304,29 +316,25 @@ struct TapGeom {                      // loop invariants of taps_setup, converte
 };
 __device__ __forceinline__ Taps taps_setup(float bx, float by, float fx, float fy, const TapGeom& g) {
   const float gx = bx + fx, gy = by + fy;
-  float ix = ((gx + 1.f) * g.wf - 1.f) * 0.5f;
-  float iy = ((gy + 1.f) * g.hf - 1.f) * 0.5f;
+  float ix = unnormalize(gx, g.wf);
+  float iy = unnormalize(gy, g.hf);
   ix = fminf(g.wm1, fmaxf(ix, 0.f));
   iy = fminf(g.hm1, fmaxf(iy, 0.f));
   const float fx0 = fminf(floorf(ix), g.wm2), fy0 = fminf(floorf(iy), g.hm2);
   const float wx1 = ix - fx0, wy1 = iy - fy0;
   const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
   Taps t;
-  t.nw = wx0 * wy0;
-  t.ne = wx1 * wy0;
-  t.sw = wx0 * wy1;
-  t.se = wx1 * wy1;
+  t.nw = __fmul_rn(wx0, wy0);
+  t.ne = __fmul_rn(wx1, wy0);
+  t.sw = __fmul_rn(wx0, wy1);
+  t.se = __fmul_rn(wx1, wy1);
   t.p = (int)fmaf(fy0, g.wf, fx0);            // y0*W + x0: small integers, exact in fp32
   return t;
 }
 template <typename T>
 __device__ __forceinline__ float taps_fetch(const T* plane, const Taps& t, int w) {
   const T* p = plane + t.p;
-  float v = lds_val<T>(p) * t.nw;
-  v += lds_val<T>(p + 1) * t.ne;
-  v += lds_val<T>(p + w) * t.sw;
-  v += lds_val<T>(p + w + 1) * t.se;
-  return v;
+  return tap_sum(lds_val<T>(p), t.nw, lds_val<T>(p + 1), t.ne, lds_val<T>(p + w), t.sw, lds_val<T>(p + w + 1), t.se);
 }
 
 template <typename T, int WS_THREADS, int ITEMS>
