@@ -1,22 +1,47 @@
-import sys, os, subprocess, numpy as np
+#!/usr/bin/env python
+"""Staged vs direct-gather warp-fuse kernel, bit comparison in separate processes (the kernel choice is latched per process
+by CLASFV_WARP_FUSE_DIRECT).  Repeats every (dtype, edge_hops) case and also compares each kernel with ITSELF across
+processes, to tell a rounding difference between the kernels from run-to-run non-determinism of one of them.
+
+    python tools/wf_diag.py [repeats]
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
 src = open(os.path.join(ROOT, "tests", "test_gpu_parity.py")).read()
 body = src[src.index('_WF_SCRIPT = r"""') + len('_WF_SCRIPT = r"""'):]
-body = body[:body.index('"""')].format(root=ROOT)
-open("/tmp/wf.py", "w").write(body)
-for dtype, edge in (("bf16", "0"),):
-    out = {}
-    for name, env in (("staged", {}), ("direct", {"CLASFV_WARP_FUSE_DIRECT": "1"})):
-        e = dict(os.environ); e.update(env)
-        subprocess.run([sys.executable, "/tmp/wf.py", dtype, edge, f"/tmp/{name}.npz"], check=True, env=e)
-        out[name] = np.load(f"/tmp/{name}.npz")
-    a, b = out["staged"]["acc"], out["direct"]["acc"]
+open("/tmp/wf.py", "w").write(body[:body.index('"""')].format(root=ROOT))
+repeats = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+
+
+def run(name, dtype, edge, tag):
+    e = dict(os.environ)
+    e.pop("CLASFV_WARP_FUSE_DIRECT", None)
+    if name == "direct":
+        e["CLASFV_WARP_FUSE_DIRECT"] = "1"
+    path = f"/tmp/wf_{name}_{tag}.npz"
+    subprocess.run([sys.executable, "/tmp/wf.py", dtype, edge, path], check=True, env=e)
+    return np.load(path)["acc"]
+
+
+def diff(a, b):
     d = a.view(np.uint32) != b.view(np.uint32)
     idx = np.argwhere(d)
-    print(dtype, "edge", edge, "differing", int(d.sum()), "of", d.size, "max abs", float(np.abs(a - b).max()),
-          "cnt equal", bool(np.array_equal(out["staged"]["cnt"], out["direct"]["cnt"])), flush=True)
+    s = f"{int(d.sum())} of {d.size} differ, max abs {float(np.abs(a - b).max()):.3g}"
     if len(idx):
-        print(" frames", np.unique(idx[:, 0])[:20], "classes", np.unique(idx[:, 1]), "rows", np.unique(idx[:, 2])[:12], "cols", np.unique(idx[:, 3])[:12])
-        for f, c, y, x in idx[:6]:
-            print("  ", f, c, y, x, a[f, c, y, x], b[f, c, y, x])
+        s += f"; frames {np.unique(idx[:, 0])[:8]} rows {np.unique(idx[:, 2])[:8]} cols {np.unique(idx[:, 3])[:8]}"
+    return s
+
+
+for dtype, edge in (("bf16", "0"), ("bf16", "1"), ("fp32", "0"), ("fp32", "1")):
+    staged = [run("staged", dtype, edge, i) for i in range(repeats)]
+    direct = [run("direct", dtype, edge, i) for i in range(repeats)]
+    print(f"{dtype} edge_hops={edge}", flush=True)
+    print("  staged vs direct       :", diff(staged[0], direct[0]), flush=True)
+    for i in range(1, repeats):
+        print(f"  staged run 0 vs run {i}  :", diff(staged[0], staged[i]))
+        print(f"  direct run 0 vs run {i}  :", diff(direct[0], direct[i]), flush=True)
