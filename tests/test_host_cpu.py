@@ -150,3 +150,67 @@ def test_config4_lengths_and_video_assignment():
             assert seen == list(range(1277))
         loads = c4.rank_loads(lengths, world, "lpt")
         assert max(loads) / (sum(loads) / world) < 1.001
+
+
+def test_clamped_corner_taps_equal_grid_sample_conditional_taps_bit_for_bit():
+    """The staged warp-fuse kernel clamps the north-west bilinear corner to (H-2, W-2) and reads all four taps
+    unconditionally (csrc/fusion.cu taps_setup / tap_sum); grid_sample (and warp_fuse_kernel) floor the clamped coordinate and
+    skip out-of-range corners.  Emulated here in numpy with the kernels' operation order (fp32, one rounding per fma): the
+    two must give the same BITS for interior points, exact integers and every clamped border."""
+    import numpy as np
+    f32 = np.float32
+    rng = np.random.default_rng(0)
+    h, w, n = 48, 64, 300_000
+    ix = rng.uniform(-3, w + 2, n).astype(f32)
+    iy = rng.uniform(-3, h + 2, n).astype(f32)
+    ix[:2000] = rng.integers(0, w, 2000).astype(f32); iy[:2000] = rng.integers(0, h, 2000).astype(f32)
+    ix[2000:3000] = f32(w - 1); iy[3000:4000] = f32(h - 1)
+    ix[4000:4500] = np.nextafter(f32(w - 1), f32(0)); iy[4500:5000] = np.nextafter(f32(h - 1), f32(0))
+    ix = np.minimum(f32(w - 1), np.maximum(ix, f32(0))); iy = np.minimum(f32(h - 1), np.maximum(iy, f32(0)))
+    plane = rng.uniform(0, 1, (h, w)).astype(f32)
+
+    def fma(a, b, c):          # fp32 fma: the product of two fp32 numbers is exact in fp64
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
+
+    # grid_sample / warp_fuse_kernel: conditional taps (a skipped tap == the clamped neighbour with weight 0)
+    fx0, fy0 = np.floor(ix), np.floor(iy)
+    x0, y0 = fx0.astype(int), fy0.astype(int)
+    x1, y1 = fx0 + f32(1), fy0 + f32(1)
+    nw, ne, sw, se = (x1 - ix) * (y1 - iy), (ix - fx0) * (y1 - iy), (x1 - ix) * (iy - fy0), (ix - fx0) * (iy - fy0)
+    x1ok, y1ok = x0 + 1 < w, y0 + 1 < h
+    xs, ys = np.minimum(x0 + 1, w - 1), np.minimum(y0 + 1, h - 1)
+    v = plane[y0, x0] * nw
+    v = np.where(x1ok, fma(plane[y0, xs], ne, v), v)
+    v = np.where(y1ok, fma(plane[ys, x0], sw, v), v)
+    ref = np.where(x1ok & y1ok, fma(plane[ys, xs], se, v), v)
+
+    # staged kernel: clamped corner, 1 - (ix - x0) weights, unconditional taps
+    gx0, gy0 = np.minimum(np.floor(ix), f32(w - 2)), np.minimum(np.floor(iy), f32(h - 2))
+    wx1, wy1 = ix - gx0, iy - gy0
+    wx0, wy0 = f32(1) - wx1, f32(1) - wy1
+    X, Y = gx0.astype(int), gy0.astype(int)
+    v = plane[Y, X] * (wx0 * wy0)
+    v = fma(plane[Y, X + 1], wx1 * wy0, v)
+    v = fma(plane[Y + 1, X], wx0 * wy1, v)
+    new = fma(plane[Y + 1, X + 1], wx1 * wy1, v)
+    assert np.array_equal(ref.view(np.uint32), new.view(np.uint32))
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside the GPU arm): stdout must be the one JSON line of the
+    contract even when libraries print to file descriptor 1, with the keys the driver reads."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("configs[1]")
