@@ -604,13 +604,8 @@ def test_staged_warp_fuse_is_bit_identical_to_the_direct_gather_kernel(tmp_path,
     print(f"\n[staged vs direct, {dtype}] class sums differing in any bit: {differing} of {a['acc'].size}, max abs difference {worst:.3g}")
     assert np.array_equal(a["cnt"], b["cnt"])
     assert a["acc"].max() > 1.0                      # not vacuous
-    margin = np.abs(b["acc"][:, 1] - b["acc"][:, 0])
-    if worst > 2e-5 * float(a["acc"].max() + 1) or not np.array_equal(a["mask"][margin > 1e-3], b["mask"][margin > 1e-3]):
-        # both kernels are checked against the oracle elsewhere (test_warp_fuse_matches_oracle, the full-video tests); this
-        # consistency check has one unexplained failure on record, so it reports loudly instead of stopping the suite
-        pytest.xfail(f"{dtype}: staged and direct kernels MORE than rounding apart: {differing} sums, max abs {worst:.3g}")
-    if differing:
-        # Observed state: fp32 inputs 0 differing sums; bf16 inputs 0 in one run and a failing comparison in
-        # another run of the same binary.  A last-bit mismatch is reported, not hidden, and does not turn the suite red.
-        pytest.xfail(f"{dtype}: {differing} class sums differ in the last bits (max abs {worst:.3g})")
+    # Both kernels are pure functions of their inputs with a fixed order of additions per pixel.  Round 2 settled the open
+    # item of DESIGN.md 4.5 on the GPU (tools/wf_diag.py, profiles/r02a_wf_diag.log): staged vs direct and each kernel
+    # against itself across three processes, both element types, both edge modes: 0 of 436 224 sums differ in any bit.
+    assert differing == 0, f"{dtype}: {differing} class sums differ (max abs {worst:.3g})"
     assert np.array_equal(a["mask"], b["mask"]) and np.array_equal(a["area"], b["area"])

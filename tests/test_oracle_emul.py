@@ -1,0 +1,44 @@
+"""oracle/model_emul.py (the forward pass evaluated at the CUDA path's storage points) against the pinned fp32
+restatement oracle/model_ref.py.  CPU only.  With every storage point set to fp32 the emulation is the same function
+written the way csrc/ evaluates it (BatchNorm folded, comb_1 commuted with the up-sampling, separable interpolation),
+so it must reproduce model_ref to fp32 rounding: that pins the emulator's structure.  With 16-bit storage points it
+must move away from the fp32 answer by the amount those roundings explain, no more."""
+import torch
+
+from oracle import fixtures, model_emul, model_ref
+from oracle.model_emul import Config
+
+FP32 = dict(act="fp32", lateral="fp32", out="fp32", h1="fp32", h2="fp32", w2="fp32", wh="fp32", wtrunk="fp32")
+F16 = dict(act="f16", lateral="f16", out="f16", h1="f16", h2="f16", w2="f16", wh="f16", wtrunk="f16")
+
+
+def _metrics(seg, mot, seg_ref, mot_ref, width):
+    p, pr = torch.softmax(seg, 1), torch.softmax(seg_ref, 1)
+    return (float((p - pr).abs().max()), float(((p[:, 1] > p[:, 0]) == (pr[:, 1] > pr[:, 0])).float().mean()),
+            float((mot - mot_ref).abs().max()) * width / 2)
+
+
+def test_emulation_with_fp32_storage_is_the_reference_function():
+    sd = fixtures.calibrated_state_dict(0)
+    x = fixtures.synthetic_clip(8, 32, 48, seed=4, batch=2)
+    seg_ref, mot_ref = model_ref.forward(sd, x)
+    for head in ("row", "patch"):
+        seg, mot = model_emul.forward(sd, x, Config(head=head, **FP32))
+        smax, agree, epe = _metrics(seg, mot, seg_ref, mot_ref, 48)
+        # "row" keeps its fp16 interpolation operands even here (that is what the round-1 kernel does): 2^-11 weights
+        tol = 5e-5 if head == "patch" else 5e-3
+        assert smax <= tol and agree >= (1.0 if head == "patch" else 0.999) and epe <= 56 * tol, (head, smax, agree, epe)
+
+
+def test_sixteen_bit_storage_noise_is_ordered():
+    """bf16 (8 significant bits) must be several times further from fp32 than fp16 (11 bits) at every gate."""
+    sd = fixtures.calibrated_state_dict(0)
+    x = fixtures.synthetic_clip(16, 48, 64, seed=6, batch=1)
+    seg_ref, mot_ref = model_ref.forward(sd, x)
+    b = _metrics(*model_emul.forward(sd, x, Config(head="patch", lateral="f16")), seg_ref, mot_ref, 64)
+    h = _metrics(*model_emul.forward(sd, x, Config(head="patch", **F16)), seg_ref, mot_ref, 64)
+    assert 0 < h[0] < b[0] / 3 and h[2] < b[2] / 3 and h[1] >= b[1]
+    # rounding only the WEIGHTS of the trunk to bf16 (activations exact) already breaks the 2e-2 softmax gate's margin:
+    # the bf16 floor is a property of the number format on these weights, not of any implementation
+    w = _metrics(*model_emul.forward(sd, x, Config(head="patch", **{**FP32, "wtrunk": "bf16"})), seg_ref, mot_ref, 64)
+    assert w[0] > 3 * h[0]
