@@ -11,7 +11,7 @@ import os
 import subprocess
 import threading
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 OUT_LOGITS, OUT_PROB = 0, 1
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
@@ -113,7 +113,9 @@ def torch_dtype_code(dtype):
         return F32
     if dtype == torch.bfloat16:
         return BF16
-    raise ClasfvError(f"unsupported element type {dtype}; use torch.float32 or torch.bfloat16")
+    if dtype == torch.float16:
+        return F16
+    raise ClasfvError(f"unsupported element type {dtype}; use torch.float32, torch.bfloat16 or torch.float16")
 
 
 def current_stream_ptr(device):

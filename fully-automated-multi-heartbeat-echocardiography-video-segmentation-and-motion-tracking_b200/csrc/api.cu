@@ -103,7 +103,7 @@ struct clasfv_handle {
   Block blocks[4][2];
   PackedConv lateral[5];
   float *b1 = nullptr, *w2 = nullptr, *b2 = nullptr, *wh = nullptr, *bh = nullptr;
-  __nv_bfloat16* w2_bf16 = nullptr;
+  std::map<std::pair<int, int>, void*> head_tabs;   // interpolation matrices of the tensor-core head per (H, W)
   // workspace
   void* ws = nullptr; size_t ws_bytes = 0;
   uint32_t* minmax = nullptr;          // per-channel {min, max} bit patterns of clasfv_ingest_u8
@@ -181,6 +181,11 @@ int pack_weight(clasfv_handle* h, const float* w, int cout, int cin, int cin_off
         packed[((size_t)tap * cout_pad + co) * cin_pad + ci] = v;
       }
   if (dtype == CLASFV_F32) return dev_upload(h, packed.data(), n * sizeof(float), out);
+  if (dtype == CLASFV_F16) {
+    std::vector<__half> ph(n);
+    for (size_t i = 0; i < n; ++i) ph[i] = __float2half_rn(packed[i]);
+    return dev_upload(h, ph.data(), n * sizeof(__half), out);
+  }
   std::vector<__nv_bfloat16> pb(n);
   for (size_t i = 0; i < n; ++i) pb[i] = __float2bfloat16_rn(packed[i]);
   return dev_upload(h, pb.data(), n * sizeof(__nv_bfloat16), out);
@@ -234,7 +239,7 @@ ConvArgs make_conv(const PackedConv& pc, int n, int ti, int hi, int wi, const vo
 
 int run_conv(clasfv_handle* h, const ConvArgs& a, cudaStream_t stream) {
   if (h->profiling) h->prof_gflop[h->cur_stage] += 2e-9 * a.macs_per_pos * (double)a.s.n * a.s.to * a.s.ho * a.s.wo;
-  if (a.act_dtype == CLASFV_BF16 && !h->force_simt) return launch_conv_umma(a, h->num_sms, stream);
+  if (a.act_dtype != CLASFV_F32 && !h->force_simt) return launch_conv_umma(a, h->num_sms, stream);
   return launch_conv_simt(a, stream);
 }
 
@@ -342,33 +347,51 @@ struct Forward {
     {
       ConvArgs c = make_conv(h->lateral[0], nb, T[0], H[0], W[0], ws + o_f[0], ws + o_g[0], nullptr, 0, act, tc_head ? 0 : 1);
       c.in2 = ws + o_f[1];
+      c.out_f16 = tc_head ? 1 : 0;               // the tensor-core head reads fp16 lateral maps whatever the trunk's type
       c.macs_per_pos *= 2;
       if ((rc = run_conv(h, c, stream))) return rc;
     }
-    for (int i = 2; i < 5; ++i)
-      if ((rc = run_conv(h, make_conv(h->lateral[i], nb, T[i], H[i], W[i], ws + o_f[i], ws + o_g[i - 1], nullptr, 0, act, tc_head ? 0 : 1), stream))) return rc;
+    for (int i = 2; i < 5; ++i) {
+      ConvArgs c = make_conv(h->lateral[i], nb, T[i], H[i], W[i], ws + o_f[i], ws + o_g[i - 1], nullptr, 0, act, tc_head ? 0 : 1);
+      c.out_f16 = tc_head ? 1 : 0;
+      if ((rc = run_conv(h, c, stream))) return rc;
+    }
     if ((rc = mark(2))) return rc;
     HeadArgs ha;
     for (int i = 0; i < 4; ++i) { ha.g[i] = ws + o_g[i]; ha.tl[i] = T[i + 1]; ha.hl[i] = H[i + 1]; ha.wl[i] = W[i + 1]; }
     if (tc_head)
       for (int i = 1; i < 4; ++i) {
-        if ((rc = launch_temporal_upsample_bf16(ws + o_g[i], ws + o_gt[i], nb, T[i + 1], t, H[i + 1], W[i + 1], stream))) return rc;
+        if ((rc = launch_temporal_upsample_f16(ws + o_g[i], ws + o_gt[i], nb, T[i + 1], t, H[i + 1], W[i + 1], stream))) return rc;
         ha.g[i] = ws + o_gt[i]; ha.tl[i] = t;
       }
-    ha.g_dtype = tc_head ? CLASFV_BF16 : CLASFV_F32;
+    ha.g_dtype = tc_head ? CLASFV_F16 : CLASFV_F32;
     ha.n = nb; ha.t = t; ha.h = height; ha.w = width;
-    ha.b1 = h->b1; ha.w2 = h->w2; ha.w2_bf16 = h->w2_bf16; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;
+    ha.b1 = h->b1; ha.w2 = h->w2; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;
+    ha.a_tab = nullptr; ha.tail_f16 = act == CLASFV_F16 ? 1 : 0;
+    if (tc_head) {
+      // interpolation matrices of this frame geometry: built on first use, kept by the handle
+      auto it = h->head_tabs.find({height, width});
+      if (it == h->head_tabs.end()) {
+        const size_t bytes = head_table_bytes(ha);
+        CLASFV_REQUIRE(bytes > 0, "clasfv_forward: the tensor-core head does not tile a %d x %d frame", height, width);
+        void* tab = nullptr;
+        CLASFV_CUDA(cudaMalloc(&tab, bytes));
+        if ((rc = launch_head_table(ha, tab, stream))) { cudaFree(tab); return rc; }
+        it = h->head_tabs.emplace(std::make_pair(height, width), tab).first;
+      }
+      ha.a_tab = it->second;
+    }
     const size_t oes = out_dtype == CLASFV_F32 ? 4 : 2;
     const size_t plane = (size_t)t * height * width * oes;
     ha.seg = seg + (size_t)c0 * 2 * plane; ha.motion = motion + (size_t)c0 * 4 * plane;
     ha.out_dtype = out_dtype; ha.out_kind = out_kind;
-    if ((rc = tc_head ? launch_head_umma(ha, stream) : launch_head(ha, stream))) return rc;
+    if ((rc = tc_head ? launch_head_umma(ha, h->num_sms, stream) : launch_head(ha, stream))) return rc;
     return mark(3);
   }
 
   int run() {
     act = h->precision; es = act == CLASFV_F32 ? 4 : 2;
-    tc_head = act == CLASFV_BF16 && !h->force_simt;     // tensor-core head reads bf16 lateral maps
+    tc_head = act != CLASFV_F32 && !h->force_simt;      // tensor-core head (reads fp16 lateral maps)
     gs = tc_head ? 2 : 4;
     const int Tn[5] = {t, t, t / 2, t / 4, t / 8};
     const int Hn[5] = {height / 2, height / 2, height / 4, height / 8, height / 16};
@@ -570,6 +593,7 @@ void clasfv_destroy(clasfv_handle* h) {
   free_packed(h);
   if (h->ws) cudaFree(h->ws);
   if (h->minmax) cudaFree(h->minmax);
+  for (auto& kv : h->head_tabs) cudaFree(kv.second);
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
   h->ring.destroy();
   delete h;
@@ -590,7 +614,7 @@ int clasfv_set_tensor(clasfv_handle* h, const char* key, const float* data_host,
 
 int clasfv_finalize(clasfv_handle* h, int precision) {
   CLASFV_REQUIRE(h, "clasfv_finalize: handle is NULL");
-  CLASFV_REQUIRE(precision == CLASFV_F32 || precision == CLASFV_BF16, "clasfv_finalize: unknown precision %d", precision);
+  CLASFV_REQUIRE(precision == CLASFV_F32 || precision == CLASFV_BF16 || precision == CLASFV_F16, "clasfv_finalize: unknown precision %d", precision);
   DeviceGuard guard(h->device);
   CLASFV_CUDA(cudaDeviceSynchronize());
   free_packed(h);
@@ -660,6 +684,10 @@ int clasfv_finalize(clasfv_handle* h, int precision) {
             for (int ci = 0; ci < 64; ++ci) two[((size_t)src * DEC + co) * 64 + ci] = w1->data[(size_t)co * 1024 + src * 64 + ci] * s1[co];
         if (h->precision == CLASFV_F32) {
           if ((rc = dev_upload(h, two.data(), two.size() * 4, &pc.w))) return rc;
+        } else if (h->precision == CLASFV_F16) {
+          std::vector<__half> th(two.size());
+          for (size_t k = 0; k < two.size(); ++k) th[k] = __float2half_rn(two[k]);
+          if ((rc = dev_upload(h, th.data(), th.size() * 2, &pc.w))) return rc;
         } else {
           std::vector<__nv_bfloat16> tb(two.size());
           for (size_t k = 0; k < two.size(); ++k) tb[k] = __float2bfloat16_rn(two[k]);
@@ -684,11 +712,6 @@ int clasfv_finalize(clasfv_handle* h, int precision) {
     for (int q = 0; q < 4; ++q) bh[2 + q] = bm->data[q];
     if ((rc = dev_upload(h, b1.data(), b1.size() * 4, reinterpret_cast<void**>(&h->b1)))) return rc;
     if ((rc = dev_upload(h, w2p.data(), w2p.size() * 4, reinterpret_cast<void**>(&h->w2)))) return rc;
-    {
-      std::vector<__nv_bfloat16> wb(w2p.size());
-      for (size_t k = 0; k < w2p.size(); ++k) wb[k] = __float2bfloat16_rn(w2p[k]);
-      if ((rc = dev_upload(h, wb.data(), wb.size() * 2, reinterpret_cast<void**>(&h->w2_bf16)))) return rc;
-    }
     if ((rc = dev_upload(h, b2.data(), b2.size() * 4, reinterpret_cast<void**>(&h->b2)))) return rc;
     if ((rc = dev_upload(h, wh.data(), wh.size() * 4, reinterpret_cast<void**>(&h->wh)))) return rc;
     if ((rc = dev_upload(h, bh.data(), bh.size() * 4, reinterpret_cast<void**>(&h->bh)))) return rc;
@@ -708,7 +731,7 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
   CLASFV_REQUIRE(n >= 1 && t >= 8 && t % 8 == 0 && height >= 16 && height % 16 == 0 && width >= 16 && width % 16 == 0,
                  "clasfv_forward: need N >= 1, T %% 8 == 0, H %% 16 == 0, W %% 16 == 0 (got N=%d T=%d H=%d W=%d)", n, t, height, width);
   CLASFV_REQUIRE(out_kind == CLASFV_OUT_LOGITS || out_kind == CLASFV_OUT_PROB, "clasfv_forward: bad out_kind");
-  CLASFV_REQUIRE(out_dtype == CLASFV_F32 || out_dtype == CLASFV_BF16, "clasfv_forward: bad out_dtype");
+  CLASFV_REQUIRE(out_dtype == CLASFV_F32 || out_dtype == CLASFV_BF16 || out_dtype == CLASFV_F16, "clasfv_forward: bad out_dtype");
   DeviceGuard guard(h->device);
   Forward f;
   f.h = h; f.stream = static_cast<cudaStream_t>(stream_v);
@@ -804,7 +827,7 @@ int clasfv_warp_fuse(clasfv_handle* h, const void* prob_dev, const void* motion_
                      int edge_hops, int accumulate, float* acc_dev, int32_t* cnt_dev, uint8_t* mask_dev,
                      int32_t* area_dev, void* stream_v) {
   CLASFV_REQUIRE(h && prob_dev && motion_dev && clip_start_host && acc_dev, "clasfv_warp_fuse: null argument");
-  CLASFV_REQUIRE(dtype == CLASFV_F32 || dtype == CLASFV_BF16, "clasfv_warp_fuse: bad dtype");
+  CLASFV_REQUIRE(dtype == CLASFV_F32 || dtype == CLASFV_BF16 || dtype == CLASFV_F16, "clasfv_warp_fuse: bad dtype");
   CLASFV_REQUIRE(n_clips >= 1 && clip_len >= 1 && t_out >= 1 && height >= 1 && width >= 1, "clasfv_warp_fuse: bad extent");
   for (int c = 1; c < n_clips; ++c) CLASFV_REQUIRE(clip_start_host[c] >= clip_start_host[c - 1], "clasfv_warp_fuse: clip starts must ascend");
   DeviceGuard guard(h->device);
@@ -882,7 +905,7 @@ int clasfv_fuse_shift_votes(clasfv_handle* h, const void* prob_dev, int dtype, i
                             const int32_t* shift_nclips_host, const int32_t* shift_clip_base_host,
                             uint8_t* mask_dev, int32_t* area_dev, void* stream_v) {
   CLASFV_REQUIRE(h && prob_dev && mask_dev && shift_len_host && shift_nclips_host && shift_clip_base_host, "clasfv_fuse_shift_votes: null argument");
-  CLASFV_REQUIRE(dtype == CLASFV_F32 || dtype == CLASFV_BF16, "clasfv_fuse_shift_votes: bad dtype");
+  CLASFV_REQUIRE(dtype == CLASFV_F32 || dtype == CLASFV_BF16 || dtype == CLASFV_F16, "clasfv_fuse_shift_votes: bad dtype");
   CLASFV_REQUIRE(n_shifts >= 1 && step >= 1 && clip_len >= 1 && t >= 1, "clasfv_fuse_shift_votes: bad extent");
   CLASFV_REQUIRE(shift_nclips_host[0] >= 1, "clasfv_fuse_shift_votes: shift 0 has no clip (the reference raises IndexError)");
   DeviceGuard guard(h->device);
@@ -910,9 +933,10 @@ int clasfv_conv3d(clasfv_handle* h, const void* x_dev, int dtype, int n, int t, 
                   int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
                   const void* residual_dev, int relu, int engine, int out_f32, void* out_dev, void* stream_v) {
   CLASFV_REQUIRE(h && x_dev && w_host && out_dev, "clasfv_conv3d: null argument");
-  CLASFV_REQUIRE(dtype == CLASFV_F32 || dtype == CLASFV_BF16, "clasfv_conv3d: bad dtype");
+  CLASFV_REQUIRE(dtype == CLASFV_F32 || dtype == CLASFV_BF16 || dtype == CLASFV_F16, "clasfv_conv3d: bad dtype");
   CLASFV_REQUIRE(cin % 16 == 0 && cout % 16 == 0, "clasfv_conv3d: channel counts must be multiples of 16");
-  CLASFV_REQUIRE(engine == 0 || (engine == 1 && dtype == CLASFV_BF16), "clasfv_conv3d: the tcgen05 engine needs bf16");
+  CLASFV_REQUIRE((engine == 0 && dtype != CLASFV_F16) || (engine == 1 && dtype != CLASFV_F32),
+                 "clasfv_conv3d: the tcgen05 engine needs bf16 or fp16, the CUDA-core engine fp32 or bf16");
   DeviceGuard guard(h->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int taps = kt * kh * kw;
@@ -927,6 +951,11 @@ int clasfv_conv3d(clasfv_handle* h, const void* x_dev, int dtype, int n, int t, 
   if (dtype == CLASFV_F32) {
     CLASFV_CUDA(cudaMalloc(&w_dev, nw * 4));
     CLASFV_CUDA(cudaMemcpy(w_dev, packed.data(), nw * 4, cudaMemcpyHostToDevice));
+  } else if (dtype == CLASFV_F16) {
+    std::vector<__half> ph(nw);
+    for (size_t i = 0; i < nw; ++i) ph[i] = __float2half_rn(packed[i]);
+    CLASFV_CUDA(cudaMalloc(&w_dev, nw * 2));
+    CLASFV_CUDA(cudaMemcpy(w_dev, ph.data(), nw * 2, cudaMemcpyHostToDevice));
   } else {
     std::vector<__nv_bfloat16> pb(nw);
     for (size_t i = 0; i < nw; ++i) pb[i] = __float2bfloat16_rn(packed[i]);

@@ -10,6 +10,7 @@
 //    dimension, so the stem reads the planar fp32 clip directly (no layout pass) and emits
 //    channels-last activations for everything downstream.
 #include "internal.h"
+#include "umma_ptx.cuh"
 
 #include <algorithm>
 
@@ -51,6 +52,11 @@ template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bflo
 template <typename T> __device__ __forceinline__ void store4(T* p, const float (&v)[4]);
 template <> __device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* p, const float (&v)[4]) {
+  uint2 w;
+  w.x = ptx::cvt_f16x2_sat(v[0], v[1]); w.y = ptx::cvt_f16x2_sat(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = w;
 }
 template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
@@ -293,6 +299,7 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t stream) {
   const ConvShape& s = a.s;
   CLASFV_REQUIRE(s.cin % BK == 0 && s.cout % 4 == 0, "conv_simt: cin %% 16 and cout %% 4 required (cin=%d cout=%d)", s.cin, s.cout);
   CLASFV_REQUIRE(!a.seg.on && !a.res.on && !a.out_batch_stride, "conv_simt: ragged clip geometry (dense-video trunk) is a tcgen05-path feature");
+  CLASFV_REQUIRE(a.act_dtype != CLASFV_F16 && !a.out_f16, "conv_simt: fp16 storage is a tcgen05-path feature");
   SimtParams p;
   p.s = s; p.in = a.in; p.in2 = a.in2; p.weight = a.weight; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.relu = a.relu;
   CLASFV_REQUIRE(!a.in2 || (s.kt * s.kh * s.kw == 1 && s.st == 1 && s.sh == 1 && s.sw == 1), "conv_simt: two-source mode is 1x1x1 only");
@@ -318,6 +325,7 @@ int launch_stem(const StemArgs& a, cudaStream_t stream) {
   CLASFV_REQUIRE(a.out_channels >= STEM_CO && a.out_channels % 4 == 0, "stem: bad output channel count %d", a.out_channels);
   dim3 grid((unsigned)cdiv(a.w / 2, STEM_TW), (unsigned)cdiv(a.h / 2, STEM_TH), (unsigned)(a.n * a.t));
   if (a.out_dtype == CLASFV_F32) stem_conv_kernel<float><<<grid, STEM_TH * STEM_TW, 0, stream>>>(a);
+  else if (a.out_dtype == CLASFV_F16) stem_conv_kernel<__half><<<grid, STEM_TH * STEM_TW, 0, stream>>>(a);
   else stem_conv_kernel<__nv_bfloat16><<<grid, STEM_TH * STEM_TW, 0, stream>>>(a);
   CLASFV_CUDA(cudaGetLastError());
   return CLASFV_OK;

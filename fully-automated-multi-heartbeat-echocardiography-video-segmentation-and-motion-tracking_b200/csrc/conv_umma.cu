@@ -67,7 +67,7 @@ struct UmmaParams {
   int nstages, a_slab_bytes, a_tx_bytes, b_slab_bytes, b_stage_slabs, resident, tmem_cols, bias_bytes;
   uint32_t idesc;
   const float* bias; const void* residual; void* out;
-  int relu, out_f32;
+  int relu, out_type;                        // out_type: CLASFV_F32 | CLASFV_BF16 | CLASFV_F16 (out and residual)
   // frame-wise A loads (time-segmented temporal convolution): the (bt+2)-frame slab is filled by one single-frame
   // box load per frame, frame v of the virtual clip coming from map 0 (v < fw_split) or map 1
   int framewise, fw_split, fw_a_toff, fw_b_toff, frame_bytes;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
       uint4 res_bf[2]; float4 res_f[4];
       auto fetch_res = [&](int cc) {
         if (!has_res) return;
-        if (p.out_f32) {
+        if (p.out_type == CLASFV_F32) {
           const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(res_base) + roff + cc);
 #pragma unroll
           for (int i = 0; i < 4; ++i) res_f[i] = __ldg(rp + i);
@@ -304,9 +304,16 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
         }
         if (cc + 32 < ncols) tc_ld16(taddr + (uint32_t)(cc + 32), acc);      // next chunk's accumulators in flight
         if (has_res) {
-          if (p.out_f32) {
+          if (p.out_type == CLASFV_F32) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) { v[4 * i] += res_f[i].x; v[4 * i + 1] += res_f[i].y; v[4 * i + 2] += res_f[i].z; v[4 * i + 3] += res_f[i].w; }
+          } else if (p.out_type == CLASFV_F16) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const __half2* hh = reinterpret_cast<const __half2*>(&res_bf[i]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(hh[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -322,10 +329,20 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (valid) {
-          if (p.out_f32) {
+          if (p.out_type == CLASFV_F32) {
             float* o = static_cast<float*>(p.out) + off + cc;
 #pragma unroll
             for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else if (p.out_type == CLASFV_F16) {
+            // saturating conversion: a value beyond +-65504 stores the largest finite fp16, never an infinity
+            __half* o = static_cast<__half*>(p.out) + off + cc;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint4 w4;
+              w4.x = cvt_f16x2_sat(v[8 * i + 0], v[8 * i + 1]); w4.y = cvt_f16x2_sat(v[8 * i + 2], v[8 * i + 3]);
+              w4.z = cvt_f16x2_sat(v[8 * i + 4], v[8 * i + 5]); w4.w = cvt_f16x2_sat(v[8 * i + 6], v[8 * i + 7]);
+              reinterpret_cast<uint4*>(o)[i] = w4;
+            }
           } else {
             __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + off + cc;
 #pragma unroll
@@ -372,13 +389,13 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool fp16) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return CLASFV_ECUDA; }
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu,%llu box %u,%u,%u)", (int)r, rank,
@@ -396,11 +413,16 @@ inline void split_offset(int off, int stride, int* q, int* r) {
 }
 
 enum ShareMode { SHARE_NONE = 0, SHARE_T = 1, SHARE_H = 2 };
-bool g_unaligned_taps = true;       // tap starts inside a swizzle atom are fine (CLASFV_UMMA_ALIGNED_TAPS=1 restores whole-atom shifts)
+// Tap starts inside a swizzle atom are fine (CLASFV_UMMA_ALIGNED_TAPS=1 restores whole-atom shifts); read once per process.
+bool unaligned_taps_allowed() {
+  static const bool allowed = getenv("CLASFV_UMMA_ALIGNED_TAPS") == nullptr;
+  return allowed;
+}
 
 // Choose the (bw,bh,bt,bb) box of <= 128 output positions that wastes the fewest MMA rows, under the
 // layout constraints of the sharing mode (see UmmaParams).  Returns false if no box satisfies them.
-bool choose_box(int wo, int ho, int to, int n, ShareMode mode, int* bw, int* bh, int* bt, int* bb, double* eff_out = nullptr, int force_t = 0) {
+bool choose_box(int wo, int ho, int to, int n, ShareMode mode, bool unaligned_taps, int* bw, int* bh, int* bt, int* bb, double* eff_out = nullptr,
+                int force_t = 0) {
   double best = -1.0; int best_rows = 0, best_halo = 1 << 30; bool found = false;
   for (int w = 1; w <= wo && w <= TILE_M; ++w)
     for (int h = 1; h <= ho && w * h <= TILE_M; ++h)
@@ -412,11 +434,11 @@ bool choose_box(int wo, int ho, int to, int n, ShareMode mode, int* bw, int* bh,
         int halo_rows = 0;
         if (mode == SHARE_T) {                   // frames are the outermost axis of the box; a frame is whole swizzle atoms
           b = 1;
-          if ((w * h) % 8 != 0 && !g_unaligned_taps) continue;
+          if ((w * h) % 8 != 0 && !unaligned_taps) continue;
           halo_rows = 2 * w * h;
         } else if (mode == SHARE_H) {            // rows are the outermost axis; a row is whole swizzle atoms
           b = 1;
-          if (t != 1 || (w % 8 != 0 && !g_unaligned_taps)) continue;
+          if (t != 1 || (w % 8 != 0 && !unaligned_taps)) continue;
           halo_rows = 2 * w;
         }
         const int64_t tiles = cdiv(wo, w) * cdiv(ho, h) * cdiv(to, t) * cdiv(n, b);
@@ -436,9 +458,14 @@ bool choose_box(int wo, int ho, int to, int n, ShareMode mode, int* bw, int* bh,
 
 int umma_selftest_supported() { return get_encode_fn() != nullptr; }
 
+int encode_tmap_16bit(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool fp16) {
+  return encode_map(map, base, rank, dims, strides_bytes, box, fp16);
+}
+
 int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   const ConvShape& s = a.s;
-  CLASFV_REQUIRE(a.act_dtype == CLASFV_BF16, "conv_umma: bf16 activations only");
+  CLASFV_REQUIRE(a.act_dtype == CLASFV_BF16 || a.act_dtype == CLASFV_F16, "conv_umma: 16-bit activations only");
+  const bool fp16 = a.act_dtype == CLASFV_F16;
   CLASFV_REQUIRE(s.cin % 16 == 0 && s.cout % 16 == 0, "conv_umma: channel counts must be multiples of 16 (cin=%d cout=%d)", s.cin, s.cout);
   const int sp_taps = s.kt * s.kh * s.kw;
   const int ntaps = sp_taps * (a.in2 ? 2 : 1);
@@ -468,8 +495,8 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   const bool unit_stride = s.st == 1 && s.sh == 1 && s.sw == 1 && !a.in2;
   ShareMode want = SHARE_NONE;
   if (unit_stride && s.kt == 3 && s.kh == 1 && s.kw == 1 && s.pt == 1) want = SHARE_T;
-  g_unaligned_taps = getenv("CLASFV_UMMA_ALIGNED_TAPS") == nullptr;
-  if (unit_stride && s.kt == 1 && s.kh == 3 && s.kw == 3 && s.ph == 1 && s.pw == 1 && (s.wo % 8 == 0 || g_unaligned_taps)) want = SHARE_H;
+  const bool unaligned_taps = unaligned_taps_allowed();
+  if (unit_stride && s.kt == 1 && s.kh == 3 && s.kw == 3 && s.ph == 1 && s.pw == 1 && (s.wo % 8 == 0 || unaligned_taps)) want = SHARE_H;
   static const bool no_share = getenv("CLASFV_UMMA_NO_SHARE") != nullptr;
   if (no_share) want = SHARE_NONE;
   p.bias_bytes = round_up(s.cout * 4, 128);
@@ -478,11 +505,11 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   // sharing cuts the A traffic of the tap group 3x but constrains the box: keep it only while the MMA rows it fills stay
   // within 80 % of what the unconstrained tiling fills (a time-segmented input has no unshared form)
   double eff_none = 0.0;
-  { int w_, h_, t_, b_; choose_box(s.wo, s.ho, s.to, s.n, SHARE_NONE, &w_, &h_, &t_, &b_, &eff_none); }
+  { int w_, h_, t_, b_; choose_box(s.wo, s.ho, s.to, s.n, SHARE_NONE, unaligned_taps, &w_, &h_, &t_, &b_, &eff_none); }
   for (int attempt = 0; attempt < 2; ++attempt) {
     mode = attempt == 0 ? want : SHARE_NONE;
     double eff = 0.0;
-    if (!choose_box(s.wo, s.ho, s.to, s.n, mode, &p.bw, &p.bh, &p.bt, &p.bb, &eff, a.seg.on ? s.to : 0)) continue;
+    if (!choose_box(s.wo, s.ho, s.to, s.n, mode, unaligned_taps, &p.bw, &p.bh, &p.bt, &p.bb, &eff, a.seg.on ? s.to : 0)) continue;
     if (mode != SHARE_NONE && !a.seg.on && eff < 0.8 * eff_none) continue;
     const int rows_out = p.bw * p.bh * p.bt * p.bb;
     int slab_rows = rows_out, taps_per_group = 1;
@@ -582,7 +609,7 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
       const uint64_t dims[5] = {(uint64_t)s.cin, (uint64_t)s.wi, (uint64_t)s.hi, (uint64_t)tt, (uint64_t)s.n};
       const uint64_t strides[4] = {(uint64_t)s.cin * e, (uint64_t)s.wi * s.cin * e, frame * e, bstride * e};
       const uint32_t boxf[5] = {(uint32_t)SLAB_K, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)(is_b ? nb : na), 1u};
-      int rc = encode_map(&p.tmap_a[v], const_cast<void*>(is_b ? a.seg.b : a.in), 5, dims, strides, boxf);
+      int rc = encode_map(&p.tmap_a[v], const_cast<void*>(is_b ? a.seg.b : a.in), 5, dims, strides, boxf, fp16);
       if (rc) return rc;
     }
   }
@@ -596,21 +623,22 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
     const uint64_t strides[4] = {(uint64_t)s.sw * s.cin * e, (uint64_t)s.sh * s.wi * s.cin * e,
                                  (uint64_t)s.st * s.hi * s.wi * s.cin * e, batch_stride * e};
     char* basep = (char*)(view_src[vv] ? a.in2 : a.in) + (((int64_t)rt * s.hi + rh) * s.wi + rw) * s.cin * (int64_t)e;
-    int rc = encode_map(&p.tmap_a[v], basep, 5, dims, strides, boxa);
+    int rc = encode_map(&p.tmap_a[v], basep, 5, dims, strides, boxa, fp16);
     if (rc) return rc;
   }
   {
     const uint64_t dims[3] = {(uint64_t)s.cin, (uint64_t)s.cout, (uint64_t)ntaps};
     const uint64_t strides[2] = {(uint64_t)s.cin * 2, (uint64_t)s.cout * s.cin * 2};
     const uint32_t box[3] = {(uint32_t)SLAB_K, (uint32_t)bn, 1};
-    int rc = encode_map(&p.tmap_b, const_cast<void*>(a.weight), 3, dims, strides, box);
+    int rc = encode_map(&p.tmap_b, const_cast<void*>(a.weight), 3, dims, strides, box, fp16);
     if (rc) return rc;
   }
   int cols = 32;
   while (cols < 2 * bn) cols *= 2;
   p.tmem_cols = cols;
-  p.idesc = idesc_bf16_f32(TILE_M, bn);
-  p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.relu = a.relu; p.out_f32 = a.out_f32;
+  p.idesc = idesc_16bit_f32(TILE_M, bn, fp16);
+  p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.relu = a.relu;
+  p.out_type = a.out_f32 ? CLASFV_F32 : a.out_f16 ? CLASFV_F16 : a.act_dtype;
   const int64_t out_frame = (int64_t)s.ho * s.wo * s.cout;
   p.out_bstride = a.out_batch_stride ? a.out_batch_stride : out_frame * s.to;
   if (a.res.on) {

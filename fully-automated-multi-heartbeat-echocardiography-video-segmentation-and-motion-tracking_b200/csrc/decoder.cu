@@ -36,6 +36,7 @@ __device__ __forceinline__ AxisTap axis_tap(int dst, int in_size, int out_size) 
 template <typename OutT> __device__ __forceinline__ void put(OutT* p, float v);
 template <> __device__ __forceinline__ void put<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void put<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void put<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 
 template <typename OutT>
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a, int rowbuf_floats) {
@@ -151,6 +152,9 @@ int launch_head(const HeadArgs& a, cudaStream_t stream) {
   if (a.out_dtype == CLASFV_F32) {
     CLASFV_CUDA(allow_max_dynamic_smem(head_kernel<float>));
     head_kernel<float><<<grid, HEAD_THREADS, smem, stream>>>(a, rowbuf);
+  } else if (a.out_dtype == CLASFV_F16) {
+    CLASFV_CUDA(allow_max_dynamic_smem(head_kernel<__half>));
+    head_kernel<__half><<<grid, HEAD_THREADS, smem, stream>>>(a, rowbuf);
   } else {
     CLASFV_CUDA(allow_max_dynamic_smem(head_kernel<__nv_bfloat16>));
     head_kernel<__nv_bfloat16><<<grid, HEAD_THREADS, smem, stream>>>(a, rowbuf);

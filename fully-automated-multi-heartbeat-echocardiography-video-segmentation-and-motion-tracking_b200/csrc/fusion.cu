@@ -21,6 +21,7 @@ template <> __device__ __forceinline__ float ldf<float>(const float* p) { return
 template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __bfloat162float(__ldg(p));
 }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(__ldg(p)); }
 
 // torch.linspace(-1, 1, steps)[idx] in fp32 (symmetric evaluation, as ATen does)
 __device__ __forceinline__ float linspace_pm1(int idx, int steps) {
@@ -295,7 +296,21 @@ template <> struct Item<__nv_bfloat16> {
     *reinterpret_cast<uchar2*>(p) = make_uchar2((unsigned char)m[0], (unsigned char)m[1]);
   }
 };
+template <> struct Item<__half> {
+  static __device__ __forceinline__ void ld(const __half* p, float (&v)[2]) {
+    const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(p));
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r)); v[0] = f.x; v[1] = f.y;
+  }
+  static __device__ __forceinline__ void ld_acc(const float* p, float (&v)[2]) {
+    const float2 o = *reinterpret_cast<const float2*>(p); v[0] = o.x; v[1] = o.y;
+  }
+  static __device__ __forceinline__ void st_acc(float* p, const float (&v)[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+  static __device__ __forceinline__ void st_mask(uint8_t* p, const int (&m)[2]) {
+    *reinterpret_cast<uchar2*>(p) = make_uchar2((unsigned char)m[0], (unsigned char)m[1]);
+  }
+};
 template <typename T> __device__ __forceinline__ float lds_val(const T* p);
+template <> __device__ __forceinline__ float lds_val<__half>(const __half* p) { return __half2float(*p); }
 template <> __device__ __forceinline__ float lds_val<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float lds_val<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(p)) << 16);
@@ -641,8 +656,9 @@ int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
                          (!a.mask || ((uintptr_t)a.mask % 2) == 0);
     if (units >= 2 && aligned && a.h >= 2 && !no_staged) {        // (w >= 2 follows from the even width)
       const size_t smem = (size_t)units * unit + 16 * (size_t)units;
-      const cudaError_t e = a.dtype == CLASFV_F32 ? launch_staged<float, WS_THREADS_PER_CTA, WS_ITEMS>(a, units, smem, s)
-                                                  : launch_staged<__nv_bfloat16, WS_THREADS_PER_CTA, WS_ITEMS>(a, units, smem, s);
+      const cudaError_t e = a.dtype == CLASFV_F32   ? launch_staged<float, WS_THREADS_PER_CTA, WS_ITEMS>(a, units, smem, s)
+                            : a.dtype == CLASFV_F16 ? launch_staged<__half, WS_THREADS_PER_CTA, WS_ITEMS>(a, units, smem, s)
+                                                    : launch_staged<__nv_bfloat16, WS_THREADS_PER_CTA, WS_ITEMS>(a, units, smem, s);
       CLASFV_CUDA(e);
       CLASFV_CUDA(cudaGetLastError());
       return CLASFV_OK;
@@ -650,6 +666,7 @@ int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
   }
   dim3 grid((unsigned)cdiv((int64_t)a.h * a.w, WF_THREADS), (unsigned)a.t_out);
   if (a.dtype == CLASFV_F32) warp_fuse_kernel<float><<<grid, WF_THREADS, 0, s>>>(a);
+  else if (a.dtype == CLASFV_F16) warp_fuse_kernel<__half><<<grid, WF_THREADS, 0, s>>>(a);
   else warp_fuse_kernel<__nv_bfloat16><<<grid, WF_THREADS, 0, s>>>(a);
   CLASFV_CUDA(cudaGetLastError());
   return CLASFV_OK;
@@ -671,6 +688,8 @@ int launch_fuse_shift_votes(const void* prob, int dtype, int t, int h, int w, in
   dim3 grid((unsigned)cdiv((int64_t)h * w, 256), (unsigned)t);
   if (dtype == CLASFV_F32)
     fuse_shift_votes_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(prob), t, h * w, clip_len, step, n_shifts, tab, mask, area);
+  else if (dtype == CLASFV_F16)
+    fuse_shift_votes_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(prob), t, h * w, clip_len, step, n_shifts, tab, mask, area);
   else
     fuse_shift_votes_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(prob), t, h * w, clip_len, step, n_shifts, tab, mask, area);
   CLASFV_CUDA(cudaGetLastError());

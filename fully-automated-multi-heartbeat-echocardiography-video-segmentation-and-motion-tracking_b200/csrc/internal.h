@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <string>
@@ -55,8 +56,9 @@ struct ConvArgs {
   const float* bias;      // [Cout] fp32 or nullptr
   const void* residual;   // (N,To,Ho,Wo,Cout) element type = out type, or nullptr
   void* out;              // (N,To,Ho,Wo,Cout)
-  int act_dtype;          // CLASFV_F32 | CLASFV_BF16: type of in / weight
+  int act_dtype;          // CLASFV_F32 | CLASFV_BF16 | CLASFV_F16: type of in / weight
   int out_f32;            // 1: out (and residual) are fp32 regardless of act_dtype
+  int out_f16;            // 1: out (and residual) are fp16 regardless of act_dtype (tcgen05 path: the decoder's lateral maps)
   int relu;
   double macs_per_pos;    // true (unpadded) MACs per output position, for the profiler's performed-FLOP count
   // ---- optional, tcgen05 path only (zero-initialised by make_conv): ragged clip geometry of the dense-video trunk
@@ -82,6 +84,8 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t stream);
 // tcgen05 / TMEM / TMA implicit GEMM, bf16 only.  conv_umma.cu
 int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream);
 int umma_selftest_supported();
+// cuTensorMapEncodeTiled for a 16-bit tensor, SWIZZLE_128B, zero fill out of bounds (conv_umma.cu)
+int encode_tmap_16bit(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool fp16);
 
 // Stem 1x7x7 stride (1,2,2) pad (0,3,3) convolution from the planar fp32 input.  conv_simt.cu
 struct StemArgs {
@@ -105,24 +109,28 @@ int launch_frame_gather(void* dst, int64_t dst_batch_stride_bytes, int n, int64_
 // Decoder head: 4-level trilinear (align_corners=True) gather-sum of the laterally projected feature
 // maps + bias + ReLU + 64x64 + ReLU + 6x64 heads + softmax / tanh.  decoder.cu
 struct HeadArgs {
-  const void* g[4];            // (N,Tl,Hl,Wl,64) fp32 (g_dtype F32) or bf16, levels 1/2 (T/1), 1/4 (T/2), 1/8 (T/4), 1/16 (T/8)
+  const void* g[4];            // (N,Tl,Hl,Wl,64) fp32 (g_dtype F32) or fp16, levels 1/2 (T/1), 1/4 (T/2), 1/8 (T/4), 1/16 (T/8)
   int g_dtype;
   int tl[4], hl[4], wl[4];
   int n, t, h, w;
   const float* b1;             // [64]   folded comb_1 bias + BN1
   const float* w2;             // [64][64] folded comb_2 * BN2 scale, row = output channel
-  const __nv_bfloat16* w2_bf16;  // same, bf16 (tensor-core head)
+  const void* a_tab;           // tensor-core head: interpolation matrices of the frame geometry (launch_head_table)
+  int tail_f16;                // tensor-core head: comb_2 / head operands in fp16 (1) or bf16 (0)
   const float* b2;             // [64]
   const float* wh;             // [6][64]  rows 0-1 segmentation head, 2-5 motion head
   const float* bh;             // [6]
   void* seg; void* motion;     // (N,2,T,H,W), (N,4,T,H,W)
-  int out_dtype;               // CLASFV_F32 | CLASFV_BF16
+  int out_dtype;               // CLASFV_F32 | CLASFV_BF16 | CLASFV_F16
   int out_kind;                // CLASFV_OUT_LOGITS | CLASFV_OUT_PROB
 };
 int launch_head(const HeadArgs& a, cudaStream_t stream);        // CUDA-core head (fp32 g)
-int launch_head_umma(const HeadArgs& a, cudaStream_t stream);   // tcgen05 head (bf16 g), decoder_umma.cu
-// (n,tl,hl,wl,64) bf16 -> (n,t,hl,wl,64) bf16, linear along T, align_corners=True (pre-pass of the tcgen05 head)
-int launch_temporal_upsample_bf16(const void* in, void* out, int n, int tl, int t, int hl, int wl, cudaStream_t stream);
+// tcgen05 head (fp16 g, every level at the output's frame rate), decoder_umma.cu
+int launch_head_umma(const HeadArgs& a, int num_sms, cudaStream_t stream);
+size_t head_table_bytes(const HeadArgs& a);                              // 0: geometry not supported
+int launch_head_table(const HeadArgs& a, void* tab, cudaStream_t stream);  // fills a.h x a.w's interpolation matrices (once per geometry)
+// (n,tl,hl,wl,64) fp16 -> (n,t,hl,wl,64) fp16, linear along T, align_corners=True (pre-pass of the tcgen05 head)
+int launch_temporal_upsample_f16(const void* in, void* out, int n, int tl, int t, int hl, int wl, cudaStream_t stream);
 
 // fusion.cu
 int launch_ingest_u8(const uint8_t* frames, int t, int h0, int w0, int bgr, float* out, int h, int w, uint32_t* minmax_dev, cudaStream_t s);

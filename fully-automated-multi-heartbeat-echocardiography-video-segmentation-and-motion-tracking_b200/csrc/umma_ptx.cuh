@@ -88,10 +88,22 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
 // Make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma / TMA reads).
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// fp16 pair {low half = a, high half = b}, saturating to the largest finite value instead of overflowing to infinity
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+
 // instruction descriptor: D=f32, A=B=bf16, both K-major (cute::UMMA::InstrDescriptor)
 __host__ __device__ inline uint32_t idesc_bf16_f32(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// same with A=B=fp16 (operand format 0); kind::f16 rejects mixed fp16 x bf16 operands
+__host__ __device__ inline uint32_t idesc_f16_f32(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__host__ __device__ inline uint32_t idesc_16bit_f32(int m, int n, bool fp16) { return fp16 ? idesc_f16_f32(m, n) : idesc_bf16_f32(m, n); }
 
 }  // namespace ptx
 }  // namespace clasfv

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, OUT_LOGITS, OUT_PROB, ClasfvError, check
+from ._lib import BF16, F16, F32, OUT_LOGITS, OUT_PROB, ClasfvError, check
 
 
 def precision_code(precision):
@@ -20,7 +20,14 @@ def precision_code(precision):
         return F32
     if precision in (BF16, "bf16", "bfloat16", torch.bfloat16):
         return BF16
-    raise ClasfvError(f"unknown precision {precision!r}: use 'fp32' or 'bf16'")
+    if precision in (F16, "fp16", "f16", "float16", "half", torch.float16):
+        return F16
+    raise ClasfvError(f"unknown precision {precision!r}: use 'fp32', 'bf16' or 'fp16'")
+
+
+def storage_dtype(precision):
+    """torch element type of the prob / motion planes the fused pipeline keeps resident in a given precision mode."""
+    return {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}[precision_code(precision)]
 
 
 class Engine:
@@ -230,7 +237,7 @@ class Engine:
         to = (t + 2 * padding[0] - kt) // stride[0] + 1
         ho = (h + 2 * padding[1] - kh) // stride[1] + 1
         wo = (w + 2 * padding[2] - kw) // stride[2] + 1
-        out_dtype = torch.float32 if (out_f32 or x.dtype == torch.float32) else torch.bfloat16
+        out_dtype = torch.float32 if (out_f32 or x.dtype == torch.float32) else x.dtype
         out = torch.empty((n, to, ho, wo, cout), dtype=out_dtype, device=x.device)
         wa = np.ascontiguousarray(weight.detach().cpu().float().numpy())
         sa = np.ascontiguousarray(scale.detach().cpu().float().numpy()) if scale is not None else None

@@ -4,7 +4,7 @@
 
 Reference flags kept (motion_segment.py:19-65): -p/--path, -m/--model, -d/--device, --fuse_method,
 -f/--fuse, -s/--step, -o/--output, -v/--verbose, -c/--content, --height, --width.
-Added: --precision {fp32,bf16}; --fuse_method also accepts "warp" (the warp-and-fuse operator).
+Added: --precision {fp32,bf16,fp16}; --fuse_method also accepts "warp" (the warp-and-fuse operator).
 ``-d cpu`` (the reference's default) is rejected: this build has no CPU path.
 """
 import argparse
@@ -39,8 +39,8 @@ def build_parser():
                     help="Content of the output: gif, binary, binary_video, all", default="binary")
     ap.add_argument("--height", required=False, type=int, help="Height of image (pretrain model uses 112)", default=112)
     ap.add_argument("--width", required=False, type=int, help="Width of image (pretrain model uses 112)", default=112)
-    ap.add_argument("--precision", required=False, type=str, choices=("fp32", "bf16"), default="fp32",
-                    help="fp32: reference-tolerance mode; bf16: tensor-core mode")
+    ap.add_argument("--precision", required=False, type=str, choices=("fp32", "bf16", "fp16"), default="fp32",
+                    help="fp32: reference-tolerance mode; bf16 / fp16: tensor-core modes")
     return ap
 
 

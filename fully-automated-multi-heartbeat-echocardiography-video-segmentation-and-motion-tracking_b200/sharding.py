@@ -141,7 +141,8 @@ def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=32, gr
     c0, c1 = ranges[rank]
     mine = starts[c0:c1]
     lo, hi = touched_window(mine, num_frames, edge_hops)
-    out_dtype = torch.float32 if eng.precision == 0 else torch.bfloat16
+    from .engine import storage_dtype
+    out_dtype = storage_dtype(eng.precision)
     dev = eng.device
     if mine:
         # only the frames this rank's clips read go to its GPU (a 2000-frame 224x224 video is 1.2 GB as fp32)

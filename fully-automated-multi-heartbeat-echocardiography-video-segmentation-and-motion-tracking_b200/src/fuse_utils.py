@@ -125,7 +125,7 @@ def segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num
     method = fuse_method.lower()
     v = _to_device_video(video, eng.device)
     num_frames, h, w = int(v.shape[1]), int(v.shape[2]), int(v.shape[3])
-    out_dtype = torch.float32 if eng.precision == 0 else torch.bfloat16
+    out_dtype = _engine.storage_dtype(eng.precision)
 
     if method == "warp":
         if num_frames < CLIP:

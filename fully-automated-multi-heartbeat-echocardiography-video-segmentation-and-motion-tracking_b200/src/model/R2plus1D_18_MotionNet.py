@@ -8,8 +8,9 @@ Same constructor, same 242-key ``state_dict`` (so ``load_state_dict(torch.load(p
 C-ABI library's sm_100a kernels.  There is no PyTorch or CPU execution path: inference mode on a
 CUDA device or an error.
 
-Extra, optional: ``precision`` ("fp32" reference-tolerance mode on CUDA cores, "bf16" tcgen05
-tensor-core mode) - constructor keyword or attribute.
+Extra, optional: ``precision`` - constructor keyword or attribute: "fp32" reference-tolerance mode on CUDA cores;
+"bf16" / "fp16" tcgen05 tensor-core modes (same kernels, same speed; fp16 stores 11 significant bits instead of 8 and
+is the 16-bit mode that meets the parity gates).
 """
 from __future__ import annotations
 
@@ -100,5 +101,5 @@ class R2plus1D_18_MotionNet(nn.Module):
         """forward + the F.softmax(seg, 1) of fuse_utils.py:60 fused into the head kernel."""
         x = self._prepare(x)
         if out_dtype is None:
-            out_dtype = torch.float32 if _engine.precision_code(self.precision) == 0 else torch.bfloat16
+            out_dtype = _engine.storage_dtype(self.precision)
         return self.engine(x.device).forward(x, OUT_PROB, out_dtype)

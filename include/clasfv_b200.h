@@ -35,6 +35,8 @@ extern "C" {
 /* element types of activation-sized buffers / arithmetic mode of the network */
 #define CLASFV_F32  0   /* fp32 storage, fp32 CUDA-core arithmetic (reference-tolerance mode)        */
 #define CLASFV_BF16 1   /* bf16 storage, tcgen05 tensor-core arithmetic with fp32 accumulation       */
+#define CLASFV_F16  2   /* fp16 storage (11 significant bits instead of 8; conversions saturate), the same
+                           tcgen05 kernels at the same rate, fp32 accumulation                          */
 
 /* error codes */
 #define CLASFV_OK          0
@@ -66,7 +68,7 @@ const char* clasfv_last_error(void);
 int  clasfv_create(int device, clasfv_handle** out);
 void clasfv_destroy(clasfv_handle* h);
 int  clasfv_set_tensor(clasfv_handle* h, const char* key, const float* data_host, const int64_t* shape, int ndim);
-int  clasfv_finalize(clasfv_handle* h, int precision /* CLASFV_F32 | CLASFV_BF16 */);
+int  clasfv_finalize(clasfv_handle* h, int precision /* CLASFV_F32 | CLASFV_BF16 | CLASFV_F16 */);
 
 /* ---- network forward --------------------------------------------------------------------------
  * Replaces R2plus1D_18_MotionNet.forward (src/model/R2plus1D_18_MotionNet.py:26-71) and, with
@@ -78,7 +80,7 @@ int  clasfv_finalize(clasfv_handle* h, int precision /* CLASFV_F32 | CLASFV_BF16
  * overlapping stride-1 windows of one resident video (3,Tv,H,W) be used in place without copies:
  * offset = start_n*H*W, channel_stride = Tv*H*W.
  * T % 8 == 0, H % 16 == 0, W % 16 == 0 (the decoder's scale-factor upsampling must land on T,H,W).
- * out_dtype selects the element type of seg_dev / motion_dev (CLASFV_F32 or CLASFV_BF16). */
+ * out_dtype selects the element type of seg_dev / motion_dev (CLASFV_F32, CLASFV_BF16 or CLASFV_F16). */
 int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_offset_host, int64_t channel_stride,
                    int n, int t, int height, int width, int out_kind, int out_dtype,
                    void* seg_dev, void* motion_dev, void* stream);
