@@ -239,10 +239,40 @@ ConvArgs make_conv(const PackedConv& pc, int n, int ti, int hi, int wi, const vo
 
 int run_conv(clasfv_handle* h, const ConvArgs& a, cudaStream_t stream) {
   if (h->profiling) h->prof_gflop[h->cur_stage] += 2e-9 * a.macs_per_pos * (double)a.s.n * a.s.to * a.s.ho * a.s.wo;
-  if (a.act_dtype != CLASFV_F32 && !h->force_simt) return launch_conv_umma(a, h->num_sms, stream);
-  return launch_conv_simt(a, stream);
+  // CLASFV_CONV_TRACE=1: time every convolution on its own (stream drained before and after) and print one line per
+  // launch to stderr - a development aid for finding the layers furthest from the roofline, never on in a measurement
+  static const bool trace = getenv("CLASFV_CONV_TRACE") != nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (trace) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(stream); cudaEventRecord(e0, stream); }
+  const int rc = (a.act_dtype != CLASFV_F32 && !h->force_simt) ? launch_conv_umma(a, h->num_sms, stream) : launch_conv_simt(a, stream);
+  if (trace) {
+    cudaEventRecord(e1, stream); cudaEventSynchronize(e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    const double gf = 2e-9 * a.macs_per_pos * (double)a.s.n * a.s.to * a.s.ho * a.s.wo;
+    const ConvShape& s = a.s;
+    fprintf(stderr, "conv n=%d in=%dx%dx%dx%d out=%dx%dx%dx%d k=%dx%dx%d s=%d,%d,%d seg=%d res=%d relu=%d  %.4f ms  %.2f GFLOP  %.0f TFLOP/s\n", s.n, s.ti, s.hi,
+            s.wi, s.cin, s.to, s.ho, s.wo, s.cout, s.kt, s.kh, s.kw, s.st, s.sh, s.sw, a.seg.on, a.residual ? 1 : 0, a.relu, ms, gf, gf / ms);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  return rc;
 }
 
+
+// interpolation matrices of the tensor-core head for ha's frame geometry: built on first use, kept by the handle
+int head_table(clasfv_handle* h, HeadArgs* ha, cudaStream_t stream) {
+  auto it = h->head_tabs.find({ha->h, ha->w});
+  if (it == h->head_tabs.end()) {
+    const size_t bytes = head_table_bytes(*ha);
+    CLASFV_REQUIRE(bytes > 0, "the tensor-core head does not tile a %d x %d frame (H %% 8, W %% 16, at most 512 x 512)", ha->h, ha->w);
+    void* tab = nullptr;
+    CLASFV_CUDA(cudaMalloc(&tab, bytes));
+    const int rc = launch_head_table(*ha, tab, stream);
+    if (rc) { cudaFree(tab); return rc; }
+    it = h->head_tabs.emplace(std::make_pair(ha->h, ha->w), tab).first;
+  }
+  ha->a_tab = it->second;
+  return CLASFV_OK;
+}
 
 // ------------------------------------------------------------------------------------------- forward
 // One clasfv_forward call.  The clips are processed in internal batches of h->sub_batch.  Two schedules:
@@ -368,19 +398,7 @@ struct Forward {
     ha.n = nb; ha.t = t; ha.h = height; ha.w = width;
     ha.b1 = h->b1; ha.w2 = h->w2; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;
     ha.a_tab = nullptr; ha.tail_f16 = act == CLASFV_F16 ? 1 : 0;
-    if (tc_head) {
-      // interpolation matrices of this frame geometry: built on first use, kept by the handle
-      auto it = h->head_tabs.find({height, width});
-      if (it == h->head_tabs.end()) {
-        const size_t bytes = head_table_bytes(ha);
-        CLASFV_REQUIRE(bytes > 0, "clasfv_forward: the tensor-core head does not tile a %d x %d frame", height, width);
-        void* tab = nullptr;
-        CLASFV_CUDA(cudaMalloc(&tab, bytes));
-        if ((rc = launch_head_table(ha, tab, stream))) { cudaFree(tab); return rc; }
-        it = h->head_tabs.emplace(std::make_pair(height, width), tab).first;
-      }
-      ha.a_tab = it->second;
-    }
+    if (tc_head && (rc = head_table(h, &ha, stream))) return rc;
     const size_t oes = out_dtype == CLASFV_F32 ? 4 : 2;
     const size_t plane = (size_t)t * height * width * oes;
     ha.seg = seg + (size_t)c0 * 2 * plane; ha.motion = motion + (size_t)c0 * 4 * plane;
@@ -978,6 +996,28 @@ int clasfv_conv3d(clasfv_handle* h, const void* x_dev, int dtype, int n, int t, 
   if (rc) return rc;
   if (e != cudaSuccess) { set_error("clasfv_conv3d: kernel failed: %s", cudaGetErrorString(e)); return CLASFV_ECUDA; }
   return CLASFV_OK;
+}
+
+int clasfv_decoder_head(clasfv_handle* h, const void* g0_dev, const void* g1_dev, const void* g2_dev, const void* g3_dev,
+                        int n, int t, int height, int width, int out_kind, int out_dtype,
+                        void* seg_dev, void* motion_dev, void* stream_v) {
+  CLASFV_REQUIRE(h && g0_dev && g1_dev && g2_dev && g3_dev && seg_dev && motion_dev, "clasfv_decoder_head: null argument");
+  if (!h->finalized || h->precision == CLASFV_F32) { set_error("clasfv_decoder_head: finalize the handle in a tensor-core precision first"); return CLASFV_ESTATE; }
+  CLASFV_REQUIRE(n >= 1 && t >= 1 && height >= 16 && height % 16 == 0 && width >= 16 && width % 16 == 0, "clasfv_decoder_head: bad extent");
+  CLASFV_REQUIRE(out_kind == CLASFV_OUT_LOGITS || out_kind == CLASFV_OUT_PROB, "clasfv_decoder_head: bad out_kind");
+  CLASFV_REQUIRE(out_dtype == CLASFV_F32 || out_dtype == CLASFV_BF16 || out_dtype == CLASFV_F16, "clasfv_decoder_head: bad out_dtype");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  HeadArgs ha;
+  const void* g[4] = {g0_dev, g1_dev, g2_dev, g3_dev};
+  for (int i = 0; i < 4; ++i) { ha.g[i] = g[i]; ha.tl[i] = t; ha.hl[i] = height >> (i + 1); ha.wl[i] = width >> (i + 1); }
+  ha.g_dtype = CLASFV_F16; ha.n = n; ha.t = t; ha.h = height; ha.w = width;
+  ha.b1 = h->b1; ha.w2 = h->w2; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;
+  ha.a_tab = nullptr; ha.tail_f16 = h->precision == CLASFV_F16 ? 1 : 0;
+  ha.seg = seg_dev; ha.motion = motion_dev; ha.out_dtype = out_dtype; ha.out_kind = out_kind;
+  int rc = head_table(h, &ha, stream);
+  if (rc) return rc;
+  return launch_head_umma(ha, h->num_sms, stream);
 }
 
 }  // extern "C"

@@ -227,6 +227,21 @@ class Engine:
                                                _lib.current_stream_ptr(prob.device)), "clasfv_fuse_shift_votes")
         return mask, area
 
+    def decoder_head(self, g, out_kind=OUT_LOGITS, out_dtype=torch.float32):
+        """The fused tensor-core head alone (test surface): g = four fp16 CUDA maps (N,T,H/2^(l+1),W/2^(l+1),64)."""
+        for x in g:
+            _lib.require_cuda(x, "g")
+            if x.dtype != torch.float16:
+                raise ClasfvError("decoder_head: lateral maps must be float16")
+        n, t, h2, w2, _ = g[0].shape
+        h, w = 2 * h2, 2 * w2
+        seg = torch.empty((n, 2, t, h, w), dtype=out_dtype, device=g[0].device)
+        mot = torch.empty((n, 4, t, h, w), dtype=out_dtype, device=g[0].device)
+        check(self.lib.clasfv_decoder_head(self._h, g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), n, t, h, w,
+                                           out_kind, _lib.torch_dtype_code(out_dtype), seg.data_ptr(), mot.data_ptr(),
+                                           _lib.current_stream_ptr(g[0].device)), "clasfv_decoder_head")
+        return seg, mot
+
     # ------------------------------------------------------------------ single layer (tests)
     def conv3d(self, x, weight, scale=None, shift=None, stride=(1, 1, 1), padding=(0, 0, 0), residual=None, relu=False,
                engine="umma", out_f32=False):

@@ -191,11 +191,20 @@ int clasfv_temporal_resample(const float* in_dev, float* out_dev, int channels, 
  * dtype (out_f32 != 0 forces fp32 output); w_host (Cout,Cin,kt,kh,kw) fp32 reference layout;
  * scale_host / shift_host (Cout) fp32 or NULL (per-channel affine applied after the convolution);
  * residual_dev (same shape/type as out) or NULL.  engine: 0 = CUDA-core kernel, 1 = tcgen05 kernel
- * (dtype must be CLASFV_BF16, Cin % 16 == 0, Cout % 16 == 0). */
+ * (dtype must be CLASFV_BF16 or CLASFV_F16, Cin % 16 == 0, Cout % 16 == 0). */
 int clasfv_conv3d(clasfv_handle* h, const void* x_dev, int dtype, int n, int t, int height, int width, int cin,
                   const float* w_host, const float* scale_host, const float* shift_host, int cout,
                   int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
                   const void* residual_dev, int relu, int engine, int out_f32, void* out_dev, void* stream);
+
+/* The fused tensor-core decoder head on its own (same test surface idea): the four laterally projected 64-channel
+ * maps g_l, channels-last fp16 (N,T,H/2^(l+1),W/2^(l+1),64), l = 0..3, all at the output's frame rate, through the
+ * head of the finalized network (comb_1 bias + ReLU, comb_2 + ReLU, segmentation / motion heads of
+ * src/model/R2plus1D_18_MotionNet.py:55-69, bilinear align_corners=True interpolation of :41-49 inside the first GEMM).
+ * The handle must be finalized in a tensor-core precision (CLASFV_BF16 or CLASFV_F16). */
+int clasfv_decoder_head(clasfv_handle* h, const void* g0_dev, const void* g1_dev, const void* g2_dev, const void* g3_dev,
+                        int n, int t, int height, int width, int out_kind, int out_dtype,
+                        void* seg_dev, void* motion_dev, void* stream);
 
 #ifdef __cplusplus
 }

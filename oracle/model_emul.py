@@ -145,32 +145,37 @@ def _hilo(v, kind):
     return hi, rnd(v - hi, kind)
 
 
-def decoder(sd, feats, t_out, h_out, w_out, cfg, out_kind="logits"):
-    s1, t1 = bn_affine(sd, "comb_batch_norm_1")
-    s2, t2 = bn_affine(sd, "comb_batch_norm_2")
+def lateral_maps(sd, feats, t_out, cfg):
+    """The four 64-channel maps the head reads: comb_1 (BN folded) applied per feature map at native resolution
+    (stem + layer1 share a resolution and are summed), rounded to `cfg.lateral`, levels 2-4 interpolated along T."""
+    s1, _t1 = bn_affine(sd, "comb_batch_norm_1")
     w1 = sd["comb_1_layer.weight"][:, :, 0, 0, 0] * s1.view(-1, 1)                  # (64, 1024)
-    b1 = s1 * sd["comb_1_layer.bias"] + t1
-    b2 = s2 * sd["comb_2_layer.bias"] + t2
-    w2 = rnd(sd["comb_2_layer.weight"][:, :, 0, 0, 0] * s2.view(-1, 1), cfg.w2)
-    wh = rnd(torch.cat([sd["segmentation_head.weight"], sd["motion_head.weight"]])[:, :, 0, 0, 0], cfg.wh)
-    bh = torch.cat([sd["segmentation_head.bias"], sd["motion_head.bias"]])
-    widths = [f.shape[1] for f in feats]
     offs = [0]
-    for c in widths:
-        offs.append(offs[-1] + c)
-    # lateral projections at native resolution (stem + layer1 are one two-source convolution)
+    for f in feats:
+        offs.append(offs[-1] + f.shape[1])
     g = []
     for i, f in enumerate(feats):
         w = w1[:, offs[i]:offs[i + 1]] if "lateral" in cfg.exact else rnd(w1[:, offs[i]:offs[i + 1]], cfg.wtrunk)
         g.append(torch.einsum("nctHW,oc->notHW", f, w))
     g = [g[0] + g[1]] + g[2:]
     g = [rnd(x, cfg.lateral) for x in g]
-    # temporal pre-pass for the levels below the output's frame rate
     for l in range(1, 4):
         i0, i1, l0, l1 = _axis(t_out, g[l].shape[2])
         a, b = g[l][:, :, i0], g[l][:, :, i1]
         up = l0.view(1, 1, -1, 1, 1) * a + l1.view(1, 1, -1, 1, 1) * b
         g[l] = rnd(torch.where((l1 == 0).view(1, 1, -1, 1, 1), a, up), cfg.lateral)
+    return g
+
+
+def head(sd, g, h_out, w_out, cfg, out_kind="logits"):
+    """The fused head on lateral maps g (list of four (N,64,T,Hl,Wl) tensors at the output's frame rate)."""
+    s1, t1 = bn_affine(sd, "comb_batch_norm_1")
+    s2, t2 = bn_affine(sd, "comb_batch_norm_2")
+    b1 = s1 * sd["comb_1_layer.bias"] + t1
+    b2 = s2 * sd["comb_2_layer.bias"] + t2
+    w2 = rnd(sd["comb_2_layer.weight"][:, :, 0, 0, 0] * s2.view(-1, 1), cfg.w2)
+    wh = rnd(torch.cat([sd["segmentation_head.weight"], sd["motion_head.weight"]])[:, :, 0, 0, 0], cfg.wh)
+    bh = torch.cat([sd["segmentation_head.bias"], sd["motion_head.bias"]])
     acc = 0.0
     wkind = "f16" if cfg.head == "row" else cfg.lateral
     for l in range(4):
@@ -192,13 +197,17 @@ def decoder(sd, feats, t_out, h_out, w_out, cfg, out_kind="logits"):
                     acc = acc + wgt.view(1, 1, 1, h_out, w_out) * g[l][:, :, :, ih[a]][:, :, :, :, iw[b]]
     bhi, blo = _hilo(b1, wkind)
     h1 = rnd(F.relu(acc + (bhi + blo).view(1, -1, 1, 1, 1)), cfg.h1)
-    b2hi, b2lo = _hilo(b2, "bf16")
+    b2hi, b2lo = _hilo(b2, "bf16" if cfg.h1 == "bf16" else ("f16" if cfg.h1 == "f16" else "fp32"))
     h2 = rnd(F.relu(torch.einsum("ncThw,oc->noThw", h1, w2) + (b2hi + b2lo).view(1, -1, 1, 1, 1)), cfg.h2)
     o = torch.einsum("ncThw,oc->noThw", h2, wh) + bh.view(1, -1, 1, 1, 1)
     seg, mot = o[:, :2], torch.tanh(o[:, 2:])
     if out_kind == "prob":
         seg = torch.softmax(seg, 1)
     return rnd(seg, cfg.out), rnd(mot, cfg.out)
+
+
+def decoder(sd, feats, t_out, h_out, w_out, cfg, out_kind="logits"):
+    return head(sd, lateral_maps(sd, feats, t_out, cfg), h_out, w_out, cfg, out_kind)
 
 
 def forward(sd, x, cfg=Config(), out_kind="logits"):
