@@ -40,6 +40,7 @@ namespace {
 constexpr float BN_EPS = 1e-5f;
 constexpr int DEC = 64;                 // decoder width
 constexpr int STEM_MID = 45, STEM_MID_PAD = 64;
+constexpr int DENSE_DEPTH = 5;          // temporal convolutions through the stem and layer1: frames a clip edge reaches
 
 struct HostTensor { std::vector<int64_t> shape; std::vector<float> data; };
 
@@ -330,20 +331,24 @@ struct Forward {
         mid_elems = std::max(mid_elems, std::max(e1, e2));
       }
     o_s0 = dense ? 0 : region(P[0] * STEM_MID_PAD * es);
-    for (int i = 0; i < 5; ++i) o_f[i] = region(P[i] * C[i] * es);
+    // dense-video schedule: the stem / layer1 outputs of a clip are never assembled (edge frames + the shared video-level map)
+    for (int i = 0; i < 5; ++i) o_f[i] = (dense && i < 2) ? 0 : region(P[i] * C[i] * es);
     o_mid = region(mid_elems * es);
     o_ta = region(P[dense ? 2 : 1] * (dense ? 128 : 64) * es);
     o_x1 = region(P[dense ? 2 : 1] * (dense ? 128 : 64) * es);
     o_ds = region(P[2] * 128 * es);
-    for (int i = 0; i < 4; ++i) o_g[i] = region(P[i + 1] * DEC * gs);
+    // level 0 of the dense-video schedule holds only the 2 * DENSE_DEPTH edge frames of every clip
+    for (int i = 0; i < 4; ++i) o_g[i] = region((dense && i == 0 ? (int64_t)nb * 2 * DENSE_DEPTH * H[1] * W[1] : P[i + 1]) * DEC * gs);
     // tensor-core head: lateral maps of levels 2-4 interpolated along T to the output's frame count
     for (int i = 1; i < 4; ++i) o_gt[i] = tc_head ? region((int64_t)nb * t * H[i + 1] * W[i + 1] * DEC * gs) : 0;
   }
 
   // one residual block on a batch of nb clips
-  int run_block(const Block& blk, int nb, const void* in, int ti, int hi, int wi, void* out, int* to, int* ho, int* wo) {
+  int run_block(const Block& blk, int nb, const void* in, int ti, int hi, int wi, void* out, int* to, int* ho, int* wo,
+                const ConvArgs::FrameSel* fsel = nullptr, int64_t in_batch_stride = 0) {
     int rc;
     ConvArgs c1 = make_conv(blk.s1, nb, ti, hi, wi, in, ws + o_mid, nullptr, 1, act, 0);
+    if (fsel) { c1.fsel = *fsel; c1.in_batch_stride = in_batch_stride; }
     if ((rc = run_conv(h, c1, stream))) return rc;
     ConvArgs c2 = make_conv(blk.t1, nb, c1.s.to, c1.s.ho, c1.s.wo, ws + o_mid, ws + o_ta, nullptr, 1, act, 0);
     if ((rc = run_conv(h, c2, stream))) return rc;
@@ -351,8 +356,13 @@ struct Forward {
     if ((rc = run_conv(h, c3, stream))) return rc;
     const void* res = in;
     if (blk.has_down) {
-      if ((rc = run_conv(h, make_conv(blk.down, nb, ti, hi, wi, in, ws + o_ds, nullptr, 0, act, 0), stream))) return rc;
+      ConvArgs cd = make_conv(blk.down, nb, ti, hi, wi, in, ws + o_ds, nullptr, 0, act, 0);
+      if (fsel) { cd.fsel = *fsel; cd.in_batch_stride = in_batch_stride; }
+      if ((rc = run_conv(h, cd, stream))) return rc;
       res = ws + o_ds;
+    } else if (fsel) {
+      set_error("internal: a frame-selected block input needs a downsample branch (the residual would read the virtual clip)");
+      return CLASFV_EINVAL;
     }
     ConvArgs c4 = make_conv(blk.t2, nb, c3.s.to, c3.s.ho, c3.s.wo, ws + o_mid, out, res, 1, act, 0);
     if ((rc = run_conv(h, c4, stream))) return rc;
@@ -360,21 +370,58 @@ struct Forward {
     return CLASFV_OK;
   }
 
-  // layers first_layer..4, lateral projections and the head, for a batch whose f[0] (and f[1] if first_layer == 1) are in place
-  int run_tail(int nb, int c0, int first_layer) {
+  // What the dense-video schedule hands to run_tail instead of assembled per-clip stem / layer1 maps
+  struct DenseIn {
+    const char* e1; const char* e5;       // per clip: the 2 edge frames of the stem output, the 2 * DENSE_DEPTH edge frames of layer1's
+    const char* v1; const char* v5;       // video-level maps, at the first frame of this batch's first clip
+    const char* g0_video;                 // video-level lateral map of level 0, same origin
+    int fs, tv_left;                      // frames between clips; video frames from that origin on
+  };
+
+  // layers first_layer..4, lateral projections and the head, for a batch whose f[0] (and f[1] if first_layer == 1) are in place -
+  // or, with `di`, are read as virtual clips (edge frames + video-level map)
+  int run_tail(int nb, int c0, int first_layer, const DenseIn* di = nullptr) {
     int rc;
+    const int64_t F64 = (int64_t)H[0] * W[0] * 64;
+    const int D = DENSE_DEPTH;
     for (int l = first_layer; l < 4; ++l) {
       const void* in = ws + o_f[l];
       int ti = T[l], hi = H[l], wi = W[l];
       for (int b = 0; b < 2; ++b) {
         void* out = b == 0 ? (void*)(ws + o_x1) : (void*)(ws + o_f[l + 1]);
-        if ((rc = run_block(h->blocks[l][b], nb, in, ti, hi, wi, out, &ti, &hi, &wi))) return rc;
+        if (di && l == 1 && b == 0) {
+          // layer2's first block reads the clip's layer-1 output: frames < D and >= t - D from the clip's edge buffer, the rest
+          // in place from the video-level map
+          ConvArgs::FrameSel fsel;
+          memset(&fsel, 0, sizeof(fsel));
+          fsel.on = 1; fsel.a_t = 2 * D; fsel.b_t = t; fsel.b = di->v5; fsel.b_batch_stride = (int64_t)di->fs * F64;
+          for (int f = 0; f < t; ++f) {
+            const bool edge = f < D || f >= t - D;
+            fsel.src[f] = edge ? 0 : 1; fsel.idx[f] = (int16_t)(f < D ? f : edge ? f - (t - 2 * D) : f);
+          }
+          if ((rc = run_block(h->blocks[l][b], nb, di->e5, ti, hi, wi, out, &ti, &hi, &wi, &fsel, (int64_t)2 * D * F64))) return rc;
+        } else {
+          if ((rc = run_block(h->blocks[l][b], nb, in, ti, hi, wi, out, &ti, &hi, &wi))) return rc;
+        }
         in = out;
       }
     }
     if ((rc = mark(1))) return rc;
     // decoder: lateral projections at native resolution, stem + layer1 share one map
-    {
+    if (di) {
+      // dense-video schedule: the video-level part of this map was projected once per call (run_dense); per clip only its
+      // 2 * D edge frames.  Stem output of edge frame j: the clip's own first / last frame, video-level frames otherwise.
+      ConvArgs c = make_conv(h->lateral[0], nb, 2 * D, H[0], W[0], di->e1, ws + o_g[0], nullptr, 0, act, 0);
+      c.in2 = di->e5; c.macs_per_pos *= 2; c.out_f16 = 1;
+      c.in_batch_stride = 2 * F64;
+      c.fsel.on = 1; c.fsel.a_t = 2; c.fsel.b_t = t; c.fsel.b = di->v1; c.fsel.b_batch_stride = (int64_t)di->fs * F64;
+      for (int j = 0; j < 2 * D; ++j) {
+        const int f = j < D ? j : t - 2 * D + j;               // clip frame of edge slot j
+        const bool own = f == 0 || f == t - 1;
+        c.fsel.src[j] = own ? 0 : 1; c.fsel.idx[j] = (int16_t)(own ? (f == 0 ? 0 : 1) : f);
+      }
+      if ((rc = run_conv(h, c, stream))) return rc;
+    } else {
       ConvArgs c = make_conv(h->lateral[0], nb, T[0], H[0], W[0], ws + o_f[0], ws + o_g[0], nullptr, 0, act, tc_head ? 0 : 1);
       c.in2 = ws + o_f[1];
       c.out_f16 = tc_head ? 1 : 0;               // the tensor-core head reads fp16 lateral maps whatever the trunk's type
@@ -389,6 +436,8 @@ struct Forward {
     if ((rc = mark(2))) return rc;
     HeadArgs ha;
     for (int i = 0; i < 4; ++i) { ha.g[i] = ws + o_g[i]; ha.tl[i] = T[i + 1]; ha.hl[i] = H[i + 1]; ha.wl[i] = W[i + 1]; }
+    ha.g0_video = nullptr; ha.g0_lo = ha.g0_hi = ha.g0_step = ha.g0_video_t = 0;
+    if (di) { ha.g0_video = di->g0_video; ha.g0_lo = D; ha.g0_hi = t - D; ha.g0_step = di->fs; ha.g0_video_t = di->tv_left; ha.tl[0] = 2 * D; }
     if (tc_head)
       for (int i = 1; i < 4; ++i) {
         if ((rc = launch_temporal_upsample_f16(ws + o_g[i], ws + o_gt[i], nb, T[i + 1], t, H[i + 1], W[i + 1], stream))) return rc;
@@ -424,7 +473,7 @@ struct Forward {
       for (int i = 2; i < n && uniform; ++i) uniform = offs_host[i] - offs_host[i - 1] == d;
       if (uniform) frame_step = d / hw;
     }
-    const bool dense = h->dense_video && tc_head && frame_step >= 1 && frame_step <= 8 && n >= 4 && t >= 16;
+    const bool dense = h->dense_video && tc_head && frame_step >= 1 && frame_step <= 8 && n >= 4 && t >= 16 && t <= CLASFV_MAX_FSEL;
     return dense ? run_dense((int)frame_step) : run_per_clip(frame_step);
   }
 
@@ -474,7 +523,7 @@ struct Forward {
     const int64_t FE = (int64_t)H[0] * W[0];
     const int midc = h->blocks[0][0].s1.cout_pad;          // 144
     const int64_t F64 = FE * 64, FM = FE * midc;           // elements per frame
-    const int D = 5;                                       // temporal convolutions through the stem and layer1
+    const int D = DENSE_DEPTH;                             // temporal convolutions through the stem and layer1
     total = 0;
     const size_t o_s0v = region((size_t)tv * FE * STEM_MID_PAD * es);
     size_t o_v[6], o_vs[6];                                // V_d (d = 1..5), VS_d (d = 2..5); V_2 and V_4 share a buffer
@@ -482,7 +531,8 @@ struct Forward {
     o_v[2] = o_v[4] = region((size_t)tv * F64 * es);
     for (int d = 2; d <= D; ++d) o_vs[d] = region((size_t)tv * FM * es);
     size_t o_e[6];
-    for (int d = 1; d < D; ++d) o_e[d] = region((size_t)nbmax * 2 * d * F64 * es);
+    for (int d = 1; d <= D; ++d) o_e[d] = region((size_t)nbmax * 2 * d * F64 * es);
+    const size_t o_g0v = region((size_t)tv * FE * DEC * 2);      // video-level lateral map of level 0 (fp16)
     const size_t o_es = region((size_t)nbmax * 2 * (D - 1) * FM * es);
     carve_batch(nbmax, true);
     int rc;
@@ -508,8 +558,17 @@ struct Forward {
       if ((rc = run_conv(h, make_conv(*temp[d], 1, tv, H[0], W[0], ws + o_vs[d], ws + o_v[d], res, 1, act, 0), stream))) return rc;
     }
     if ((rc = mark(1))) return rc;
+    {
+      // level 0 of the decoder's lateral maps over the video: one projection of (stem output, layer1 output) per video
+      // frame instead of one per clip frame
+      ConvArgs c = make_conv(h->lateral[0], 1, tv, H[0], W[0], ws + o_v[1], ws + o_g0v, nullptr, 0, act, 0);
+      c.in2 = ws + o_v[D]; c.macs_per_pos *= 2; c.out_f16 = 1;
+      set_stage(2);
+      if ((rc = run_conv(h, c, stream))) return rc;
+      if ((rc = mark(2))) return rc;
+    }
 
-    // ---- per batch of clips: edge frames of layer1, assembly, layers 2-4, decoder
+    // ---- per batch of clips: edge frames of layer1, layers 2-4 on virtual clips, decoder
     for (int c0 = 0; c0 < n; c0 += nbmax) {
       const int nb = std::min(nbmax, n - c0);
       if ((rc = mark(-1))) return rc;
@@ -518,9 +577,9 @@ struct Forward {
       auto vview = [&](size_t off, int64_t frame_elems) { return ws + off + (size_t)c0 * fs * frame_elems * es; };
       for (int d = 1; d <= D; ++d) {
         const int64_t fin = d == 1 ? FE * STEM_MID_PAD : FM;             // input frame (elements)
-        char* e_out = d == D ? ws + o_f[1] : ws + o_e[d];
-        const int64_t e_bstride = d == D ? (int64_t)t * F64 : (int64_t)2 * d * F64;
-        const int e_right = d == D ? t - d : d;                            // first right-edge frame in e_out
+        char* e_out = ws + o_e[d];
+        const int64_t e_bstride = (int64_t)2 * d * F64;
+        const int e_right = d;                                             // first right-edge frame in e_out
         if (d >= 2 &&
             (rc = run_conv(h, make_conv(*spat[d], nb, 2 * (d - 1), H[0], W[0], ws + o_e[d - 1], ws + o_es, nullptr, 1, act, 0), stream))) return rc;
         const char* vsrc = d == 1 ? vview(o_s0v, fin) : vview(o_vs[d], fin);
@@ -554,15 +613,14 @@ struct Forward {
           if ((rc = run_conv(h, c, stream))) return rc;
         }
       }
-      // assemble the per-clip stem output (lateral projection input) and the interior of the layer1 output
-      {
-        const int64_t fb = F64 * (int64_t)es;
-        FrameGatherSeg s0[3] = {{ws + o_e[1], 2 * fb, 0, 0, 1}, {vview(o_v[1], F64), fs * fb, 1, 1, t - 2}, {ws + o_e[1], 2 * fb, 1, t - 1, 1}};
-        if ((rc = launch_frame_gather(ws + o_f[0], (int64_t)t * fb, nb, fb, s0, 3, stream))) return rc;
-        FrameGatherSeg s1[1] = {{vview(o_v[D], F64), fs * fb, D, D, t - 2 * D}};
-        if ((rc = launch_frame_gather(ws + o_f[1], (int64_t)t * fb, nb, fb, s1, 1, stream))) return rc;
-      }
-      if ((rc = run_tail(nb, c0, 1))) return rc;
+      // No per-clip copy of the stem / layer1 outputs is assembled: layer2 and the lateral projection read virtual clips
+      // (ConvArgs::FrameSel), the head reads level 0 from the video-level map between the edges
+      DenseIn di;
+      di.e1 = ws + o_e[1]; di.e5 = ws + o_e[D];
+      di.v1 = vview(o_v[1], F64); di.v5 = vview(o_v[D], F64);
+      di.g0_video = ws + o_g0v + (size_t)c0 * fs * FE * DEC * 2;
+      di.fs = fs; di.tv_left = tv - c0 * fs;
+      if ((rc = run_tail(nb, c0, 1, &di))) return rc;
     }
     if (h->profiling) ++h->prof_calls;
     return CLASFV_OK;

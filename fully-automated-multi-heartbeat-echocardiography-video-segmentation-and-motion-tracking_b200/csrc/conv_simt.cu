@@ -257,43 +257,7 @@ __global__ void __launch_bounds__(STEM_TH * STEM_TW) stem_conv_kernel(const Stem
   for (int q = STEM_CO / 4; q < a.out_channels / 4; ++q) store4<OutT>(out + 4 * q, zero);
 }
 
-// Frame gather: dst[clip][dst_t0 + f] = src[clip * src_batch_stride + (src_t0 + f) frames] for up to 4 segments.
-// Assembles a per-clip activation from the shared video-level map and the per-clip edge frames.
-struct GatherParams {
-  uint4* dst; int64_t dst_bstride16, frame16;      // in 16-byte units
-  int nsegs;
-  const uint4* src[4]; int64_t src_bstride16[4]; int src_t0[4], dst_t0[4], first[5];   // first[k] = running frame count
-};
-
-__global__ void __launch_bounds__(256) frame_gather_kernel(const GatherParams g) {
-  int f = blockIdx.y, k = 0;
-  while (k + 1 < g.nsegs && f >= g.first[k + 1]) ++k;
-  f -= g.first[k];
-  const int64_t clip = blockIdx.z;
-  const uint4* __restrict__ src = g.src[k] + clip * g.src_bstride16[k] + (int64_t)(g.src_t0[k] + f) * g.frame16;
-  uint4* __restrict__ dst = g.dst + clip * g.dst_bstride16 + (int64_t)(g.dst_t0[k] + f) * g.frame16;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < g.frame16; i += (int64_t)gridDim.x * 256) dst[i] = __ldg(src + i);
-}
-
 }  // namespace
-
-int launch_frame_gather(void* dst, int64_t dst_batch_stride_bytes, int n, int64_t frame_bytes, const FrameGatherSeg* segs, int nsegs,
-                        cudaStream_t stream) {
-  CLASFV_REQUIRE(nsegs >= 1 && nsegs <= 4 && n >= 1 && frame_bytes % 16 == 0 && dst_batch_stride_bytes % 16 == 0, "frame_gather: bad argument");
-  GatherParams g;
-  g.dst = static_cast<uint4*>(dst); g.dst_bstride16 = dst_batch_stride_bytes / 16; g.frame16 = frame_bytes / 16; g.nsegs = nsegs;
-  int total = 0;
-  for (int k = 0; k < nsegs; ++k) {
-    CLASFV_REQUIRE(segs[k].src_batch_stride_bytes % 16 == 0 && segs[k].frames >= 1, "frame_gather: bad segment");
-    g.src[k] = static_cast<const uint4*>(segs[k].src); g.src_bstride16[k] = segs[k].src_batch_stride_bytes / 16;
-    g.src_t0[k] = segs[k].src_t0; g.dst_t0[k] = segs[k].dst_t0; g.first[k] = total; total += segs[k].frames;
-  }
-  g.first[nsegs] = total;
-  const int bx = (int)std::min<int64_t>(cdiv(g.frame16, 256 * 4), 64);
-  frame_gather_kernel<<<dim3((unsigned)bx, (unsigned)total, (unsigned)n), 256, 0, stream>>>(g);
-  CLASFV_CUDA(cudaGetLastError());
-  return CLASFV_OK;
-}
 
 int launch_conv_simt(const ConvArgs& a, cudaStream_t stream) {
   const ConvShape& s = a.s;

@@ -40,7 +40,8 @@ constexpr int UMMA_K = 16;
 constexpr int UMMA_THREADS = 320;         // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int EPI_WARPS = 8;
 constexpr int MAX_TAPS = 27;
-constexpr int MAX_VIEWS = 4;
+constexpr int MAX_VIEWS = 4;          // stride parities of one source
+constexpr int MAX_MAPS = 2 * MAX_VIEWS;   // second half: the same views of a frame-selected convolution's source B
 constexpr int SMEM_BUDGET = 222 * 1024;
 
 // Filter taps are organised in GROUPS that share one A slab.  A group is one TMA box load of the input
@@ -52,7 +53,7 @@ constexpr int SMEM_BUDGET = 222 * 1024;
 //   1x3x3 spatial,  stride 1 : 3 groups (kw) of 3 taps (kh), halo of 2 rows   (box bw x (bh+2), bt = bb = 1, bw % 8 == 0)
 //   anything else            : every tap its own group, no halo
 struct UmmaParams {
-  CUtensorMap tmap_a[MAX_VIEWS];
+  CUtensorMap tmap_a[MAX_MAPS];
   CUtensorMap tmap_b;
   int ngroups, ntaps, kslabs, k16_last;
   int8_t grp_view[MAX_TAPS], grp_dw[MAX_TAPS], grp_dh[MAX_TAPS], grp_dt[MAX_TAPS];
@@ -77,6 +78,11 @@ struct UmmaParams {
   const void* residual_b;
   int res_split, res_a_toff, res_b_toff;
   int64_t res_a_bstride, res_b_bstride;
+  // frame-selected input (see ConvArgs::FrameSel): tiles are single frames (bt == 1); input frame f = t0 * fsel_st of the
+  // virtual clip comes from map view + MAX_VIEWS * fsel_src[f] at frame coordinate fsel_idx[f]
+  int fsel_on, fsel_st;
+  int8_t grp_fsel[MAX_TAPS];
+  int8_t fsel_src[CLASFV_MAX_FSEL]; int16_t fsel_idx[CLASFV_MAX_FSEL];
 };
 
 // ------------------------------------------------------------------------------------ the kernel
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
   const int total_tiles = m_tiles * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
-    for (int v = 0; v < MAX_VIEWS; ++v) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a[v]) : "memory");
+    for (int v = 0; v < (p.fsel_on ? MAX_MAPS : MAX_VIEWS); ++v) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a[v]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
     for (int s = 0; s < p.nstages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
@@ -133,6 +139,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
       const int tw = p.tiles_w, th = p.tiles_h, tt = p.tiles_t, bw = p.bw, bh = p.bh, bt = p.bt, bb = p.bb, bn = p.bn;
       const int a_slab_bytes = p.a_slab_bytes, b_slab_bytes = p.b_slab_bytes, b_stage_slabs = p.b_stage_slabs, frame_bytes = p.frame_bytes;
       const int framewise = p.framewise, fw_split = p.fw_split, fw_a_toff = p.fw_a_toff, fw_b_toff = p.fw_b_toff;
+      const int fsel_on = p.fsel_on, fsel_st = p.fsel_st;
       const uint32_t tx = (uint32_t)p.a_tx_bytes + (resident ? 0u : (uint32_t)(tpg * b_slab_bytes));
       if (resident) {
         // the whole filter bank of this (single) N tile stays in shared memory for the life of the CTA
@@ -150,9 +157,13 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
         const int h0 = (mt % th) * bh; mt /= th;
         const int t0 = (mt % tt) * bt; mt /= tt;
         const int b0 = mt * bb;
+        // frame-selected input: this (single-frame) tile's input frame picks the source map and the frame coordinate
+        int fsel_map = 0, fsel_ct = 0;
+        if (fsel_on) { const int f = t0 * fsel_st; fsel_map = p.fsel_src[f] ? MAX_VIEWS : 0; fsel_ct = p.fsel_idx[f]; }
         for (int g = 0; g < ngroups; ++g) {
-          const CUtensorMap* map = &p.tmap_a[p.grp_view[g]];
-          const int cw = w0 + p.grp_dw[g], ch = h0 + p.grp_dh[g], ct = t0 + p.grp_dt[g];
+          const bool sel = fsel_on && p.grp_fsel[g];
+          const CUtensorMap* map = &p.tmap_a[p.grp_view[g] + (sel ? fsel_map : 0)];
+          const int cw = w0 + p.grp_dw[g], ch = h0 + p.grp_dh[g], ct = sel ? fsel_ct : t0 + p.grp_dt[g];
           int widx[3];
 #pragma unroll
           for (int j = 0; j < 3; ++j) widx[j] = (!resident && j < tpg) ? p.tap_widx[g * tpg + j] : 0;
@@ -505,11 +516,13 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   // sharing cuts the A traffic of the tap group 3x but constrains the box: keep it only while the MMA rows it fills stay
   // within 80 % of what the unconstrained tiling fills (a time-segmented input has no unshared form)
   double eff_none = 0.0;
-  { int w_, h_, t_, b_; choose_box(s.wo, s.ho, s.to, s.n, SHARE_NONE, unaligned_taps, &w_, &h_, &t_, &b_, &eff_none); }
+  { int w_, h_, t_, b_; choose_box(s.wo, s.ho, s.to, s.n, SHARE_NONE, unaligned_taps, &w_, &h_, &t_, &b_, &eff_none, a.fsel.on ? 1 : 0); }
+  CLASFV_REQUIRE(!a.fsel.on || (s.kt == 1 && s.pt == 0 && !a.seg.on && s.ti <= CLASFV_MAX_FSEL && a.fsel.b && a.fsel.a_t >= 1 && a.fsel.b_t >= 1),
+                 "conv_umma: a frame-selected input needs a convolution without temporal extent and a clip of at most %d frames", CLASFV_MAX_FSEL);
   for (int attempt = 0; attempt < 2; ++attempt) {
     mode = attempt == 0 ? want : SHARE_NONE;
     double eff = 0.0;
-    if (!choose_box(s.wo, s.ho, s.to, s.n, mode, unaligned_taps, &p.bw, &p.bh, &p.bt, &p.bb, &eff, a.seg.on ? s.to : 0)) continue;
+    if (!choose_box(s.wo, s.ho, s.to, s.n, mode, unaligned_taps, &p.bw, &p.bh, &p.bt, &p.bb, &eff, a.seg.on ? s.to : a.fsel.on ? 1 : 0)) continue;
     if (mode != SHARE_NONE && !a.seg.on && eff < 0.8 * eff_none) continue;
     const int rows_out = p.bw * p.bh * p.bt * p.bb;
     int slab_rows = rows_out, taps_per_group = 1;
@@ -588,6 +601,14 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   }
   p.grp_first[ng] = (int8_t)nt;
   p.ngroups = ng;
+  for (int g = 0; g < ng; ++g) p.grp_fsel[g] = (int8_t)(a.fsel.on && view_src[p.grp_view[g]] == 0 ? 1 : 0);
+  if (a.fsel.on) {
+    p.fsel_on = 1; p.fsel_st = s.st;
+    for (int f = 0; f < s.ti; ++f) {
+      CLASFV_REQUIRE(a.fsel.idx[f] >= 0 && a.fsel.idx[f] < (a.fsel.src[f] ? a.fsel.b_t : a.fsel.a_t), "conv_umma: frame table entry %d out of range", f);
+      p.fsel_src[f] = a.fsel.src[f]; p.fsel_idx[f] = a.fsel.idx[f];
+    }
+  }
   p.tpg = mode == SHARE_NONE ? 1 : 3;
   p.tap_step_rows = mode == SHARE_T ? p.bw * p.bh : mode == SHARE_H ? p.bw : 0;
   CLASFV_REQUIRE(nt == ntaps, "conv_umma: internal tap bookkeeping error");
@@ -613,7 +634,29 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
-  for (int v = 0; v < MAX_VIEWS && !a.seg.on; ++v) {
+  for (int v = 0; v < MAX_MAPS && a.fsel.on; ++v) {
+    // frame-selected source: per H/W parity view one map over source A (slots 0..3) and one over source B (slots 4..7);
+    // frames are addressed directly (no temporal stride in the map: tiles are single frames).  Views of `in2` keep the
+    // ordinary map in their slot of the first half and alias it in the second.
+    const int vv = (v % MAX_VIEWS) < nviews ? v % MAX_VIEWS : 0;
+    const bool is_b = v >= MAX_VIEWS && view_src[vv] == 0;
+    const int rh = view_rh[vv], rw = view_rw[vv], rt = view_rt[vv];
+    const uint64_t e = 2, frame = (uint64_t)s.hi * s.wi * s.cin;
+    uint64_t tt, tstride, bstride; const void* src;
+    if (view_src[vv] != 0) {                     // in2: ordinary strided clip
+      tt = (uint64_t)cdiv(s.ti - rt, s.st); tstride = (uint64_t)s.st * frame; bstride = (uint64_t)s.ti * frame; src = (const char*)a.in2 + (uint64_t)rt * frame * e;
+    } else if (is_b) {
+      tt = (uint64_t)a.fsel.b_t; tstride = frame; bstride = (uint64_t)a.fsel.b_batch_stride; src = a.fsel.b;
+    } else {
+      tt = (uint64_t)a.fsel.a_t; tstride = frame; bstride = a.in_batch_stride ? (uint64_t)a.in_batch_stride : frame * tt; src = a.in;
+    }
+    const uint64_t dims[5] = {(uint64_t)s.cin, (uint64_t)cdiv(s.wi - rw, s.sw), (uint64_t)cdiv(s.hi - rh, s.sh), tt, (uint64_t)s.n};
+    const uint64_t strides[4] = {(uint64_t)s.sw * s.cin * e, (uint64_t)s.sh * s.wi * s.cin * e, tstride * e, bstride * e};
+    char* basep = (char*)src + ((int64_t)rh * s.wi + rw) * s.cin * (int64_t)e;
+    int rc = encode_map(&p.tmap_a[v], basep, 5, dims, strides, boxa, fp16);
+    if (rc) return rc;
+  }
+  for (int v = 0; v < MAX_VIEWS && !a.seg.on && !a.fsel.on; ++v) {
     const int vv = v < nviews ? v : 0;          // unused slots alias view 0 so that prefetch.tensormap is harmless
     const int rt = view_rt[vv], rh = view_rh[vv], rw = view_rw[vv];
     const uint64_t dims[5] = {(uint64_t)s.cin, (uint64_t)cdiv(s.wi - rw, s.sw), (uint64_t)cdiv(s.hi - rh, s.sh),

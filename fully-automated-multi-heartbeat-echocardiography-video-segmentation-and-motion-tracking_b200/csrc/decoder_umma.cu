@@ -146,7 +146,7 @@ struct HeadGeom {
   int16_t xlo[4][MAX_TW], ylo[4][MAX_TH];   // first low-resolution column / row of the box of patch column tw / patch row th
 };
 
-struct HeadMaps { CUtensorMap g[4]; };
+struct HeadMaps { CUtensorMap g[4]; CUtensorMap g0_video; };   // g0_video: dense-video schedule only (HeadArgs::g0_video)
 
 struct Smem {                     // byte offsets from the 1024-aligned base
   static constexpr uint32_t W2B = 0;                      // 2 slabs of 64 x 128 B: W2 (K 0..63), then K 64..79 = {b2 hi, b2 lo, 0...}
@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   }
   if (tid == 0) {
     for (int v = 0; v < 4; ++v) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.g[v]) : "memory");
+    if (a.g0_video) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.g0_video) : "memory");
     for (int s = 0; s < 2; ++s) { mbar_init(bar(A_FULL, s), 1); mbar_init(bar(A_EMPTY, s), 1); }
     for (int s = 0; s < MAX_BSTAGES; ++s) { mbar_init(bar(B_FULL, s), 1); mbar_init(bar(B_EMPTY, s), 1); }
     for (int s = 0; s < 2; ++s) {
@@ -294,6 +295,8 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
       const int nb = g.nb, ntile = g.ntile, tiles_w = g.tiles_w;
       const uint32_t tx = (uint32_t)g.b_tx_bytes, stage_bytes = (uint32_t)g.b_stage_bytes;
       const uint32_t koff1 = (uint32_t)g.koff[1] * 128u, koff2 = (uint32_t)g.koff[2] * 128u, koff3 = (uint32_t)g.koff[3] * 128u;
+      const bool sel = a.g0_video != nullptr;
+      const int g0_lo = a.g0_lo, g0_hi = a.g0_hi, g0_step = a.g0_step;
       int stage = 0; uint32_t phase = 0;
       int ui = 0;
       for (int u = blockIdx.x; u < g.units; u += gridDim.x, ++ui) {
@@ -310,7 +313,10 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
           mbar_wait(bar(B_EMPTY, stage), phase ^ 1u);
           mbar_arrive_expect_tx(bar(B_FULL, stage), tx);
           const uint32_t dst = sbase + Smem::BBUF + (uint32_t)stage * stage_bytes;
-          tma_load_5d(dst, &maps.g[0], bar(B_FULL, stage), 0, x0, y0, t, clip);
+          // level 0 under the dense-video schedule: the clip's edge frames from its own map, the interior in place from
+          // the shared video-level map
+          if (sel && t >= g0_lo && t < g0_hi) tma_load_5d(dst, &maps.g0_video, bar(B_FULL, stage), 0, x0, y0, clip * g0_step + t, 0);
+          else tma_load_5d(dst, &maps.g[0], bar(B_FULL, stage), 0, x0, y0, (sel && t >= g0_hi) ? t - (g0_hi - g0_lo) : t, clip);
           tma_load_5d(dst + koff1, &maps.g[1], bar(B_FULL, stage), 0, x1, y1, t, clip);
           tma_load_5d(dst + koff2, &maps.g[2], bar(B_FULL, stage), 0, x2, y2, t, clip);
           tma_load_5d(dst + koff3, &maps.g[3], bar(B_FULL, stage), 0, x3, y3, t, clip);
@@ -604,14 +610,26 @@ int launch_head_umma(const HeadArgs& a, int num_sms, cudaStream_t stream) {
   CLASFV_REQUIRE(a.g_dtype == CLASFV_F16 && a.a_tab, "head_umma: fp16 lateral maps and the interpolation table are required");
   HeadGeom g;
   CLASFV_REQUIRE(head_geometry(a, &g), "head_umma: frame %d x %d is not supported (H %% 8, W %% 16, at most 512 x 512)", a.h, a.w);
-  for (int l = 0; l < 4; ++l) CLASFV_REQUIRE(a.tl[l] == a.t, "head_umma: level %d must be at the output's frame rate (temporal pre-pass)", l);
+  for (int l = 1; l < 4; ++l) CLASFV_REQUIRE(a.tl[l] == a.t, "head_umma: level %d must be at the output's frame rate (temporal pre-pass)", l);
+  CLASFV_REQUIRE(a.g0_video ? (a.g0_lo >= 0 && a.g0_hi >= a.g0_lo && a.g0_hi <= a.t && a.tl[0] == a.g0_lo + a.t - a.g0_hi &&
+                               (a.n - 1) * a.g0_step + a.t <= a.g0_video_t)
+                            : a.tl[0] == a.t, "head_umma: bad level-0 frame layout");
   HeadMaps maps;
+  memset(&maps, 0, sizeof(maps));
   for (int l = 0; l < 4; ++l) {
-    const uint64_t dims[5] = {(uint64_t)HC, (uint64_t)a.wl[l], (uint64_t)a.hl[l], (uint64_t)a.t, (uint64_t)a.n};
+    const uint64_t dims[5] = {(uint64_t)HC, (uint64_t)a.wl[l], (uint64_t)a.hl[l], (uint64_t)a.tl[l], (uint64_t)a.n};
     const uint64_t strides[4] = {(uint64_t)HC * 2, (uint64_t)a.wl[l] * HC * 2, (uint64_t)a.hl[l] * a.wl[l] * HC * 2,
-                                 (uint64_t)a.t * a.hl[l] * a.wl[l] * HC * 2};
+                                 (uint64_t)a.tl[l] * a.hl[l] * a.wl[l] * HC * 2};
     const uint32_t box[5] = {(uint32_t)HC, (uint32_t)g.nx[l], (uint32_t)g.ny[l], 1u, 1u};
     int rc = encode_tmap_16bit(&maps.g[l], const_cast<void*>(a.g[l]), 5, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  if (a.g0_video) {
+    const uint64_t dims[5] = {(uint64_t)HC, (uint64_t)a.wl[0], (uint64_t)a.hl[0], (uint64_t)a.g0_video_t, 1};
+    const uint64_t strides[4] = {(uint64_t)HC * 2, (uint64_t)a.wl[0] * HC * 2, (uint64_t)a.hl[0] * a.wl[0] * HC * 2,
+                                 (uint64_t)a.g0_video_t * a.hl[0] * a.wl[0] * HC * 2};
+    const uint32_t box[5] = {(uint32_t)HC, (uint32_t)g.nx[0], (uint32_t)g.ny[0], 1u, 1u};
+    int rc = encode_tmap_16bit(&maps.g0_video, const_cast<void*>(a.g0_video), 5, dims, strides, box, true);
     if (rc) return rc;
   }
   const size_t smem = 1024 + Smem::BBUF + (size_t)g.nb * g.b_stage_bytes;

@@ -39,6 +39,8 @@ inline cudaError_t allow_max_dynamic_smem(Kernel kernel) { return allow_max_dyna
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int CLASFV_MAX_FSEL = 64;      // longest virtual clip of a frame-selected convolution
+
 // One convolution on channels-last (N,T,H,W,C) activations.
 struct ConvShape {
   int n, ti, hi, wi, cin;      // cin, cout: stored (padded) channel counts
@@ -77,6 +79,16 @@ struct ConvArgs {
     int on, split, a_toff, b_toff;
     int64_t a_batch_stride; const void* b; int64_t b_batch_stride;
   } res;
+  // Frame-selected input of a convolution without temporal extent (kt == 1, pt == 0; fsel.on): the clip the convolution
+  // sees is VIRTUAL, s.ti frames long.  Its frame f is frame fsel.idx[f] of `in` (fsel.src[f] == 0; fsel.a_t frames per clip,
+  // in_batch_stride) or of fsel.b (fsel.src[f] == 1; fsel.b_t frames per clip, fsel.b_batch_stride).  Applies to `in` only
+  // (not to `in2`).  The dense-video trunk reads a clip's layer-1 output this way: edge frames from the clip's own
+  // buffer, interior frames in place from the shared video-level map (no assembled per-clip copy).
+  struct FrameSel {
+    int on, a_t, b_t;
+    const void* b; int64_t b_batch_stride;
+    int8_t src[CLASFV_MAX_FSEL]; int16_t idx[CLASFV_MAX_FSEL];
+  } fsel;
 };
 
 // CUDA-core implicit GEMM (both storage types).  conv_simt.cu
@@ -101,11 +113,6 @@ struct StemArgs {
 };
 int launch_stem(const StemArgs& a, cudaStream_t stream);
 
-// Frame gather (conv_simt.cu): dst[clip][dst_t0 + f] = src[clip][src_t0 + f], f < frames, for up to 4 segments
-struct FrameGatherSeg { const void* src; int64_t src_batch_stride_bytes; int src_t0, dst_t0, frames; };
-int launch_frame_gather(void* dst, int64_t dst_batch_stride_bytes, int n, int64_t frame_bytes, const FrameGatherSeg* segs, int nsegs,
-                        cudaStream_t stream);
-
 // Decoder head: 4-level trilinear (align_corners=True) gather-sum of the laterally projected feature
 // maps + bias + ReLU + 64x64 + ReLU + 6x64 heads + softmax / tanh.  decoder.cu
 struct HeadArgs {
@@ -115,6 +122,10 @@ struct HeadArgs {
   int n, t, h, w;
   const float* b1;             // [64]   folded comb_1 bias + BN1
   const float* w2;             // [64][64] folded comb_2 * BN2 scale, row = output channel
+  // tensor-core head, dense-video schedule: level 0 of clip c, frame t is g[0][c][t] for t < g0_lo, g[0][c][t - (g0_hi - g0_lo)]
+  // for t >= g0_hi (g[0] then holds tl[0] = g0_lo + t - g0_hi edge frames per clip), and frame c * g0_step + t of the
+  // video-level map g0_video (g0_video_t frames) in between.  g0_video == nullptr: g[0] holds whole clips.
+  const void* g0_video; int g0_lo, g0_hi, g0_step, g0_video_t;
   const void* a_tab;           // tensor-core head: interpolation matrices of the frame geometry (launch_head_table)
   int tail_f16;                // tensor-core head: comb_2 / head operands in fp16 (1) or bf16 (0)
   const float* b2;             // [64]
