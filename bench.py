@@ -4,14 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
+    python bench.py --workload long-video [--gpus N] ...      (BASELINE configs[4], see run_long_video)
+
 One "step" = one whole pass of the hot path over one synthetic video of BASELINE.json configs[1]
 (112x112, 200 frames, bf16): every stride-1 32-frame window (169 clips) through the R(2+1)D-18
 encoder + decoder heads, then warp-and-fuse into one (200,112,112) mask.  With N > 1 every rank
 processes its own video (videos shard across GPUs with no collective: weak scaling).
 
   value  fused frames/s with the video already resident in HBM (CUDA events, max over ranks)
-  e2e    the same through the public drop-in fuse_utils.segment_a_video_with_fusion(video, model,
-         fuse_method="warp"): pinned host video -> device, host mask back, every step
+  e2e    the same through the public API with HOST NumPy videos in and host int64 masks out, every step:
+         fuse_utils.segment_videos_with_fusion (the many-video form of segment_a_video_with_fusion(video, model,
+         fuse_method="warp"): pinned staging + copies overlapped with the neighbouring videos' compute); median of
+         three K-step brackets.  e2e.single_call is the one-video-at-a-time synchronous call.
+  fp16   the same two numbers in the fp16 tensor-core mode (same kernels; the 16-bit mode that meets the parity gates)
   roofline      trunk convolutions (tcgen05 implicit GEMM): algorithmic FLOP/s vs measured bf16 peak
   roofline_warp_fuse  the fusion kernel: algorithmic bytes/s vs measured HBM copy bandwidth
   cpu_baseline  the oracle (PyTorch CPU restatement of the reference path) on a bounded sample
@@ -47,11 +52,14 @@ ENCODER_GFLOP_PER_CLIP = 2 * 81.038
 KERNELS_PER_FORWARD = 42                           # stem + 40 convolutions + head
 
 
+TRAFFIC_FILE = "r02_dram_traffic_per_step.json"
+
+
 def ncu_traffic():
-    """DRAM bytes per bench step and kernel, from the committed ncu launch list of this workload
-    (profiles/r01_final_dram_traffic_per_step.json, written by tools/launch_list.sh + tools/launch_list_aggregate.py)."""
+    """DRAM bytes per bench step and kernel, from the committed ncu launch list of this workload and these kernels
+    (profiles/r02_dram_traffic_per_step.json, written by tools/launch_list.sh + tools/launch_list_aggregate.py)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_final_dram_traffic_per_step.json")) as f:
+        with open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)) as f:
             return json.load(f)["per_kernel"]
     except Exception:
         return {}
@@ -167,81 +175,52 @@ def workload_config():
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
-    ap.add_argument("--batch-clips", type=int, default=int(os.environ.get("CLASFV_BATCH_CLIPS", "64")))
-    ap.add_argument("--precision", default="bf16", choices=("bf16", "fp32"))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--per-clip", action="store_true", help="disable the dense-video schedule (every clip runs the whole trunk)")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        return run_reference_arm(args, rank)
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
 
+
+def measure_precision(args, precision, dev, rank, world, barrier, full):
+    """value (video resident, CUDA events) and e2e (public API, NumPy in / NumPy out) of one precision mode.  `full`: also the
+    stage profile, clocks and launch count (the primary mode)."""
+    import gc
+    import numpy as np
     import torch
-    import torch.distributed as dist
-    import clasfv_b200  # noqa: F401
     from clasfv_b200 import synthetic
     from clasfv_b200._lib import OUT_PROB
+    from clasfv_b200.engine import storage_dtype
     from clasfv_b200.src import fuse_utils
     from clasfv_b200.src.model.R2plus1D_18_MotionNet import R2plus1D_18_MotionNet
 
-    if not torch.cuda.is_available():
-        sys.exit("bench.py: no CUDA device - clasfv_b200 has no CPU path (use --impl reference for the CPU arm)")
-    if args.warmup < 3:
-        print("bench.py: note - fewer than 3 warm-up steps requested", file=sys.stderr)
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    net = R2plus1D_18_MotionNet(pretrained=False, precision=args.precision)
+    net = R2plus1D_18_MotionNet(pretrained=False, precision=precision)
     net.load_state_dict(synthetic.random_state_dict(0))
     net = net.to(dev).eval()
     eng = net.engine()
-    out_dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32
-
-    video_host = torch.from_numpy(synthetic.synthetic_echo_video(T_VIDEO, H, W, seed=rank)).pin_memory()
-    video = video_host.to(dev)
+    out_dtype = storage_dtype(precision)
+    videos_np = [synthetic.synthetic_echo_video(T_VIDEO, H, W, seed=2 * rank + i) for i in range(2)]     # host NumPy fp32 (3,T,H,W)
+    video = torch.from_numpy(videos_np[0]).to(dev)
     starts = list(range(N_CLIPS))
     prob = torch.empty((N_CLIPS, 2, CLIP, H, W), dtype=out_dtype, device=dev)
     mot = torch.empty((N_CLIPS, 4, CLIP, H, W), dtype=out_dtype, device=dev)
     bc = args.batch_clips
-
     eng.set_option("dense_video", 0 if args.per_clip else 1)
 
-    def step_resident():
-        eng.forward_windows(video, prob, mot, OUT_PROB, starts, CLIP, bc)
-        return eng.warp_fuse(prob, mot, starts, T_VIDEO)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # warm-up keeps the previous step's result alive while the next one is produced, exactly like the timed loop below:
-    # otherwise the second set of output buffers (acc 20 MB, mask, ...) is cudaMalloc'ed by torch's caching allocator inside
-    # the SECOND TIMED step, and that cudaMalloc stalls the stream for 20-60 ms in one run out of five (found with
-    # tools/bench_repeat.sh: the gap always sat in front of step 1's fusion kernel)
+    # otherwise the second set of output buffers is cudaMalloc'ed by torch's caching allocator inside the SECOND TIMED step
     res = None
     for _ in range(args.warmup):
-        res = step_resident()
+        eng.forward_windows(video, prob, mot, OUT_PROB, starts, CLIP, bc)
+        res = eng.warp_fuse(prob, mot, starts, T_VIDEO)
     barrier()
-    # Python's cyclic garbage collector is switched off inside the timed regions (as timeit does).
-    import gc
     gc.collect()
-    gc.disable()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    eng.profile_begin()
+    gc.disable()                          # Python's cyclic garbage collector is off inside the timed regions (as timeit does)
+    sampler = ClockSampler(dev.index)
+    if full:
+        sampler.start()
+        eng.profile_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fuse_events = []
+    launches0 = eng.launch_count()
     barrier()
     ev0.record()
     for _ in range(args.steps):
@@ -253,38 +232,120 @@ def main():
         fuse_events.append((fa, fb))
     ev1.record()
     barrier()
-    clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    stage_ms, calls = eng.profile_end()
-    stage_gflop = eng.last_profile_gflop
-    fuse_ms = sum(a.elapsed_time(b) for a, b in fuse_events) / len(fuse_events)
+    out = {"ms_total": ev0.elapsed_time(ev1), "launches": eng.launch_count() - launches0}
+    if full:
+        out["clocks"] = sampler.stop()
+        out["stage_ms"], _calls = eng.profile_end()
+        out["stage_gflop"] = eng.last_profile_gflop
+    out["fuse_ms_each"] = [a.elapsed_time(b) for a, b in fuse_events]
+    out["flow_px"] = float((mot.float().abs().mean() * (W / 2)).item())      # what the gather pattern of warp_fuse depends on
+    del res
 
-    flow_px = float((mot.float().abs().mean() * (W / 2)).item())      # what the gather pattern of warp_fuse depends on
-    # ---- e2e through the public API (pinned host video in, host mask out, every step)
-    mask = None
-    for _ in range(max(3, args.warmup)):          # keeps the previous result alive like the timed loop (second pinned buffer)
-        mask = fuse_utils.segment_a_video_with_fusion(video_host, net, fuse_method="warp", batch_clips=bc)
-    # two brackets of K steps each, the faster one is reported (both are in the JSON line): a single host-side hiccup
-    # (allocator growth, scheduler noise on the box's CPU) in a K-step bracket otherwise halves the number
-    brackets = []
-    for _ in range(2):
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            mask = fuse_utils.segment_a_video_with_fusion(video_host, net, fuse_method="warp", batch_clips=bc)
-        torch.cuda.synchronize()
-        brackets.append(time.perf_counter() - t0)
-    e2e_s = min(brackets)
+    # ---- e2e through the public API: host NumPy videos in, host int64 masks out, every step
+    def stream_of_videos(k):
+        return (videos_np[i % 2] for i in range(k))
+
+    def run_pipelined(k):
+        masks = 0
+        for m in fuse_utils.segment_videos_with_fusion(stream_of_videos(k), net, batch_clips=bc):
+            assert m.shape == (T_VIDEO, H, W) and m.dtype == np.int64
+            masks += 1
+        assert masks == k
+
+    def run_single(k):
+        for v in stream_of_videos(k):
+            m = fuse_utils.segment_a_video_with_fusion(v, net, fuse_method="warp", batch_clips=bc)
+        assert m.shape == (T_VIDEO, H, W) and m.dtype == np.int64
+
+    for fn, key in ((run_pipelined, "e2e_brackets"), (run_single, "single_brackets")):
+        fn(max(3, args.warmup))
+        br = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            fn(args.steps)
+            torch.cuda.synchronize()
+            br.append(time.perf_counter() - t0)
+        out[key] = br
     gc.enable()
-    assert mask.shape == (T_VIDEO, H, W)
-
-    times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([out["ms_total"], median(out["e2e_brackets"]) * 1e3, median(out["single_brackets"]) * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
+        import torch.distributed as dist
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(times[0]), float(times[1])
+    out["ms_total"], out["e2e_ms"], out["single_ms"] = (float(x) for x in times)
+    out["h2d_bytes"] = int(videos_np[0].nbytes)
+    out["d2h_bytes"] = int(T_VIDEO * H * W * 8)
+    return out
+
+
+def e2e_block(m, args, world):
+    fps = lambda ms: world * T_VIDEO * args.steps / (ms / 1e3)  # noqa: E731
+    return {"value": fps(m["e2e_ms"]), "unit": "frames/s", "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": m["d2h_bytes"],
+            "api": "fuse_utils.segment_videos_with_fusion(iterable of host NumPy (3,T,H,W) float32 videos, model) -> host int64 (T,H,W) masks; "
+                   "every video is staged through pinned memory, uploaded, segmented and its mask copied back inside the timed region",
+            "brackets_ms_per_step": [1e3 * t / args.steps for t in m["e2e_brackets"]], "reported": "median of three K-step brackets (max over ranks)",
+            "single_call": {"value": fps(m["single_ms"]), "api": "fuse_utils.segment_a_video_with_fusion(numpy_video, model, fuse_method='warp'), one "
+                            "synchronous call per step", "brackets_ms_per_step": [1e3 * t / args.steps for t in m["single_brackets"]]}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--workload", default="video", choices=("video", "long-video"))
+    ap.add_argument("--batch-clips", type=int, default=int(os.environ.get("CLASFV_BATCH_CLIPS", "192")))
+    ap.add_argument("--precision", default="bf16", choices=("bf16", "fp16", "fp32"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the fp16 measurement")
+    ap.add_argument("--per-clip", action="store_true", help="disable the dense-video schedule (every clip runs the whole trunk)")
+    ap.add_argument("--frames", type=int, default=2000, help="long-video workload: frames")
+    ap.add_argument("--size", type=int, default=224, help="long-video workload: frame height = width")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    import clasfv_b200  # noqa: F401
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device - clasfv_b200 has no CPU path (use --impl reference for the CPU arm)")
+    if args.warmup < 3:
+        print("bench.py: note - fewer than 3 warm-up steps requested", file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 or args.workload == "long-video":
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29631")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        else:
+            dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "long-video":
+        rc = run_long_video(args, dev, rank, world, barrier)
+        dist.destroy_process_group()
+        return rc
+
+    m = measure_precision(args, args.precision, dev, rank, world, barrier, full=True)
+    m16 = None
+    if args.precision == "bf16" and not args.no_secondary:
+        m16 = measure_precision(args, "fp16", dev, rank, world, barrier, full=False)
 
     if rank == 0:
         peaks = measured_peaks()
+        bc = args.batch_clips
+        ms_total, stage_ms, stage_gflop = m["ms_total"], m["stage_ms"], m["stage_gflop"]
+        fuse_ms = sum(m["fuse_ms_each"]) / len(m["fuse_ms_each"])
         ms_per_step = ms_total / args.steps
         value = world * T_VIDEO * args.steps / (ms_total / 1e3)
         trunk_ms_per_step = stage_ms["trunk"] / args.steps
@@ -292,56 +353,117 @@ def main():
         # once for the frames overlapping windows share); algorithmic = SURVEY 8(d)'s per-clip figure x clips
         performed_tflops = stage_gflop["trunk"] / args.steps / trunk_ms_per_step          # GFLOP/ms == TFLOP/s
         algorithmic_tflops = TRUNK_GFLOP_PER_CLIP * N_CLIPS / trunk_ms_per_step
-        achieved_tflops = performed_tflops
-        n_batches = (N_CLIPS + bc - 1) // bc
-        tr = ncu_traffic() if (not args.per_clip and bc == 64 and args.precision == "bf16") else {}
+        tr = ncu_traffic() if (not args.per_clip and bc >= N_CLIPS and args.precision == "bf16") else {}
         conv_traffic = (tr["conv_umma_kernel"]["dram_read_bytes"] + tr["conv_umma_kernel"]["dram_write_bytes"]) if "conv_umma_kernel" in tr else None
         wf_key = next((k for k in tr if k.startswith("warp_fuse_staged")), None)
         fuse_traffic = (tr[wf_key]["dram_read_bytes"] + tr[wf_key]["dram_write_bytes"]) if wf_key else None
-        # dense schedule: 10 video-level launches; per batch 14 edge convs + 2 gathers + 27 layer2-4 convs + 4 lateral + 3 temporal
-        # pre-pass + 1 head; + 1 fusion kernel per video (ncu launch list: profiles/r01y_launches_bench_steps1.csv)
-        launches_per_step = (n_batches * (KERNELS_PER_FORWARD + 3) if args.per_clip else 10 + n_batches * 51) + 1
-        elt = 2 if args.precision == "bf16" else 4
+        elt = 4 if args.precision == "fp32" else 2
         fuse_bytes = N_CLIPS * CLIP * H * W * 6 * elt + T_VIDEO * H * W * (8 + 1) + T_VIDEO * 8
         line = {
             "metric": "frames/sec segmented+tracked (fusion on)", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": dict(workload_config(), batch_clips=bc, parallelism=f"video-sharded x{world}, no collective"),
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "fp16", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "config": workload_config(),
+            "run_config": {"batch_clips": bc, "parallelism": f"video-sharded x{world}, no collective"},
             "clip_frames_per_s": world * N_CLIPS * CLIP * args.steps / (ms_total / 1e3),
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()} | {"warp_fuse": fuse_ms},
-            "warp_fuse_ms_each_step": [round(a.elapsed_time(b), 3) for a, b in fuse_events],
-            "e2e": {"value": world * T_VIDEO * args.steps / (e2e_ms / 1e3), "unit": "frames/s",
-                    "h2d_bytes_per_step": int(video_host.numel() * 4), "d2h_bytes_per_step": int(T_VIDEO * H * W * 8),
-                    "brackets_ms_per_step": [1e3 * t / args.steps for t in brackets], "reported": "faster of two K-step brackets (rank-local; max over ranks)"},
-            "gpu_launches": args.steps * launches_per_step,
+            "warp_fuse_ms_each_step": [round(x, 3) for x in m["fuse_ms_each"]],
+            "e2e": e2e_block(m, args, world),
+            "gpu_launches": m["launches"],
+            "gpu_launches_is": "kernels launched through the library handle inside the timed region of `value` (counted by the library: "
+                               "clasfv_launch_count), %d per step" % (m["launches"] // max(1, args.steps)),
             "roofline": {"kernel": "conv_umma_kernel (trunk: stem 3x1x1 + layer1-4)",
-                         "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peaks["bf16_tflops"], "traffic": conv_traffic,
-                         "traffic_is": "DRAM read+write bytes of all conv_umma_kernel launches of one step (ncu, profiles/"
-                                       "r01_final_dram_traffic_per_step.json); null with --per-clip or another batch size",
+                         "bound": "tensor", "achieved": performed_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": performed_tflops / peaks["bf16_tflops"], "traffic": conv_traffic,
+                         "traffic_is": "DRAM read+write bytes of all conv_umma_kernel launches of one step (ncu launch list of this "
+                                       "command and these kernels, profiles/" + TRAFFIC_FILE + "); null with --per-clip, another "
+                                       "batch size or another precision",
                          "peak_source": peaks["source"] + " (sustained; burst %.1f)" % peaks["bf16_tflops_burst"],
-                         "achieved_is": "performed FLOPs (2 x true MACs executed by the kernel) / trunk time",
+                         "achieved_is": "performed FLOPs (2 x true MACs executed by the kernel, counted per launch by the library) / "
+                                        "trunk time from CUDA events inside clasfv_forward",
                          "performed_gflop_per_step": stage_gflop["trunk"] / args.steps,
                          "algorithmic_gflop_per_clip": TRUNK_GFLOP_PER_CLIP,
                          "algorithmic_equivalent_tflops": algorithmic_tflops,
                          "schedule": "per-clip" if args.per_clip else
                                      "dense-video: stem+layer1 once per video frame, clip-edge frames per clip (bit-identical outputs)"},
-            "roofline_warp_fuse": {"kernel": "warp_fuse_kernel", "bound": "hbm", "achieved": fuse_bytes / (fuse_ms * 1e6),
+            "roofline_warp_fuse": {"kernel": "warp_fuse_staged_kernel", "bound": "hbm", "achieved": fuse_bytes / (fuse_ms * 1e6),
                                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fuse_bytes / (fuse_ms * 1e6) / peaks["hbm_gbs"],
-                                   "traffic": fuse_traffic, "algorithmic_bytes": fuse_bytes,
-                                   "traffic_note": "ncu --set full of the same kernel on configs[2] (256 clips): DRAM read+write / algorithmic "
-                                                   "bytes = 1.00 fp32, 0.99 bf16 (profiles/r01y_wf_ncu.csv); instruction-bound, see DESIGN.md 4.5"},
-            "clocks": clocks, "mean_abs_flow_px": flow_px,
+                                   "traffic": fuse_traffic, "algorithmic_bytes": fuse_bytes},
+            "clocks": m["clocks"], "mean_abs_flow_px": m["flow_px"],
         }
+        if m16 is not None:
+            v16 = world * T_VIDEO * args.steps / (m16["ms_total"] / 1e3)
+            line["fp16"] = {"note": "the same workload in the fp16 tensor-core mode (same kernels; 11 significant bits instead of 8): the "
+                                    "16-bit mode whose masks meet the north-star parity gates (tests/test_gpu_parity.py, DESIGN.md 5)",
+                            "value": v16, "ms_per_step": m16["ms_total"] / args.steps, "e2e": e2e_block(m16, args, world)}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_sample(4)
             line["cpu_baseline"] = {"value": cb["frames_per_s"], "unit": "frames/s", "cores": cb["threads"], "kind": "port",
+                                    "value_is": "EXTRAPOLATED: the sample's seconds per clip x 169 clips",
                                     "sample": "4 of 169 stride-1 clips (reference network restated on PyTorch CPU, "
                                               f"{cb['sec_per_clip_model']:.2f} s/clip) + oracle warp-fuse, scaled to the whole video"}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+def run_long_video(args, dev, rank, world, barrier):
+    """BASELINE configs[4]: ONE long video (default 2000 frames, 224 x 224: 1969 stride-1 clips) split by clip range across the
+    ranks, neighbour halo exchange of the partial class sums over NCCL (sharding.segment_long_video).  A step is the whole
+    video.  value: frames/s with the video resident on every GPU and the mask left on the device (gather=False);
+    e2e: the public call with the HOST video in and the host uint8 mask out on rank 0.  Strong scaling."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from clasfv_b200 import sharding, synthetic
+    from clasfv_b200.src.model.R2plus1D_18_MotionNet import R2plus1D_18_MotionNet
+    t, size = args.frames, args.size
+    net = R2plus1D_18_MotionNet(pretrained=False, precision=args.precision)
+    net.load_state_dict(synthetic.random_state_dict(0))
+    net = net.to(dev).eval()
+    video = synthetic.synthetic_echo_video(t, size, size, seed=3)
+    bc = min(args.batch_clips, 64 if size > 112 else 192)
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    video_dev = torch.from_numpy(video).to(dev)
+
+    def timed(fn, k):
+        ts = []
+        for _ in range(k):
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        x = torch.tensor(ts, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(x, op=dist.ReduceOp.MAX)
+        return [float(v) for v in x]
+
+    stage = {}
+    resident = lambda: sharding.segment_long_video(video_dev, net, batch_clips=bc, gather=False)      # noqa: E731
+    public = lambda: sharding.segment_long_video(video, net, batch_clips=bc, gather="rank0", timings=stage)  # noqa: E731
+    timed(resident, warm)
+    t_res = timed(resident, steps)
+    timed(public, warm)
+    stage.clear()
+    t_pub = timed(public, steps)
+    st = torch.tensor([stage.get(k, 0.0) / steps for k in ("upload", "forward", "fuse", "halo", "gather", "d2h")], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        n_clips = t - CLIP + 1
+        line = {"metric": "frames/sec segmented+tracked (fusion on)", "value": t / median(t_res), "unit": "frames/s", "n_gpus": world,
+                "steps": steps, "warmup": warm, "ms_per_step": 1e3 * median(t_res), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "fp16", "fp32": "f32"}[args.precision], "data": "synthetic",
+                "config": {"workload": f"configs[4]: one {t}-frame {size}x{size} video, {n_clips} stride-1 clips split by clip range across "
+                                       f"{world} rank(s), NCCL neighbour halo exchange of the partial class sums", "frames": t, "height": size,
+                           "width": size, "clips": n_clips, "batch_clips": bc, "parallelism": f"clip-range split x{world}, P2P halo"},
+                "e2e": {"value": t / median(t_pub), "unit": "frames/s", "h2d_bytes_per_step": int(video.nbytes), "d2h_bytes_per_step": int(t * size * size),
+                        "api": "sharding.segment_long_video(host NumPy video, model, gather='rank0') -> host uint8 mask on rank 0",
+                        "seconds_each": t_pub, "stage_seconds_max_over_ranks": dict(zip(("upload", "forward", "fuse", "halo", "gather", "d2h"), [float(x) for x in st]))},
+                "seconds_each_resident": t_res}
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     return 0
 
 

@@ -23,7 +23,7 @@ EXPORTS = (
     "clasfv_finalize", "clasfv_forward", "clasfv_workspace_bytes", "clasfv_warp", "clasfv_motion_field",
     "clasfv_warp_fuse", "clasfv_build_shift_clips", "clasfv_fuse_shift_votes", "clasfv_temporal_resample",
     "clasfv_conv3d", "clasfv_profile_begin", "clasfv_profile_end", "clasfv_finalize_mask",
-    "clasfv_set_option", "clasfv_profile_gflop", "clasfv_warp_mode", "clasfv_ingest_u8", "clasfv_decoder_head",
+    "clasfv_set_option", "clasfv_profile_gflop", "clasfv_warp_mode", "clasfv_ingest_u8", "clasfv_decoder_head", "clasfv_launch_count",
 )
 
 
@@ -85,6 +85,8 @@ def lib():
         l.clasfv_temporal_resample.argtypes = [vp, vp, i32, i32, i32, i64, vp]
         l.clasfv_conv3d.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32,
                                     i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp]
+        l.clasfv_launch_count.argtypes = [vp]
+        l.clasfv_launch_count.restype = i64
         l.clasfv_decoder_head.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
         for name in EXPORTS:
             getattr(l, name)                  # every declared symbol must resolve

@@ -118,6 +118,7 @@ struct clasfv_handle {
   int prof_calls = 0;
   int cur_stage = 0;
   double prof_gflop[4] = {0, 0, 0, 0};
+  int64_t launches = 0;        // kernels this handle has launched since it was created (clasfv_launch_count)
   // options (clasfv_set_option)
   int sub_batch = 32;          // clips per internal batch of clasfv_forward
   bool dense_video = true;     // share layer-1 work between overlapping windows of one video (bf16 tensor-core path)
@@ -243,6 +244,7 @@ int run_conv(clasfv_handle* h, const ConvArgs& a, cudaStream_t stream) {
   // CLASFV_CONV_TRACE=1: time every convolution on its own (stream drained before and after) and print one line per
   // launch to stderr - a development aid for finding the layers furthest from the roofline, never on in a measurement
   static const bool trace = getenv("CLASFV_CONV_TRACE") != nullptr;
+  ++h->launches;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (trace) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(stream); cudaEventRecord(e0, stream); }
   const int rc = (a.act_dtype != CLASFV_F32 && !h->force_simt) ? launch_conv_umma(a, h->num_sms, stream) : launch_conv_simt(a, stream);
@@ -267,6 +269,7 @@ int head_table(clasfv_handle* h, HeadArgs* ha, cudaStream_t stream) {
     CLASFV_REQUIRE(bytes > 0, "the tensor-core head does not tile a %d x %d frame (H %% 8, W %% 16, at most 512 x 512)", ha->h, ha->w);
     void* tab = nullptr;
     CLASFV_CUDA(cudaMalloc(&tab, bytes));
+    ++h->launches;
     const int rc = launch_head_table(*ha, tab, stream);
     if (rc) { cudaFree(tab); return rc; }
     it = h->head_tabs.emplace(std::make_pair(ha->h, ha->w), tab).first;
@@ -440,6 +443,7 @@ struct Forward {
     if (di) { ha.g0_video = di->g0_video; ha.g0_lo = D; ha.g0_hi = t - D; ha.g0_step = di->fs; ha.g0_video_t = di->tv_left; ha.tl[0] = 2 * D; }
     if (tc_head)
       for (int i = 1; i < 4; ++i) {
+        ++h->launches;
         if ((rc = launch_temporal_upsample_f16(ws + o_g[i], ws + o_gt[i], nb, T[i + 1], t, H[i + 1], W[i + 1], stream))) return rc;
         ha.g[i] = ws + o_gt[i]; ha.tl[i] = t;
       }
@@ -452,6 +456,7 @@ struct Forward {
     const size_t plane = (size_t)t * height * width * oes;
     ha.seg = seg + (size_t)c0 * 2 * plane; ha.motion = motion + (size_t)c0 * 4 * plane;
     ha.out_dtype = out_dtype; ha.out_kind = out_kind;
+    ++h->launches;
     if ((rc = tc_head ? launch_head_umma(ha, h->num_sms, stream) : launch_head(ha, stream))) return rc;
     return mark(3);
   }
@@ -503,6 +508,7 @@ struct Forward {
       sa.x = x; sa.clip_offset = static_cast<const int64_t*>(offs_dev); sa.channel_stride = channel_stride;
       sa.n = nb; sa.t = t; sa.h = height; sa.w = width; sa.weight = h->stem_w; sa.bias = h->stem_b; sa.out = ws + o_s0; sa.out_channels = STEM_MID_PAD; sa.out_dtype = act;
       if (fs) { sa.n = 1; sa.t = (int)((nb - 1) * fs + t); }
+      ++h->launches;
       if ((rc = launch_stem(sa, stream))) return rc;
       if ((rc = mark(0))) return rc;
       {
@@ -547,6 +553,7 @@ struct Forward {
     StemArgs sa;
     sa.x = x; sa.clip_offset = static_cast<const int64_t*>(offs_dev); sa.channel_stride = channel_stride;
     sa.n = 1; sa.t = tv; sa.h = height; sa.w = width; sa.weight = h->stem_w; sa.bias = h->stem_b; sa.out = ws + o_s0v; sa.out_channels = STEM_MID_PAD; sa.out_dtype = act;
+    ++h->launches;
     if ((rc = launch_stem(sa, stream))) return rc;
     if ((rc = mark(0))) return rc;
     const PackedConv* spat[6] = {nullptr, nullptr, &h->blocks[0][0].s1, &h->blocks[0][0].s2, &h->blocks[0][1].s1, &h->blocks[0][1].s2};
@@ -797,6 +804,7 @@ int clasfv_finalize(clasfv_handle* h, int precision) {
 }
 
 int64_t clasfv_workspace_bytes(const clasfv_handle* h) { return h ? (int64_t)h->ws_bytes : 0; }
+int64_t clasfv_launch_count(const clasfv_handle* h) { return h ? h->launches : 0; }
 
 int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_offset_host, int64_t channel_stride,
                    int n, int t, int height, int width, int out_kind, int out_dtype,
@@ -879,6 +887,7 @@ int clasfv_ingest_u8(clasfv_handle* h, const uint8_t* frames_dev, int t, int hei
   CLASFV_REQUIRE(t >= 1 && height0 >= 1 && width0 >= 1 && height >= 1 && width >= 1, "clasfv_ingest_u8: bad extent");
   DeviceGuard guard(h->device);
   if (!h->minmax) CLASFV_CUDA(cudaMalloc(&h->minmax, 6 * sizeof(uint32_t)));
+  h->launches += 2;
   return launch_ingest_u8(frames_dev, t, height0, width0, bgr ? 1 : 0, video_dev, height, width, h->minmax, static_cast<cudaStream_t>(stream_v));
 }
 
@@ -929,6 +938,7 @@ int clasfv_warp_fuse(clasfv_handle* h, const void* prob_dev, const void* motion_
   a.clip_start = static_cast<const int32_t*>(tab); a.frame_lo = a.clip_start + n_clips; a.frame_hi = a.frame_lo + t_out;
   a.n_clips = n_clips; a.clip_len = clip_len; a.t_out = t_out; a.h = height; a.w = width; a.edge_hops = edge_hops; a.accumulate = accumulate;
   a.acc = acc_dev; a.cnt = cnt_dev; a.mask = mask_dev; a.area = area_dev;
+  ++h->launches;
   return launch_warp_fuse(a, stream);
 }
 
@@ -973,6 +983,7 @@ int clasfv_build_shift_clips(clasfv_handle* h, const float* video_dev, int t, in
   ShiftTable tab; const int32_t* clip_shift = nullptr;
   int rc = upload_shift_table(h, n_shifts, shift_start_host, shift_len_host, shift_nclips_host, shift_clip_base_host, total, stream, &tab, &clip_shift);
   if (rc) return rc;
+  ++h->launches;
   return launch_build_shift_clips(video_dev, t, height, width, clip_len, n_shifts, total, clip_shift, tab, clips_dev, stream);
 }
 
@@ -991,6 +1002,7 @@ int clasfv_fuse_shift_votes(clasfv_handle* h, const void* prob_dev, int dtype, i
   ShiftTable tab;
   int rc = upload_shift_table(h, n_shifts, nullptr, shift_len_host, shift_nclips_host, shift_clip_base_host, total, stream, &tab, nullptr);
   if (rc) return rc;
+  ++h->launches;
   return launch_fuse_shift_votes(prob_dev, dtype, t, height, width, clip_len, step, n_shifts, tab, mask_dev, area_dev, stream);
 }
 
@@ -1072,6 +1084,7 @@ int clasfv_decoder_head(clasfv_handle* h, const void* g0_dev, const void* g1_dev
   ha.g_dtype = CLASFV_F16; ha.n = n; ha.t = t; ha.h = height; ha.w = width;
   ha.b1 = h->b1; ha.w2 = h->w2; ha.b2 = h->b2; ha.wh = h->wh; ha.bh = h->bh;
   ha.a_tab = nullptr; ha.tail_f16 = h->precision == CLASFV_F16 ? 1 : 0;
+  ha.g0_video = nullptr; ha.g0_lo = ha.g0_hi = ha.g0_step = ha.g0_video_t = 0;
   ha.seg = seg_dev; ha.motion = motion_dev; ha.out_dtype = out_dtype; ha.out_kind = out_kind;
   int rc = head_table(h, &ha, stream);
   if (rc) return rc;

@@ -169,6 +169,10 @@ class Engine:
         self.last_profile_gflop = {"stem": gf[0], "trunk": gf[1], "lateral": gf[2], "head": gf[3]}
         return {"stem": ms[0], "trunk": ms[1], "lateral": ms[2], "head": ms[3]}, calls.value
 
+    def launch_count(self):
+        """Kernels launched through this handle so far."""
+        return int(self.lib.clasfv_launch_count(self._h))
+
     def workspace_bytes(self):
         return int(self.lib.clasfv_workspace_bytes(self._h))
 

@@ -122,13 +122,38 @@ def exchange_partials(acc, cnt, window, owners, group=None, windows=None):
     return acc_own, cnt_own
 
 
-def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=32, group=None, gather=True):
+_stage = {}       # (device index, bytes) -> pinned staging buffer for a rank's frame range
+
+
+def _upload_frame_range(video, fa, fb, dev):
+    """video[:, fa:fb] of a host (3,T,H,W) array -> contiguous fp32 CUDA tensor through a reusable pinned buffer (a pageable
+    copy of a non-contiguous slice would be np.ascontiguousarray + a driver-staged transfer: ~4x slower at 224 x 224)."""
+    if isinstance(video, torch.Tensor) and video.is_cuda:
+        return video[:, fa:fb].to(device=dev, dtype=torch.float32).contiguous()
+    src = video if isinstance(video, torch.Tensor) else torch.from_numpy(video)
+    shape = (3, fb - fa) + tuple(src.shape[2:])
+    key = (dev.index, int(np.prod(shape)))
+    buf = _stage.get(key)
+    if buf is None:
+        _stage.clear()
+        buf = _stage[key] = torch.empty(int(np.prod(shape)), dtype=torch.float32, pin_memory=True)
+    host = buf.view(shape)
+    host.copy_(src[:, fa:fb])
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
+    out.copy_(host, non_blocking=True)
+    return out
+
+
+def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=64, group=None, gather=True, mask_dtype=np.uint8,
+                       timings=None):
     """One long video (3,T,H,W) split by clip range across the ranks of ``group`` (BASELINE config 5).
-    Every rank passes the same video; returns the full (T,H,W) int64 mask on every rank when ``gather``,
-    else (owned mask, (f0, f1))."""
+    Every rank passes the same host video.  ``gather``: True / "all" - the full (T,H,W) mask on every rank; "rank0" - on
+    rank 0 only (None elsewhere); False - (owned mask, (f0, f1)).  Masks are ``mask_dtype`` (uint8 by default: a 2000-frame
+    224 x 224 int64 mask is 800 MB of host traffic per rank; pass np.int64 for the reference's element type).
+    ``timings``: optional dict that receives the seconds of each stage measured with CUDA events on this rank."""
     from . import engine as _engine
     from ._lib import OUT_PROB
-    from .src.fuse_utils import _to_device_video, _unwrap
+    from .src.fuse_utils import _unwrap
     net = _unwrap(model)
     eng = net.engine()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -144,33 +169,75 @@ def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=32, gr
     from .engine import storage_dtype
     out_dtype = storage_dtype(eng.precision)
     dev = eng.device
+    cuda = dev.type == "cuda"
+    marks = []
+
+    def mark(name):
+        if timings is not None and cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
     if mine:
         # only the frames this rank's clips read go to its GPU (a 2000-frame 224x224 video is 1.2 GB as fp32)
         fa, fb = mine[0], mine[-1] + CLIP
-        v = _to_device_video(video[:, fa:fb], dev)
+        v = _upload_frame_range(video, fa, fb, dev)
+        mark("upload")
         prob = torch.empty((len(mine), 2, CLIP, h, w), dtype=out_dtype, device=dev)
         mot = torch.empty((len(mine), 4, CLIP, h, w), dtype=out_dtype, device=dev)
         eng.forward_windows(v, prob, mot, OUT_PROB, [s - fa for s in mine], CLIP, batch_clips)
+        mark("forward")
         res = eng.warp_fuse(prob, mot, [s - lo for s in mine], hi - lo, edge_hops=edge_hops, want_mask=False, want_area=False)
         acc, cnt = res["acc"], res["cnt"]
+        mark("fuse")
     else:
         acc = torch.zeros((0, 2, h, w), dtype=torch.float32, device=dev)
         cnt = torch.zeros((0,), dtype=torch.int32, device=dev)
     windows = [touched_window(starts[a:b], num_frames, edge_hops) for a, b in ranges]
     acc_own, cnt_own = exchange_partials(acc, cnt, (lo, hi), owners, group, windows=windows)
+    mark("halo")
     f0, f1 = owners[rank]
     if f1 > f0:
         mask, _area = _engine.finalize_mask(acc_own.contiguous())
     else:
         mask = torch.zeros((0, h, w), dtype=torch.uint8, device=dev)
+
+    def to_host(m):
+        host = torch.empty(m.shape, dtype=torch.uint8, pin_memory=cuda)
+        host.copy_(m, non_blocking=True)
+        if cuda:
+            torch.cuda.current_stream(dev).synchronize()
+        out = host.numpy()
+        return out if mask_dtype == np.uint8 else out.astype(mask_dtype)
+
+    def finish(result):
+        if timings is not None and cuda:
+            mark("end")
+            torch.cuda.current_stream(dev).synchronize()
+            for (_n0, e0), (n1, e1) in zip(marks, marks[1:]):
+                timings[n1] = timings.get(n1, 0.0) + e0.elapsed_time(e1) * 1e-3
+        return result
+
     if not gather:
-        return mask.cpu().numpy().astype(np.int64), (f0, f1)
-    # device-side gather of the owned masks (padded to the largest owned range), one host copy at the end
+        out = to_host(mask)
+        mark("d2h")
+        return finish((out, (f0, f1)))
+    # device-side gather of the owned uint8 masks (padded to the largest owned range), one host copy at the end
     most = max(b - a for a, b in owners)
     padded = torch.zeros((most, h, w), dtype=torch.uint8, device=dev)
     padded[:f1 - f0] = mask
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded, group=group)
+    if gather == "rank0":
+        parts = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
+        dist.gather(padded, parts, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    else:
+        parts = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(parts, padded, group=group)
+    mark("gather")
+    if parts is None:
+        return finish(None)
     full = torch.cat([p[:b - a] for p, (a, b) in zip(parts, owners)], 0)
     assert full.shape[0] == num_frames
-    return full.to(torch.int64).cpu().numpy()
+    out = to_host(full)
+    mark("d2h")
+    return finish(out)

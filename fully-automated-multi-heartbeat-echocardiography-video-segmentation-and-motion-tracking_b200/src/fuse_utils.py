@@ -116,7 +116,7 @@ def plan_shifts(num_frames, step=1, num_clips=10):
 
 
 def segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num_clips=10,
-                                fuse_method="simple", class_list=[0, 1], batch_clips=64, edge_hops=False,
+                                fuse_method="simple", class_list=[0, 1], batch_clips=192, edge_hops=False,
                                 return_details=False):
     net = _unwrap(model)
     eng = net.engine()
@@ -178,6 +178,118 @@ def segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num
     if return_details:
         return fused, {"area": area.cpu().numpy()[keep], "clips": total, "plan": plan, "prob": prob}
     return fused
+
+
+class _VideoPipeline:
+    """State of segment_videos_with_fusion: two pinned staging slots and two device video slots per (shape), one copy
+    stream; prob / motion planes of the video in flight are reused when consecutive videos have the same shape."""
+
+    def __init__(self, eng):
+        self.eng = eng
+        self.copy_stream = torch.cuda.Stream(device=eng.device)
+        self.stage = [None, None]
+        self.dev_video = [None, None]
+        self.uploaded = [None, None]         # event: the slot's last host->device copy (its pinned buffer is reusable after it)
+        self.consumed = [None, None]         # event: the compute that read the slot's device video has finished
+        self.planes = None
+
+    def upload(self, slot, video):
+        """host (3,T,H,W) float array -> device, on the copy stream; returns (device tensor, event)."""
+        src = video if isinstance(video, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(video))
+        if src.dim() != 4 or src.shape[0] != 3:
+            raise ClasfvError(f"expected a video of shape (3,T,H,W), got {tuple(src.shape)}")
+        n = src.numel()
+        if self.stage[slot] is None or self.stage[slot].numel() < n:
+            self.stage[slot] = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        if self.dev_video[slot] is None or self.dev_video[slot].numel() < n:
+            self.dev_video[slot] = torch.empty(n, dtype=torch.float32, device=self.eng.device)
+        host = self.stage[slot][:n].view(src.shape)
+        dev = self.dev_video[slot][:n].view(src.shape)
+        if self.uploaded[slot] is not None:
+            self.uploaded[slot].synchronize()    # the pinned buffer is still the source of an earlier copy until then
+        if not src.is_cuda:
+            host.copy_(src)                      # float64 / uint8 inputs are converted here
+        with torch.cuda.stream(self.copy_stream):
+            if self.consumed[slot] is not None:
+                self.copy_stream.wait_event(self.consumed[slot])   # the video that lived in this slot is no longer being read
+            dev.copy_(src if src.is_cuda else host, non_blocking=True)
+            ev = torch.cuda.Event(); ev.record()
+        self.uploaded[slot] = ev
+        return dev, ev, slot
+
+    def plane_buffers(self, n, h, w, dtype):
+        key = (n, h, w, dtype)
+        if self.planes is None or self.planes[0] != key:
+            self.planes = None               # release before allocating the next shape
+            dev = self.eng.device
+            self.planes = (key, torch.empty((n, 2, CLIP, h, w), dtype=dtype, device=dev), torch.empty((n, 4, CLIP, h, w), dtype=dtype, device=dev))
+        return self.planes[1], self.planes[2]
+
+
+def segment_videos_with_fusion(videos, model, step=1, batch_clips=192, edge_hops=False, return_details=False):
+    """Warp-and-fuse segmentation of MANY videos (BASELINE config 4; the many-video counterpart of
+    ``segment_a_video_with_fusion(video, model, fuse_method="warp")``, reference src/fuse_utils.py:36-102): a generator that
+    takes an iterable of host (3,T,H,W) float arrays and yields one (T,H,W) int64 mask per video, in order, identical to
+    the single-video call.  Host and device work overlap across videos: while video i is segmented, video i+1 is staged
+    through pinned memory and uploaded on a copy stream, and the mask of video i-1 travels back; every video still pays its
+    own host->device and device->host copy.  With ``return_details`` yields (mask, {"area": per-frame LV pixel count})."""
+    net = _unwrap(model)
+    eng = net.engine()
+    out_dtype = _engine.storage_dtype(eng.precision)
+    pipe = _VideoPipeline(eng)
+    main = torch.cuda.current_stream(eng.device)
+    it = iter(videos)
+
+    def start(slot, video):
+        return pipe.upload(slot, video)
+
+    def compute(dev_video, ready, slot):
+        main.wait_event(ready)
+        num_frames, h, w = int(dev_video.shape[1]), int(dev_video.shape[2]), int(dev_video.shape[3])
+        if num_frames < CLIP:
+            raise ClasfvError("warp fusion needs at least one full 32-frame clip")
+        starts = list(range(0, num_frames - CLIP + 1, step))
+        if starts[-1] != num_frames - CLIP:
+            starts.append(num_frames - CLIP)
+        prob, mot = pipe.plane_buffers(len(starts), h, w, out_dtype)
+        eng.forward_windows(dev_video, prob, mot, OUT_PROB, starts, CLIP, batch_clips)
+        res = eng.warp_fuse(prob, mot, starts, num_frames, edge_hops=edge_hops)
+        wide = res["mask"].to(torch.int64)
+        done = torch.cuda.Event(); done.record(main)
+        pipe.consumed[slot] = done
+        host = torch.empty(wide.shape, dtype=torch.int64, pin_memory=True)
+        area = torch.empty(res["area"].shape, dtype=torch.int32, pin_memory=True) if return_details else None
+        with torch.cuda.stream(pipe.copy_stream):
+            pipe.copy_stream.wait_event(done)
+            host.copy_(wide, non_blocking=True)
+            if area is not None:
+                area.copy_(res["area"], non_blocking=True)
+            wide.record_stream(pipe.copy_stream)
+            res["area"].record_stream(pipe.copy_stream)
+            back = torch.cuda.Event(); back.record()
+        return host, area, back
+
+    def finish(pending):
+        host, area, back = pending
+        back.synchronize()
+        return (host.numpy(), {"area": area.numpy()}) if return_details else host.numpy()
+
+    try:
+        nxt = start(0, next(it))
+    except StopIteration:
+        return
+    slot, pending = 0, None
+    while nxt is not None:
+        cur = nxt
+        out = compute(*cur)                         # enqueue video i on the main stream
+        try:
+            nxt = start(1 - slot, next(it))         # stage + upload video i+1 while the GPU works on video i
+        except StopIteration:
+            nxt = None
+        if pending is not None:
+            yield finish(pending)                   # mask of video i-1 (its copy overlapped video i's compute)
+        pending, slot = out, 1 - slot
+    yield finish(pending)
 
 
 # ------------------------------------------------------------------------------------------- EF (host)

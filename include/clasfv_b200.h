@@ -108,6 +108,9 @@ int clasfv_profile_gflop(clasfv_handle* h, double* stage_gflop_host /* [4] */);
 
 /* Largest workspace (bytes) the handle currently holds; informational. */
 int64_t clasfv_workspace_bytes(const clasfv_handle* h);
+/* Kernels launched through this handle since clasfv_create (every forward / fusion / ingest kernel; measurement support:
+ * bench.py reports the difference over its timed region as gpu_launches). */
+int64_t clasfv_launch_count(const clasfv_handle* h);
 
 /* ---- video ingest -----------------------------------------------------------------------------
  * Replaces the float pipeline of motion_segment.py:96-106 after the cv2 decode: frames_dev (T,H0,W0,3) uint8 (bgr != 0:
