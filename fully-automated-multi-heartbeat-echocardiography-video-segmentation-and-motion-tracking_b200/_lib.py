@@ -12,7 +12,7 @@ import subprocess
 import threading
 
 F32, BF16, F16 = 0, 1, 2
-OUT_LOGITS, OUT_PROB = 0, 1
+OUT_LOGITS, OUT_PROB, OUT_LVPROB = 0, 1, 2
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(CSRC, "libclasfv_b200.so")
@@ -72,7 +72,7 @@ def lib():
         l.clasfv_ingest_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]
         l.clasfv_warp_mode.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
         l.clasfv_motion_field.argtypes = [vp, vp, i32, i32, i32, vp]
-        l.clasfv_warp_fuse.argtypes = [vp, vp, vp, i32, C.POINTER(C.c_int32), i32, i32, i32, i32, i32, i32, i32,
+        l.clasfv_warp_fuse.argtypes = [vp, vp, i32, vp, i32, C.POINTER(C.c_int32), i32, i32, i32, i32, i32, i32, i32,
                                        vp, vp, vp, vp, vp]
         i32p = C.POINTER(C.c_int32)
         l.clasfv_build_shift_clips.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32p, i32p, i32p, i32p, vp, vp]

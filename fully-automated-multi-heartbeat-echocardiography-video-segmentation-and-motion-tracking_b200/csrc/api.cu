@@ -454,7 +454,7 @@ struct Forward {
     if (tc_head && (rc = head_table(h, &ha, stream))) return rc;
     const size_t oes = out_dtype == CLASFV_F32 ? 4 : 2;
     const size_t plane = (size_t)t * height * width * oes;
-    ha.seg = seg + (size_t)c0 * 2 * plane; ha.motion = motion + (size_t)c0 * 4 * plane;
+    ha.seg = seg + (size_t)c0 * (out_kind == CLASFV_OUT_LVPROB ? 1 : 2) * plane; ha.motion = motion + (size_t)c0 * 4 * plane;
     ha.out_dtype = out_dtype; ha.out_kind = out_kind;
     ++h->launches;
     if ((rc = tc_head ? launch_head_umma(ha, h->num_sms, stream) : launch_head(ha, stream))) return rc;
@@ -814,7 +814,7 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
   CLASFV_REQUIRE(x_dev && seg_dev && motion_dev, "clasfv_forward: null buffer");
   CLASFV_REQUIRE(n >= 1 && t >= 8 && t % 8 == 0 && height >= 16 && height % 16 == 0 && width >= 16 && width % 16 == 0,
                  "clasfv_forward: need N >= 1, T %% 8 == 0, H %% 16 == 0, W %% 16 == 0 (got N=%d T=%d H=%d W=%d)", n, t, height, width);
-  CLASFV_REQUIRE(out_kind == CLASFV_OUT_LOGITS || out_kind == CLASFV_OUT_PROB, "clasfv_forward: bad out_kind");
+  CLASFV_REQUIRE(out_kind == CLASFV_OUT_LOGITS || out_kind == CLASFV_OUT_PROB || out_kind == CLASFV_OUT_LVPROB, "clasfv_forward: bad out_kind");
   CLASFV_REQUIRE(out_dtype == CLASFV_F32 || out_dtype == CLASFV_BF16 || out_dtype == CLASFV_F16, "clasfv_forward: bad out_dtype");
   DeviceGuard guard(h->device);
   Forward f;
@@ -907,13 +907,14 @@ int clasfv_motion_field(const float* flow_dev, float* grid_dev, int n, int heigh
   return launch_motion_field(flow_dev, grid_dev, n, height, width, static_cast<cudaStream_t>(stream));
 }
 
-int clasfv_warp_fuse(clasfv_handle* h, const void* prob_dev, const void* motion_dev, int dtype,
+int clasfv_warp_fuse(clasfv_handle* h, const void* prob_dev, int prob_planes, const void* motion_dev, int dtype,
                      const int32_t* clip_start_host, int n_clips, int clip_len, int t_out, int height, int width,
                      int edge_hops, int accumulate, float* acc_dev, int32_t* cnt_dev, uint8_t* mask_dev,
                      int32_t* area_dev, void* stream_v) {
   CLASFV_REQUIRE(h && prob_dev && motion_dev && clip_start_host && acc_dev, "clasfv_warp_fuse: null argument");
   CLASFV_REQUIRE(dtype == CLASFV_F32 || dtype == CLASFV_BF16 || dtype == CLASFV_F16, "clasfv_warp_fuse: bad dtype");
   CLASFV_REQUIRE(n_clips >= 1 && clip_len >= 1 && t_out >= 1 && height >= 1 && width >= 1, "clasfv_warp_fuse: bad extent");
+  CLASFV_REQUIRE(prob_planes == 1 || prob_planes == 2, "clasfv_warp_fuse: prob_planes must be 1 (LV) or 2 (background, LV)");
   for (int c = 1; c < n_clips; ++c) CLASFV_REQUIRE(clip_start_host[c] >= clip_start_host[c - 1], "clasfv_warp_fuse: clip starts must ascend");
   DeviceGuard guard(h->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -934,7 +935,7 @@ int clasfv_warp_fuse(clasfv_handle* h, const void* prob_dev, const void* motion_
   }, &tab);
   if (rc) return rc;
   WarpFuseArgs a;
-  a.prob = prob_dev; a.motion = motion_dev; a.dtype = dtype;
+  a.prob = prob_dev; a.motion = motion_dev; a.dtype = dtype; a.prob_planes = prob_planes;
   a.clip_start = static_cast<const int32_t*>(tab); a.frame_lo = a.clip_start + n_clips; a.frame_hi = a.frame_lo + t_out;
   a.n_clips = n_clips; a.clip_len = clip_len; a.t_out = t_out; a.h = height; a.w = width; a.edge_hops = edge_hops; a.accumulate = accumulate;
   a.acc = acc_dev; a.cnt = cnt_dev; a.mask = mask_dev; a.area = area_dev;
@@ -1074,7 +1075,7 @@ int clasfv_decoder_head(clasfv_handle* h, const void* g0_dev, const void* g1_dev
   CLASFV_REQUIRE(h && g0_dev && g1_dev && g2_dev && g3_dev && seg_dev && motion_dev, "clasfv_decoder_head: null argument");
   if (!h->finalized || h->precision == CLASFV_F32) { set_error("clasfv_decoder_head: finalize the handle in a tensor-core precision first"); return CLASFV_ESTATE; }
   CLASFV_REQUIRE(n >= 1 && t >= 1 && height >= 16 && height % 16 == 0 && width >= 16 && width % 16 == 0, "clasfv_decoder_head: bad extent");
-  CLASFV_REQUIRE(out_kind == CLASFV_OUT_LOGITS || out_kind == CLASFV_OUT_PROB, "clasfv_decoder_head: bad out_kind");
+  CLASFV_REQUIRE(out_kind == CLASFV_OUT_LOGITS || out_kind == CLASFV_OUT_PROB || out_kind == CLASFV_OUT_LVPROB, "clasfv_decoder_head: bad out_kind");
   CLASFV_REQUIRE(out_dtype == CLASFV_F32 || out_dtype == CLASFV_BF16 || out_dtype == CLASFV_F16, "clasfv_decoder_head: bad out_dtype");
   DeviceGuard guard(h->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);

@@ -124,16 +124,21 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a, in
       for (int k = 0; k < 6; ++k) o[k] = fmaf(whs[k * HC + j], hj, o[k]);
     }
     float s0 = o[0], s1 = o[1];
-    if (a.out_kind == CLASFV_OUT_PROB) {
+    const bool lv_only = a.out_kind == CLASFV_OUT_LVPROB;
+    if (a.out_kind == CLASFV_OUT_PROB || lv_only) {
       const float mx = fmaxf(s0, s1);
       const float e0 = expf(s0 - mx), e1 = expf(s1 - mx);
       const float inv = 1.f / (e0 + e1);
       s0 = e0 * inv; s1 = e1 * inv;
     }
     const int64_t pix = (int64_t)h * a.w + w;
-    OutT* seg = static_cast<OutT*>(a.seg) + ((int64_t)n * 2 * a.t + t) * plane + pix;
-    put<OutT>(seg, s0);
-    put<OutT>(seg + (int64_t)a.t * plane, s1);
+    OutT* seg = static_cast<OutT*>(a.seg) + ((int64_t)n * (lv_only ? 1 : 2) * a.t + t) * plane + pix;
+    if (lv_only) {
+      put<OutT>(seg, s1);
+    } else {
+      put<OutT>(seg, s0);
+      put<OutT>(seg + (int64_t)a.t * plane, s1);
+    }
     OutT* mot = static_cast<OutT*>(a.motion) + ((int64_t)n * 4 * a.t + t) * plane + pix;
 #pragma unroll
     for (int k = 0; k < 4; ++k) put<OutT>(mot + (int64_t)k * a.t * plane, tanhf(o[2 + k]));

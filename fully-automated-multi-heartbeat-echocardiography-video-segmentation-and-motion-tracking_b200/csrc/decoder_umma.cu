@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int64_t plane = (int64_t)a.h * a.w;
     const int ntile = g.ntile, tiles_w = g.tiles_w;
-    const bool prob_out = a.out_kind == CLASFV_OUT_PROB;
+    const bool lv_only = a.out_kind == CLASFV_OUT_LVPROB, prob_out = a.out_kind == CLASFV_OUT_PROB || lv_only;
     float bias[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) bias[k] = bhs[k];
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
       const int clip = u / ntile, sp = u - clip * ntile;
       const int th = sp / tiles_w, tw = sp - th * tiles_w;
       const int64_t pix = (int64_t)(th * TILE_H + (vrow >> 4)) * a.w + tw * TILE_W + (vrow & 15);
-      OutT* seg = static_cast<OutT*>(a.seg) + (int64_t)clip * 2 * T * plane + pix;
+      OutT* seg = static_cast<OutT*>(a.seg) + (int64_t)clip * (lv_only ? 1 : 2) * T * plane + pix;
       OutT* mot = static_cast<OutT*>(a.motion) + (int64_t)clip * 4 * T * plane + pix;
       for (int t = 0; t < T; ++t, ++i) {
         const int s = i & 1; const uint32_t ph = (uint32_t)(i >> 1) & 1u;
@@ -490,8 +490,12 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
           s0 = d > 0.f ? lo : hi; s1 = d > 0.f ? hi : lo;
         }
         const int64_t fo = (int64_t)t * plane;
-        put<OutT>(seg + fo, s0);
-        put<OutT>(seg + fo + (int64_t)T * plane, s1);
+        if (lv_only) {
+          put<OutT>(seg + fo, s1);
+        } else {
+          put<OutT>(seg + fo, s0);
+          put<OutT>(seg + fo + (int64_t)T * plane, s1);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           float th;     // MUFU.TANH: relative error ~2^-11 (1.4e-3 px on a 3 px flow at 112 px), below the 16-bit storage noise upstream

@@ -201,20 +201,20 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
   const int i = valid ? pix / a.w : 0, j = valid ? pix % a.w : 0;
   const float base_x = linspace_pm1(j, a.w), base_y = linspace_pm1(i, a.h);
   const int L = a.clip_len;
-  const T* __restrict__ prob = static_cast<const T*>(a.prob);
+  // the LV plane of clip c (the last of its prob_planes class planes)
+  const T* __restrict__ prob = static_cast<const T*>(a.prob) + (int64_t)(a.prob_planes - 1) * L * hw;
   const T* __restrict__ mot = static_cast<const T*>(a.motion);
   float* acc = a.acc + (int64_t)g * 2 * hw;
-  float a0 = 0.f, a1 = 0.f;
-  if (a.accumulate && valid) { a0 = acc[pix]; a1 = acc[hw + pix]; }
+  float a1 = 0.f;          // LV votes of this call; what the accumulators already hold is added at the end
   int votes = 0;
   const int lo = __ldg(a.frame_lo + g), hi = __ldg(a.frame_hi + g);
   for (int c = lo; c < hi; ++c) {
     const int t = g - __ldg(a.clip_start + c);
-    const T* pc = prob + (int64_t)c * 2 * L * hw;
+    const T* pc = prob + (int64_t)c * a.prob_planes * L * hw;
     const T* mc = mot + (int64_t)c * 4 * L * hw;
     if (t >= 0 && t < L) {                                   // direct vote
       ++votes;
-      if (valid) { a0 += ldf<T>(pc + (int64_t)t * hw + pix); a1 += ldf<T>(pc + (int64_t)(L + t) * hw + pix); }
+      if (valid) a1 += ldf<T>(pc + (int64_t)t * hw + pix);
     }
     int ts = t - 1;                                          // forward hop: frame ts -> ts + 1 == t
     if (ts >= 0 && ts < L && (a.edge_hops || ts + 1 < L)) {
@@ -222,8 +222,7 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
       if (valid) {
         const float fx = ldf<T>(mc + (int64_t)ts * hw + pix), fy = ldf<T>(mc + (int64_t)(L + ts) * hw + pix);
         const Bilinear b = bilinear_setup_base(base_x, base_y, fx, fy, a.h, a.w);
-        a0 += bilinear_fetch<T>(pc + (int64_t)ts * hw, b, a.w);
-        a1 += bilinear_fetch<T>(pc + (int64_t)(L + ts) * hw, b, a.w);
+        a1 += bilinear_fetch<T>(pc + (int64_t)ts * hw, b, a.w);
       }
     }
     ts = t + 1;                                              // backward hop: frame ts -> ts - 1 == t
@@ -232,11 +231,13 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
       if (valid) {
         const float fx = ldf<T>(mc + (int64_t)(2 * L + ts) * hw + pix), fy = ldf<T>(mc + (int64_t)(3 * L + ts) * hw + pix);
         const Bilinear b = bilinear_setup_base(base_x, base_y, fx, fy, a.h, a.w);
-        a0 += bilinear_fetch<T>(pc + (int64_t)ts * hw, b, a.w);
-        a1 += bilinear_fetch<T>(pc + (int64_t)(L + ts) * hw, b, a.w);
+        a1 += bilinear_fetch<T>(pc + (int64_t)ts * hw, b, a.w);
       }
     }
   }
+  // background sum = votes - LV sum (class probabilities and bilinear weights each sum to one): only the LV plane is read
+  float a0 = __fsub_rn((float)votes, a1);
+  if (a.accumulate && valid) { a0 = __fadd_rn(acc[pix], a0); a1 = __fadd_rn(acc[hw + pix], a1); }
   const bool lv = valid && (a1 > a0);
   if (valid) {
     acc[pix] = a0; acc[hw + pix] = a1;
@@ -250,6 +251,11 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
 }
 
 // ------------------------------------------------------------------------------------------- F2, staged
+// Both kernels read ONLY the LV plane of every clip frame (north-star: "each clip's per-frame LV softmax
+// is warped"): the LV class sum is accumulated and the background sum is votes - LV sum, because the two class
+// probabilities and the four bilinear weights each sum to one.  That is 5 planes per clip frame instead of 6 and half the
+// taps and the staging; at 224 x 224 a 16-bit LV plane is 100 KB, so two ring units fit and the staged kernel runs there too.
+//
 // The same operator with the gather sources staged in shared memory.  warp_fuse_kernel above is bound by the
 // L1/LSU pipe (16 scattered global loads per clip and pixel); here a CTA owns one output frame g and one slice of
 // its pixels, and for every hop (clip c, source frame ts) landing on g a producer warp bulk-copies the two class
@@ -259,7 +265,8 @@ __global__ void __launch_bounds__(WF_THREADS) warp_fuse_kernel(const WarpFuseArg
 // order of additions per pixel is exactly warp_fuse_kernel's (clip by clip: direct, forward hop, backward hop), so
 // both kernels give bit-identical sums.  No float atomics, no intermediate warped volume.
 constexpr int WS_MAX_UNITS = 8;
-// CTA shape (measured, config 3, 256 clips, ms at zero / 4 px flow).  An item is a pair of adjacent pixels, loaded with one
+// CTA shape (measured in round 1 on the two-plane kernel, config 3, 256 clips, ms at zero / 4 px flow; re-measured in round 2 on
+// the LV-plane kernel: 512x7 0.63 / 0.66 fp32, 0.66 / 0.68 bf16; 768x5 the same; 1024x4 0.74 / 0.75 fp32, 0.86 / 0.88 bf16).  An item is a pair of adjacent pixels, loaded with one
 // instruction (8 bytes fp32, 4 bytes bf16).  512 threads x 7 pairs (128 registers, no spills worth the name, 14 independent
 // tap chains per thread) is the best shape for both element types:
 //   fp32   512x7 0.80 / 0.96    384x9 0.85 / 0.98    768x5 0.94 / 1.09
@@ -361,12 +368,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
   const int hw = a.h * a.w;
   const int L = a.clip_len;
   const uint32_t plane_bytes = (uint32_t)hw * (uint32_t)sizeof(T);
-  const uint32_t unit_bytes = 2u * plane_bytes;
+  const uint32_t unit_bytes = plane_bytes;                  // one ring unit = the LV plane of one hop's source frame
   const uint32_t sbase = smem_u32(ws_smem);
   const uint32_t bar0 = sbase + (uint32_t)n_units * unit_bytes;         // full[u] at bar0 + 8u, empty[u] at bar0 + 8(n_units + u)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const T* __restrict__ prob = static_cast<const T*>(a.prob);
+  const T* __restrict__ prob = static_cast<const T*>(a.prob) + (int64_t)(a.prob_planes - 1) * L * hw;     // LV planes
   const T* __restrict__ mot = static_cast<const T*>(a.motion);
+  const int64_t clip_elems = (int64_t)a.prob_planes * L * hw;
   const int lo = __ldg(a.frame_lo + g), hi = __ldg(a.frame_hi + g);
 
   if (threadIdx.x == 0) {
@@ -381,7 +389,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
       int item = 0;
       for (int c = lo; c < hi; ++c) {
         const int t = g - __ldg(a.clip_start + c);
-        const T* pc = prob + (int64_t)c * 2 * L * hw;
+        const T* pc = prob + (int64_t)c * clip_elems;
         for (int hop = 0; hop < 2; ++hop) {
           const int ts = hop == 0 ? t - 1 : t + 1;
           const bool on = ts >= 0 && ts < L && (a.edge_hops || (hop == 0 ? ts + 1 < L : ts >= 1));
@@ -392,8 +400,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
           const uint32_t dst = sbase + (uint32_t)u * unit_bytes;
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                        ::"r"(dst), "l"(pc + (int64_t)ts * hw), "r"(plane_bytes), "r"(bar0 + 8u * u) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(dst + plane_bytes), "l"(pc + (int64_t)(L + ts) * hw), "r"(plane_bytes), "r"(bar0 + 8u * u) : "memory");
           ++item;
         }
       }
@@ -421,7 +427,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
     // items past the slice end are simply not there: n_items is the same for all but the last lanes of a slice
     const int n_items = p0 < pix_end ? min(ITEMS, (pix_end - p0 + ITEM_STEP - 1) / ITEM_STEP) : 0;
     float bx[ITEMS][PP], by[ITEMS];
-    float s0[ITEMS][PP], s1[ITEMS][PP];
+    float s1[ITEMS][PP];                                      // LV votes of this call
     float* acc = a.acc + (int64_t)g * 2 * hw;
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
@@ -430,25 +436,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
       const int i = on ? p / a.w : 0, j = on ? p % a.w : 0;     // PP == 2: W is even, a pair never straddles rows
       by[k] = linspace_pm1(i, a.h);
 #pragma unroll
-      for (int q = 0; q < PP; ++q) { bx[k][q] = linspace_pm1(j + q < a.w ? j + q : j, a.w); s0[k][q] = 0.f; s1[k][q] = 0.f; }
-      if (a.accumulate && on) { Item<T>::ld_acc(acc + p, s0[k]); Item<T>::ld_acc(acc + hw + p, s1[k]); }
+      for (int q = 0; q < PP; ++q) { bx[k][q] = linspace_pm1(j + q < a.w ? j + q : j, a.w); s1[k][q] = 0.f; }
     }
+    int votes = 0;
     const TapGeom geom(a.h, a.w);
     int item = 0;
     for (int c = lo; c < hi; ++c) {
       const int t = g - __ldg(a.clip_start + c);
-      const T* pc = prob + (int64_t)c * 2 * L * hw + p0;
+      const T* pc = prob + (int64_t)c * clip_elems + p0;
       const T* mc = mot + (int64_t)c * 4 * L * hw + p0;
       if (t >= 0 && t < L) {                                   // direct vote
-        const T* d0 = pc + (int64_t)t * hw;
-        const T* d1 = pc + (int64_t)(L + t) * hw;
+        const T* d1 = pc + (int64_t)t * hw;
+        ++votes;
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
           if (k >= n_items) break;
-          float v0[PP], v1[PP];
-          Item<T>::ld(d0 + k * ITEM_STEP, v0); Item<T>::ld(d1 + k * ITEM_STEP, v1);
+          float v1[PP];
+          Item<T>::ld(d1 + k * ITEM_STEP, v1);
 #pragma unroll
-          for (int q = 0; q < PP; ++q) { s0[k][q] += v0[q]; s1[k][q] += v1[q]; }
+          for (int q = 0; q < PP; ++q) s1[k][q] += v1[q];
         }
       }
 #pragma unroll
@@ -456,6 +462,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
         const int ts = hop == 0 ? t - 1 : t + 1;
         const bool on = ts >= 0 && ts < L && (a.edge_hops || (hop == 0 ? ts + 1 < L : ts >= 1));
         if (!on) continue;
+        ++votes;
         const T* fxp = mc + (int64_t)((hop == 0 ? 0 : 2 * L) + ts) * hw;
         const T* fyp = mc + (int64_t)((hop == 0 ? L : 3 * L) + ts) * hw;
         float fx[ITEMS][PP], fy[ITEMS][PP];
@@ -464,15 +471,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
           if (k < n_items) { Item<T>::ld(fxp + k * ITEM_STEP, fx[k]); Item<T>::ld(fyp + k * ITEM_STEP, fy[k]); }
         const int u = item % n_units; const uint32_t ph = (uint32_t)(item / n_units) & 1u;
         mbar_wait(bar0 + 8u * u, ph);
-        const T* u0 = reinterpret_cast<const T*>(ws_smem + (size_t)u * unit_bytes);
-        const T* u1 = u0 + hw;
+        const T* u1 = reinterpret_cast<const T*>(ws_smem + (size_t)u * unit_bytes);
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
           if (k >= n_items) break;
 #pragma unroll
           for (int q = 0; q < PP; ++q) {
             const Taps ta = taps_setup(bx[k][q], by[k], fx[k][q], fy[k][q], geom);
-            s0[k][q] += taps_fetch<T>(u0, ta, a.w);
             s1[k][q] += taps_fetch<T>(u1, ta, a.w);
           }
         }
@@ -486,11 +491,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
     for (int k = 0; k < ITEMS; ++k) {
       if (k >= n_items) break;
       const int p = p0 + k * ITEM_STEP;
-      Item<T>::st_acc(acc + p, s0[k]);
+      // background sum = votes - LV sum; previous content added last (the same expressions as warp_fuse_kernel: same bits)
+      float s0[PP];
+#pragma unroll
+      for (int q = 0; q < PP; ++q) s0[q] = __fsub_rn((float)votes, s1[k][q]);
+      if (a.accumulate) {
+        float o0[PP], o1[PP];
+        Item<T>::ld_acc(acc + p, o0); Item<T>::ld_acc(acc + hw + p, o1);
+#pragma unroll
+        for (int q = 0; q < PP; ++q) { s0[q] = __fadd_rn(o0[q], s0[q]); s1[k][q] = __fadd_rn(o1[q], s1[k][q]); }
+      }
+      Item<T>::st_acc(acc + p, s0);
       Item<T>::st_acc(acc + hw + p, s1[k]);
       int m[PP];
 #pragma unroll
-      for (int q = 0; q < PP; ++q) { m[q] = s1[k][q] > s0[k][q] ? 1 : 0; lv_count += m[q]; }
+      for (int q = 0; q < PP; ++q) { m[q] = s1[k][q] > s0[q] ? 1 : 0; lv_count += m[q]; }
       if (a.mask) Item<T>::st_mask(a.mask + (int64_t)g * hw + p, m);
     }
     if (a.area) {
@@ -648,7 +663,7 @@ int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
   {
     const int64_t hw = (int64_t)a.h * a.w;
     const size_t es = a.dtype == CLASFV_F32 ? 4 : 2;
-    const size_t unit = 2 * (size_t)hw * es;
+    const size_t unit = (size_t)hw * es;
     const size_t budget = 225 * 1024;
     int units = (int)std::min<size_t>((budget - 16 * WS_MAX_UNITS) / unit, (size_t)WS_MAX_UNITS);
     static const bool no_staged = getenv("CLASFV_WARP_FUSE_DIRECT") != nullptr;

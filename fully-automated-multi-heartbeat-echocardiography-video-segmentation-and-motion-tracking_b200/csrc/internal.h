@@ -149,6 +149,7 @@ int launch_warp(const float* src, const float* flow, float* out, int n, int c, i
 int launch_motion_field(const float* flow, float* grid, int n, int h, int w, cudaStream_t s);
 struct WarpFuseArgs {
   const void* prob; const void* motion; int dtype;
+  int prob_planes;             // class planes per clip in `prob`: 2 (background, LV) or 1 (LV only); the LV plane is the last
   const int32_t* clip_start;   // device [n_clips]
   const int32_t* frame_lo;     // device [t_out]   first candidate clip for the frame
   const int32_t* frame_hi;     // device [t_out]   one past the last candidate clip

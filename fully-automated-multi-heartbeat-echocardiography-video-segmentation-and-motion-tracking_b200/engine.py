@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BF16, F16, F32, OUT_LOGITS, OUT_PROB, ClasfvError, check
+from ._lib import BF16, F16, F32, OUT_LOGITS, OUT_LVPROB, OUT_PROB, ClasfvError, check
 
 
 def precision_code(precision):
@@ -95,7 +95,7 @@ class Engine:
                 raise ClasfvError("clip window outside the video")
             offs = _lib.i64_array([int(s) * h * w for s in clip_starts])
             ch_stride = tv * h * w
-        seg = torch.empty((n, 2, t, h, w), dtype=out_dtype, device=x.device)
+        seg = torch.empty((n, 1 if out_kind == OUT_LVPROB else 2, t, h, w), dtype=out_dtype, device=x.device)
         mot = torch.empty((n, 4, t, h, w), dtype=out_dtype, device=x.device)
         if n == 0:
             return seg, mot
@@ -115,6 +115,7 @@ class Engine:
             offs = _lib.i64_array([int(s) * h * w for s in clip_starts])
             ch_stride = tv * h * w
         assert seg.is_contiguous() and mot.is_contiguous() and seg.shape[0] == n and mot.shape[0] == n
+        assert seg.shape[1] == (1 if out_kind == OUT_LVPROB else 2), "OUT_LVPROB writes one class plane, the other kinds two"
         check(self.lib.clasfv_forward(self._h, x.data_ptr(), offs, ch_stride, n, t, h, w, out_kind,
                                       _lib.torch_dtype_code(seg.dtype), seg.data_ptr(), mot.data_ptr(),
                                       _lib.current_stream_ptr(x.device)), "clasfv_forward")
@@ -179,11 +180,12 @@ class Engine:
     # ------------------------------------------------------------------ fusion
     def warp_fuse(self, prob, motion, clip_starts, num_frames, edge_hops=False, acc=None, accumulate=False,
                   want_mask=True, want_area=True, cnt=None):
-        """F2 (oracle/fuse_ref.py:warp_fuse). Returns dict(acc, cnt, mask, area)."""
+        """F2 (oracle/fuse_ref.py:warp_fuse). prob (n,2,L,H,W) class probabilities or (n,1,L,H,W) the LV probability alone.
+        Returns dict(acc, cnt, mask, area)."""
         _lib.require_cuda(prob, "prob"); _lib.require_cuda(motion, "motion")
         n, c, clip_len, h, w = prob.shape
-        if c != 2 or tuple(motion.shape) != (n, 4, clip_len, h, w) or motion.dtype != prob.dtype:
-            raise ClasfvError("warp_fuse: prob must be (n,2,L,H,W) and motion (n,4,L,H,W) of the same dtype")
+        if c not in (1, 2) or tuple(motion.shape) != (n, 4, clip_len, h, w) or motion.dtype != prob.dtype:
+            raise ClasfvError("warp_fuse: prob must be (n,2,L,H,W) or (n,1,L,H,W) and motion (n,4,L,H,W) of the same dtype")
         if len(clip_starts) != n:
             raise ClasfvError("warp_fuse: one start per clip")
         dev = prob.device
@@ -194,7 +196,7 @@ class Engine:
             cnt = torch.zeros((num_frames,), dtype=torch.int32, device=dev)
         mask = torch.empty((num_frames, h, w), dtype=torch.uint8, device=dev) if want_mask else None
         area = torch.empty((num_frames,), dtype=torch.int32, device=dev) if want_area else None
-        check(self.lib.clasfv_warp_fuse(self._h, prob.data_ptr(), motion.data_ptr(), _lib.torch_dtype_code(prob.dtype),
+        check(self.lib.clasfv_warp_fuse(self._h, prob.data_ptr(), c, motion.data_ptr(), _lib.torch_dtype_code(prob.dtype),
                                         _lib.i32_array(clip_starts), n, clip_len, num_frames, h, w,
                                         1 if edge_hops else 0, 1 if accumulate else 0, acc.data_ptr(), cnt.data_ptr(),
                                         mask.data_ptr() if mask is not None else None,

@@ -122,26 +122,60 @@ def exchange_partials(acc, cnt, window, owners, group=None, windows=None):
     return acc_own, cnt_own
 
 
-_stage = {}       # (device index, bytes) -> pinned staging buffer for a rank's frame range
+_stage = {}       # (device index, elements) -> pinned staging buffer for a rank's frame range
+_copy_streams = {}
 
 
-def _upload_frame_range(video, fa, fb, dev):
-    """video[:, fa:fb] of a host (3,T,H,W) array -> contiguous fp32 CUDA tensor through a reusable pinned buffer (a pageable
-    copy of a non-contiguous slice would be np.ascontiguousarray + a driver-staged transfer: ~4x slower at 224 x 224)."""
-    if isinstance(video, torch.Tensor) and video.is_cuda:
-        return video[:, fa:fb].to(device=dev, dtype=torch.float32).contiguous()
-    src = video if isinstance(video, torch.Tensor) else torch.from_numpy(video)
-    shape = (3, fb - fa) + tuple(src.shape[2:])
-    key = (dev.index, int(np.prod(shape)))
-    buf = _stage.get(key)
-    if buf is None:
-        _stage.clear()
-        buf = _stage[key] = torch.empty(int(np.prod(shape)), dtype=torch.float32, pin_memory=True)
-    host = buf.view(shape)
-    host.copy_(src[:, fa:fb])
-    out = torch.empty(shape, dtype=torch.float32, device=dev)
-    out.copy_(host, non_blocking=True)
-    return out
+class _FrameRangeUpload:
+    """video[:, fa:fb] of a host (3,T,H,W) array -> a contiguous fp32 CUDA tensor, chunk by chunk: a few host threads copy
+    frame chunks into a reusable pinned buffer (a strided 600 MB copy on one thread runs at ~6 GB/s, and torchrun pins
+    OMP_NUM_THREADS to 1), every chunk's transfer is enqueued on a copy stream as soon as it is staged, and
+    ``ready(frame)`` returns the event after which all frames below ``frame`` are on the device - so the first clips of
+    the range are segmented while the rest of the range is still in flight."""
+
+    def __init__(self, video, fa, fb, dev):
+        self.n = fb - fa
+        shape = (3, self.n) + tuple(video.shape[2:])
+        self.out = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.events = []                                         # (frames on the device so far, event)
+        if isinstance(video, torch.Tensor) and video.is_cuda:
+            self.out.copy_(video[:, fa:fb])
+            self.pending = None
+            return
+        src = video if isinstance(video, torch.Tensor) else torch.from_numpy(video)
+        key = (dev.index, int(np.prod(shape)))
+        buf = _stage.get(key)
+        if buf is None:
+            _stage.clear()
+            buf = _stage[key] = torch.empty(int(np.prod(shape)), dtype=torch.float32, pin_memory=True)
+        self.host = buf.view(shape)
+        self.stream = _copy_streams.setdefault(dev.index, torch.cuda.Stream(device=dev))
+        self.stream.wait_stream(torch.cuda.current_stream(dev))      # the previous call's reads of the staging area are done
+        chunk = max(8, -(-self.n // 16))
+        pieces = [(a, min(self.n, a + chunk)) for a in range(0, self.n, chunk)]
+
+        def stage(piece):
+            a, b = piece
+            self.host[:, a:b].copy_(src[:, fa + a:fa + b])
+            return piece
+
+        from concurrent.futures import ThreadPoolExecutor
+        self.pool = ThreadPoolExecutor(max_workers=4)
+        self.pending = [self.pool.submit(stage, p) for p in pieces]
+
+    def ready(self, frame):
+        """Event after which frames [0, frame) of the range are on the device (None: already there)."""
+        if self.pending is None:
+            return None
+        while self.pending and (not self.events or self.events[-1][0] < frame):
+            a, b = self.pending.pop(0).result()
+            with torch.cuda.stream(self.stream):
+                self.out[:, a:b].copy_(self.host[:, a:b], non_blocking=True)
+                ev = torch.cuda.Event(); ev.record()
+            self.events.append((b, ev))
+        if not self.pending:
+            self.pool.shutdown(wait=False)
+        return next(ev for upto, ev in self.events if upto >= frame)
 
 
 def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=64, group=None, gather=True, mask_dtype=np.uint8,
@@ -152,7 +186,7 @@ def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=64, gr
     224 x 224 int64 mask is 800 MB of host traffic per rank; pass np.int64 for the reference's element type).
     ``timings``: optional dict that receives the seconds of each stage measured with CUDA events on this rank."""
     from . import engine as _engine
-    from ._lib import OUT_PROB
+    from ._lib import OUT_LVPROB
     from .src.fuse_utils import _unwrap
     net = _unwrap(model)
     eng = net.engine()
@@ -182,11 +216,21 @@ def segment_long_video(video, model, step=1, edge_hops=False, batch_clips=64, gr
     if mine:
         # only the frames this rank's clips read go to its GPU (a 2000-frame 224x224 video is 1.2 GB as fp32)
         fa, fb = mine[0], mine[-1] + CLIP
-        v = _upload_frame_range(video, fa, fb, dev)
-        mark("upload")
-        prob = torch.empty((len(mine), 2, CLIP, h, w), dtype=out_dtype, device=dev)
+        up = _FrameRangeUpload(video, fa, fb, dev)
+        v = up.out
+        prob = torch.empty((len(mine), 1, CLIP, h, w), dtype=out_dtype, device=dev)
         mot = torch.empty((len(mine), 4, CLIP, h, w), dtype=out_dtype, device=dev)
-        eng.forward_windows(v, prob, mot, OUT_PROB, [s - fa for s in mine], CLIP, batch_clips)
+        # the range is segmented in a few sub-ranges of clips, each as soon as its frames have arrived
+        n_sub = max(1, min(4, len(mine) // 48))
+        bounds = [round(i * len(mine) / n_sub) for i in range(n_sub + 1)]
+        main = torch.cuda.current_stream(dev) if cuda else None
+        for a, b in zip(bounds, bounds[1:]):
+            ev = up.ready(mine[b - 1] + CLIP - fa)
+            if ev is not None:
+                main.wait_event(ev)
+            if a == 0:
+                mark("upload")                   # what the first sub-range had to wait for; the rest overlaps the forward
+            eng.forward_windows(v, prob[a:b], mot[a:b], OUT_LVPROB, [s - fa for s in mine[a:b]], CLIP, batch_clips)
         mark("forward")
         res = eng.warp_fuse(prob, mot, [s - lo for s in mine], hi - lo, edge_hops=edge_hops, want_mask=False, want_area=False)
         acc, cnt = res["acc"], res["cnt"]

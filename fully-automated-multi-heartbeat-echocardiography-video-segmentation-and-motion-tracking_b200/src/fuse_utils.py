@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from .. import engine as _engine
-from .._lib import OUT_PROB, ClasfvError
+from .._lib import OUT_LVPROB, OUT_PROB, ClasfvError
 from .echonet_dataset import EDESpairs
 
 CLIP = 32
@@ -134,11 +134,11 @@ def segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num
         if starts[-1] != num_frames - CLIP:
             starts.append(num_frames - CLIP)        # the tail is always covered
         n = len(starts)
-        prob = torch.empty((n, 2, CLIP, h, w), dtype=out_dtype, device=v.device)
+        prob = torch.empty((n, 1, CLIP, h, w), dtype=out_dtype, device=v.device)      # the LV probability: all that fusion reads
         mot = torch.empty((n, 4, CLIP, h, w), dtype=out_dtype, device=v.device)
         # one call per run of equally spaced windows: the library batches internally (batch_clips) and shares the stem
         # and layer1 between the overlapping windows (dense-video schedule, csrc/api.cu)
-        eng.forward_windows(v, prob, mot, OUT_PROB, starts, CLIP, batch_clips)
+        eng.forward_windows(v, prob, mot, OUT_LVPROB, starts, CLIP, batch_clips)
         res = eng.warp_fuse(prob, mot, starts, num_frames, edge_hops=edge_hops)
         fused = _mask_to_host_int64(res["mask"])
         if return_details:
@@ -222,7 +222,7 @@ class _VideoPipeline:
         if self.planes is None or self.planes[0] != key:
             self.planes = None               # release before allocating the next shape
             dev = self.eng.device
-            self.planes = (key, torch.empty((n, 2, CLIP, h, w), dtype=dtype, device=dev), torch.empty((n, 4, CLIP, h, w), dtype=dtype, device=dev))
+            self.planes = (key, torch.empty((n, 1, CLIP, h, w), dtype=dtype, device=dev), torch.empty((n, 4, CLIP, h, w), dtype=dtype, device=dev))
         return self.planes[1], self.planes[2]
 
 
@@ -252,7 +252,7 @@ def segment_videos_with_fusion(videos, model, step=1, batch_clips=192, edge_hops
         if starts[-1] != num_frames - CLIP:
             starts.append(num_frames - CLIP)
         prob, mot = pipe.plane_buffers(len(starts), h, w, out_dtype)
-        eng.forward_windows(dev_video, prob, mot, OUT_PROB, starts, CLIP, batch_clips)
+        eng.forward_windows(dev_video, prob, mot, OUT_LVPROB, starts, CLIP, batch_clips)
         res = eng.warp_fuse(prob, mot, starts, num_frames, edge_hops=edge_hops)
         wide = res["mask"].to(torch.int64)
         done = torch.cuda.Event(); done.record(main)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CLASFV_ABI_VERSION 1
+#define CLASFV_ABI_VERSION 2
 
 /* element types of activation-sized buffers / arithmetic mode of the network */
 #define CLASFV_F32  0   /* fp32 storage, fp32 CUDA-core arithmetic (reference-tolerance mode)        */
@@ -49,6 +49,7 @@ extern "C" {
 /* forward() output selection */
 #define CLASFV_OUT_LOGITS 0    /* seg = raw 2-class logits (what the reference forward returns)        */
 #define CLASFV_OUT_PROB   1    /* seg = softmax over the class axis, fused into the head kernel        */
+#define CLASFV_OUT_LVPROB 2    /* seg = (N,1,T,H,W): the LV class probability only (what warp-and-fuse reads) */
 
 typedef struct clasfv_handle clasfv_handle;
 
@@ -139,17 +140,19 @@ int clasfv_warp_mode(const float* src_dev, const float* flow_dev, float* out_dev
 int clasfv_motion_field(const float* flow_dev, float* grid_dev, int n, int height, int width, void* stream);
 
 /* ---- warp + fuse (north-star operator F2; specified by oracle/fuse_ref.py:warp_fuse) -----------
- * prob_dev (n,2,L,H,W), motion_dev (n,4,L,H,W) of element type dtype; clip c covers global frames
- * clip_start_host[c] + t (ascending starts).  Every clip frame votes on its own frame, and - warped
- * along its forward / backward flow - on the next / previous frame; hops leaving the clip are
- * dropped unless edge_hops != 0; votes outside [0, t_out) are dropped.
+ * prob_dev (n,prob_planes,L,H,W), motion_dev (n,4,L,H,W) of element type dtype; prob_planes = 2 (background, LV:
+ * the softmax of the segmentation logits) or 1 (the LV probability alone, CLASFV_OUT_LVPROB); only the LV plane is
+ * read.  Clip c covers global frames clip_start_host[c] + t (ascending starts).  Every clip frame votes its LV
+ * probability on its own frame, and - warped along its forward / backward flow - on the next / previous frame; hops
+ * leaving the clip are dropped unless edge_hops != 0; votes outside [0, t_out) are dropped.
  * Outputs (any may be NULL except acc_dev):
- *   acc_dev  (t_out,2,H,W) fp32  running class sums. accumulate != 0 adds to the existing content
- *                                 (fusing a video clip-batch by clip-batch), else overwrites.
+ *   acc_dev  (t_out,2,H,W) fp32  plane 1 = sum of the LV votes, plane 0 = votes - plane 1 (the background sum: class
+ *                                 probabilities and bilinear weights sum to one). accumulate != 0 adds to the existing
+ *                                 content (fusing a video clip-batch by clip-batch), else overwrites.
  *   cnt_dev  (t_out) int32       votes per frame (same accumulate rule)
  *   mask_dev (t_out,H,W) uint8   argmax over the two sums after this call (ties -> 0)
  *   area_dev (t_out) int32       LV pixel count of mask per frame (the EF size trace, fuse_utils.py:106) */
-int clasfv_warp_fuse(clasfv_handle* h, const void* prob_dev, const void* motion_dev, int dtype,
+int clasfv_warp_fuse(clasfv_handle* h, const void* prob_dev, int prob_planes, const void* motion_dev, int dtype,
                      const int32_t* clip_start_host, int n_clips, int clip_len, int t_out, int height, int width,
                      int edge_hops, int accumulate, float* acc_dev, int32_t* cnt_dev, uint8_t* mask_dev,
                      int32_t* area_dev, void* stream);

@@ -191,7 +191,8 @@ def apply_sequence_deformation(flow_source_image, motion_output, start_index, en
 def warp_fuse(prob, motion, clip_starts, num_frames, edge_hops=False, accumulate=torch.float64):
     """North-star warp-and-fuse operator (not in the reference; composition of S1 + W1).
 
-    prob   (n, 2, 32, H, W) per-frame class probabilities of clip c (softmax of the seg logits)
+    prob   (n, 2, 32, H, W) per-frame class probabilities of clip c (softmax of the seg logits), or (n, 1, 32, H, W) the
+           LV probability alone: only the LV plane (the last) is used
     motion (n, 4, 32, H, W) tanh motion, channels [fwd x, fwd y, bwd x, bwd y]
     clip c covers global frames clip_starts[c] + t, t in [0, 32).
 
@@ -205,26 +206,31 @@ def warp_fuse(prob, motion, clip_starts, num_frames, edge_hops=False, accumulate
     ``edge_hops=True`` the two unsupervised edge flows vote as well (SURVEY.md 8a row F2
     wording); votes that land outside [0, num_frames) are dropped either way.
 
-    Returns (acc (T, 2, H, W), cnt (T,), mask (T, H, W) uint8) with mask = argmax_k acc
-    (ties -> class 0, as np.argmax).
+    The operator fuses the LV probability ("each clip's per-frame LV softmax is warped", north-star): acc[:, 1] is the sum
+    of the LV votes and acc[:, 0] = cnt - acc[:, 1] the background sum - what summing the warped background plane gives as
+    well, because the two class probabilities and the four bilinear weights each sum to one.  fused = LV where
+    acc[:, 1] > acc[:, 0], i.e. where the mean LV probability exceeds 1/2; ties -> background.
+
+    Returns (acc (T, 2, H, W), cnt (T,), mask (T, H, W) uint8).
     """
     n, _, clip, h, w = prob.shape
-    acc = torch.zeros(num_frames, 2, h, w, dtype=accumulate)
+    lv = torch.zeros(num_frames, h, w, dtype=accumulate)
     cnt = torch.zeros(num_frames, dtype=torch.int64)
     for c in range(n):
         s = int(clip_starts[c])
         for t in range(clip):
             g = s + t
-            p = prob[c, :, t].unsqueeze(0).float()
+            p = prob[c, -1:, t].unsqueeze(0).float()
             if 0 <= g < num_frames:
-                acc[g] += p[0].to(accumulate)
+                lv[g] += p[0, 0].to(accumulate)
                 cnt[g] += 1
             if (edge_hops or t + 1 < clip) and 0 <= g + 1 < num_frames:
-                acc[g + 1] += warp(p, motion[c, 0:2, t].unsqueeze(0).float())[0].to(accumulate)
+                lv[g + 1] += warp(p, motion[c, 0:2, t].unsqueeze(0).float())[0, 0].to(accumulate)
                 cnt[g + 1] += 1
             if (edge_hops or t >= 1) and 0 <= g - 1 < num_frames:
-                acc[g - 1] += warp(p, motion[c, 2:4, t].unsqueeze(0).float())[0].to(accumulate)
+                lv[g - 1] += warp(p, motion[c, 2:4, t].unsqueeze(0).float())[0, 0].to(accumulate)
                 cnt[g - 1] += 1
+    acc = torch.stack([cnt.view(-1, 1, 1).to(accumulate) - lv, lv], 1)
     mask = (acc[:, 1] > acc[:, 0]).to(torch.uint8)
     return acc, cnt, mask
 

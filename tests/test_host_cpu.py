@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert os.path.dirname(_lib.LIB_PATH).startswith(clasfv_b200.PACKAGE_DIR)      # built in-tree
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.clasfv_abi_version() == 1
+    assert lib.clasfv_abi_version() == 2
     assert lib.clasfv_last_error() is not None
 
 

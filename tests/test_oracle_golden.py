@@ -132,9 +132,13 @@ def test_warp_fuse_oracle_properties():
     # bilinear weights sum to one: the two class sums add up to the vote count
     np.testing.assert_allclose((acc[:, 0] + acc[:, 1]).numpy(), cnt.view(-1, 1, 1).expand(-1, h, w).numpy(), atol=1e-4)
     assert int(cnt[0]) == 2 and int(cnt.max()) == 3 * n       # frame 0: direct + one backward hop
-    # linearity in prob
+    # the LV sum is linear in the LV probability, and is what summing the warped background plane would leave for plane 0
     acc2, _, _ = fuse_ref.warp_fuse(2 * prob, motion, starts, 32 + n - 1)
-    np.testing.assert_allclose(acc2.numpy(), 2 * acc.numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(acc2[:, 1].numpy(), 2 * acc[:, 1].numpy(), rtol=1e-6, atol=1e-6)
+    bg, _, _ = fuse_ref.warp_fuse(prob[:, :1], motion, starts, 32 + n - 1)          # the background plane fused as if it were the LV plane
+    np.testing.assert_allclose(bg[:, 1].numpy(), acc[:, 0].numpy(), atol=2e-5)
+    lv, _, m1 = fuse_ref.warp_fuse(prob[:, 1:], motion, starts, 32 + n - 1)         # one-plane input = the same operator
+    assert torch.equal(lv, acc) and torch.equal(m1, mask)
     # edge hops add exactly the two unsupervised flows per clip
     _, cnt_e, _ = fuse_ref.warp_fuse(prob, motion, starts, 32 + n + 3, edge_hops=True)
     _, cnt_s, _ = fuse_ref.warp_fuse(prob, motion, starts, 32 + n + 3, edge_hops=False)

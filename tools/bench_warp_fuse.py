@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """BASELINE.json configs[2]: the warp+fusion kernel alone, HBM-bandwidth sweep.
 
-256 stride-1 clips x 32 frames x 112x112 softmax + fwd/bwd flow fields (2.466 GB fp32), sweeping the clip
-count, the element type and the flow magnitude (the gather pattern).  Prints one JSON line per point:
-algorithmic bytes (6 planes per clip-frame read once + the fused outputs written once) / CUDA-event time.
+256 stride-1 clips x 32 frames x 112x112 LV softmax + fwd/bwd flow fields, sweeping the clip count, the element type,
+the frame size and the flow magnitude (the gather pattern).  Prints one JSON line per point: algorithmic bytes (the LV
+plane + 4 flow planes per clip-frame read once + the fused outputs written once; `GBps_6plane` counts the background plane
+the operator no longer reads, i.e. SURVEY 8(d)'s figure) / CUDA-event time.
 """
 import argparse
 import json
@@ -19,7 +20,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--clips", type=int, nargs="*", default=[16, 64, 256])
     ap.add_argument("--flow-px", type=float, nargs="*", default=[0.0, 1.0, 4.0, 8.0])
-    ap.add_argument("--dtypes", nargs="*", default=["fp32", "bf16"])
+    ap.add_argument("--dtypes", nargs="*", default=["fp32", "bf16", "fp16"])
+    ap.add_argument("--size", type=int, default=112)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--once", action="store_true", help="one point per dtype (256 clips, 4 px), 1 warm-up + 1 launch: for ncu captures")
     args = ap.parse_args()
@@ -31,12 +33,12 @@ def main():
     except Exception:
         peak = 6650.0
     eng = Engine("cuda:0")
-    h = w = 112
+    h = w = args.size
     g = torch.Generator(device="cuda").manual_seed(0)
     for dt in args.dtypes:
-        dtype = torch.float32 if dt == "fp32" else torch.bfloat16
+        dtype = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[dt]
         for n in args.clips:
-            prob = torch.softmax(torch.randn(n, 2, 32, h, w, generator=g, device="cuda"), 1).to(dtype)
+            prob = torch.sigmoid(torch.randn(n, 1, 32, h, w, generator=g, device="cuda")).to(dtype)      # the LV probability
             for px in args.flow_px:
                 # tanh(N(0, sigma)) with sigma chosen so that the rms displacement is `px` pixels
                 mot = torch.tanh(torch.randn(n, 4, 32, h, w, generator=g, device="cuda") * (px / 56.0)).to(dtype)
@@ -52,9 +54,11 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / args.iters
-                nbytes = n * 32 * h * w * 6 * prob.element_size() + t_out * h * w * 9 + t_out * 8
-                print(json.dumps({"kernel": "warp_fuse", "dtype": dt, "clips": n, "flow_px_rms": px, "ms": round(ms, 4),
+                nbytes = n * 32 * h * w * 5 * prob.element_size() + t_out * h * w * 9 + t_out * 8
+                nbytes6 = nbytes + n * 32 * h * w * prob.element_size()
+                print(json.dumps({"kernel": "warp_fuse", "dtype": dt, "size": h, "clips": n, "flow_px_rms": px, "ms": round(ms, 4),
                                   "algorithmic_bytes": nbytes, "GBps": round(nbytes / ms / 1e6, 1), "frac_of_measured_hbm": round(nbytes / ms / 1e6 / peak, 4),
+                                  "GBps_6plane": round(nbytes6 / ms / 1e6, 1),
                                   "note": "inputs of 16 clips (39-77 MB) fit the 126 MB L2" if n <= 16 else ""}), flush=True)
                 del mot
             del prob

@@ -23,7 +23,7 @@ if os.environ.get("CLASFV_CONV_TRACE") is None:
 sys.path.insert(0, ROOT)
 import torch
 from clasfv_b200 import synthetic
-from clasfv_b200._lib import OUT_PROB
+from clasfv_b200._lib import OUT_LVPROB
 from clasfv_b200.src.model.R2plus1D_18_MotionNet import R2plus1D_18_MotionNet
 tv = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
@@ -32,8 +32,8 @@ eng = net.engine(); eng.set_option("sub_batch", 64)
 video = torch.from_numpy(synthetic.synthetic_echo_video(tv, 112, 112, seed=0)).cuda()
 n = tv - 31
 dt = torch.bfloat16 if prec == "bf16" else torch.float16
-prob = torch.empty((n, 2, 32, 112, 112), dtype=dt, device="cuda"); mot = torch.empty((n, 4, 32, 112, 112), dtype=dt, device="cuda")
+prob = torch.empty((n, 1, 32, 112, 112), dtype=dt, device="cuda"); mot = torch.empty((n, 4, 32, 112, 112), dtype=dt, device="cuda")
 for _ in range(2):
-    eng.forward_into(video, prob, mot, OUT_PROB, clip_starts=list(range(n)), clip_len=32)
+    eng.forward_into(video, prob, mot, OUT_LVPROB, clip_starts=list(range(n)), clip_len=32)
 torch.cuda.synchronize()
 print("ok")

@@ -26,10 +26,10 @@ net = R2plus1D_18_MotionNet(pretrained=False, precision=precision)
 net.load_state_dict(synthetic.random_state_dict(0))
 net = net.cuda().eval()
 video = synthetic.synthetic_echo_video(t, h, w, seed=3)
-sharding.segment_long_video(video[:, :64], net)            # warm-up (workspace, NCCL channels)
+sharding.segment_long_video(video, net)                      # warm-up with the real shape (workspace, staging, NCCL channels)
 dist.barrier(); torch.cuda.synchronize()
 t0 = time.perf_counter()
-full = sharding.segment_long_video(video, net)
+full = sharding.segment_long_video(video, net, mask_dtype=np.int64)
 torch.cuda.synchronize(); dist.barrier()
 dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
 dist.all_reduce(dt, op=dist.ReduceOp.MAX)

@@ -6,7 +6,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 from clasfv_b200 import synthetic  # noqa: E402
-from clasfv_b200._lib import OUT_PROB  # noqa: E402
+from clasfv_b200._lib import OUT_LVPROB  # noqa: E402
 from clasfv_b200.src.model.R2plus1D_18_MotionNet import R2plus1D_18_MotionNet  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
@@ -19,9 +19,9 @@ if len(sys.argv) > 3:
     eng.set_option("dense_video", int(sys.argv[3]))
     eng.set_option("sub_batch", n)
 video = torch.from_numpy(synthetic.synthetic_echo_video(32 + n - 1, 112, 112, seed=0)).cuda()
-prob = torch.empty((n, 2, 32, 112, 112), dtype=torch.bfloat16, device="cuda")
+prob = torch.empty((n, 1, 32, 112, 112), dtype=torch.bfloat16, device="cuda")
 mot = torch.empty((n, 4, 32, 112, 112), dtype=torch.bfloat16, device="cuda")
 for _ in range(iters):
-    eng.forward_into(video, prob, mot, OUT_PROB, clip_starts=list(range(n)), clip_len=32)
+    eng.forward_into(video, prob, mot, OUT_LVPROB, clip_starts=list(range(n)), clip_len=32)
 torch.cuda.synchronize()
 print("ok", float(prob.float().mean()))
