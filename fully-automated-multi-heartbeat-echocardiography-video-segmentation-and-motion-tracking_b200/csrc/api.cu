@@ -479,7 +479,13 @@ struct Forward {
       if (uniform) frame_step = d / hw;
     }
     const bool dense = h->dense_video && tc_head && frame_step >= 1 && frame_step <= 8 && n >= 4 && t >= 16 && t <= CLASFV_MAX_FSEL;
-    return dense ? run_dense((int)frame_step) : run_per_clip(frame_step);
+    if (dense) {
+      // the video-level maps grow with the run of windows: when they do not fit, the per-clip schedule computes the same
+      // (bit-identical) outputs inside the per-batch workspace
+      const int rc = run_dense((int)frame_step);
+      if (rc != CLASFV_ENOMEM) return rc;
+    }
+    return run_per_clip(frame_step);
   }
 
   // ------------------------------------------------------------------ per-clip schedule

@@ -33,6 +33,8 @@ def storage_dtype(precision):
 class Engine:
     """One packed CLAS-FV network on one CUDA device."""
 
+    MAX_RUN = 1024        # windows per clasfv_forward call of forward_windows
+
     def __init__(self, device):
         self.lib = _lib.lib()
         dev = torch.device(device)
@@ -74,9 +76,9 @@ class Engine:
         self.precision = code
 
     # ------------------------------------------------------------------ network
-    def forward(self, x, out_kind=OUT_LOGITS, out_dtype=torch.float32, clip_starts=None, clip_len=None):
-        """x: (N,3,T,H,W) fp32 CUDA tensor, or with ``clip_starts`` a resident video (3,Tv,H,W) whose
-        windows [s, s+clip_len) are the clips (no copy).  Returns (seg, motion)."""
+    def _clip_geometry(self, x, clip_starts, clip_len):
+        """Validation shared by forward() and forward_into(): device, element type, contiguity, shape, and that every clip
+        window lies inside the video.  Returns (n, t, h, w, clip offsets or None, channel stride)."""
         _lib.require_cuda(x, "x")
         if x.dtype != torch.float32:
             raise ClasfvError("network input must be float32")
@@ -84,17 +86,20 @@ class Engine:
             if x.dim() != 5 or x.shape[1] != 3:
                 raise ClasfvError(f"expected input of shape (N,3,T,H,W), got {tuple(x.shape)}")
             n, _, t, h, w = x.shape
-            offs, ch_stride = None, 0
-        else:
-            if x.dim() != 4 or x.shape[0] != 3:
-                raise ClasfvError(f"expected a video of shape (3,T,H,W), got {tuple(x.shape)}")
-            _, tv, h, w = x.shape
-            t = int(clip_len)
-            n = len(clip_starts)
-            if n and (min(clip_starts) < 0 or max(clip_starts) + t > tv):
-                raise ClasfvError("clip window outside the video")
-            offs = _lib.i64_array([int(s) * h * w for s in clip_starts])
-            ch_stride = tv * h * w
+            return n, t, h, w, None, 0
+        if x.dim() != 4 or x.shape[0] != 3:
+            raise ClasfvError(f"expected a video of shape (3,T,H,W), got {tuple(x.shape)}")
+        _, tv, h, w = x.shape
+        t = int(clip_len)
+        n = len(clip_starts)
+        if n and (min(clip_starts) < 0 or max(clip_starts) + t > tv):
+            raise ClasfvError("clip window outside the video")
+        return n, t, h, w, _lib.i64_array([int(s) * h * w for s in clip_starts]), tv * h * w
+
+    def forward(self, x, out_kind=OUT_LOGITS, out_dtype=torch.float32, clip_starts=None, clip_len=None):
+        """x: (N,3,T,H,W) fp32 CUDA tensor, or with ``clip_starts`` a resident video (3,Tv,H,W) whose
+        windows [s, s+clip_len) are the clips (no copy).  Returns (seg, motion)."""
+        n, t, h, w, offs, ch_stride = self._clip_geometry(x, clip_starts, clip_len)
         seg = torch.empty((n, 1 if out_kind == OUT_LVPROB else 2, t, h, w), dtype=out_dtype, device=x.device)
         mot = torch.empty((n, 4, t, h, w), dtype=out_dtype, device=x.device)
         if n == 0:
@@ -106,16 +111,14 @@ class Engine:
 
     def forward_into(self, x, seg, mot, out_kind, clip_starts=None, clip_len=None):
         """As :meth:`forward`, writing into caller-provided slices of larger (N,2,T,H,W)/(N,4,T,H,W) buffers."""
-        if clip_starts is None:
-            n, _, t, h, w = x.shape
-            offs, ch_stride = None, 0
-        else:
-            _, tv, h, w = x.shape
-            t, n = int(clip_len), len(clip_starts)
-            offs = _lib.i64_array([int(s) * h * w for s in clip_starts])
-            ch_stride = tv * h * w
-        assert seg.is_contiguous() and mot.is_contiguous() and seg.shape[0] == n and mot.shape[0] == n
-        assert seg.shape[1] == (1 if out_kind == OUT_LVPROB else 2), "OUT_LVPROB writes one class plane, the other kinds two"
+        n, t, h, w, offs, ch_stride = self._clip_geometry(x, clip_starts, clip_len)
+        _lib.require_cuda(seg, "seg"); _lib.require_cuda(mot, "mot")
+        planes = 1 if out_kind == OUT_LVPROB else 2
+        if tuple(seg.shape) != (n, planes, t, h, w) or tuple(mot.shape) != (n, 4, t, h, w) or seg.dtype != mot.dtype or seg.device != x.device:
+            raise ClasfvError(f"forward_into: outputs must be ({n},{planes},{t},{h},{w}) and ({n},4,{t},{h},{w}) tensors of one type on "
+                              f"the input's device (got {tuple(seg.shape)} {seg.dtype}, {tuple(mot.shape)} {mot.dtype})")
+        if n == 0:
+            return
         check(self.lib.clasfv_forward(self._h, x.data_ptr(), offs, ch_stride, n, t, h, w, out_kind,
                                       _lib.torch_dtype_code(seg.dtype), seg.data_ptr(), mot.data_ptr(),
                                       _lib.current_stream_ptr(x.device)), "clasfv_forward")
@@ -131,7 +134,9 @@ class Engine:
             j = i + 1
             if j < n:
                 d = starts[j] - starts[i]
-                while j + 1 < n and starts[j + 1] - starts[j] == d:
+                # a run is cut at MAX_RUN windows: the library keeps video-level maps for the frames of a run (about
+                # 5.6 MB per frame at 112 x 112, 22 MB at 224 x 224), so the cap bounds that part of the workspace
+                while j + 1 < n and starts[j + 1] - starts[j] == d and j + 1 - i < self.MAX_RUN:
                     j += 1
                 j += 1
             self.forward_into(video, seg[i:j], mot[i:j], out_kind, clip_starts=starts[i:j], clip_len=clip_len)

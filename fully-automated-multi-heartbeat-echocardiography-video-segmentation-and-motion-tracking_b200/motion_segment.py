@@ -14,12 +14,10 @@ import sys
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(_HERE))
 import clasfv_b200  # noqa: E402,F401
-from clasfv_b200.src.echonet_dataset import zeroone_normalizer  # noqa: E402
 from clasfv_b200.src.fuse_utils import compute_ef_using_putative_clips, segment_a_video_with_fusion  # noqa: E402
 from clasfv_b200.src.model.R2plus1D_18_MotionNet import R2plus1D_18_MotionNet  # noqa: E402
 
@@ -59,29 +57,6 @@ def load_frames(path):
             raise ValueError("Failed to load frame #{} of {}.".format(count, path))
         video[count, :, :] = frame
     return video
-
-
-def load_video(path):
-    """cv2 decode -> (3, T, H, W) float32 RGB, as motion_segment.py:80-96."""
-    import cv2
-    capture = cv2.VideoCapture(path)
-    frame_count = int(capture.get(cv2.CAP_PROP_FRAME_COUNT))
-    frame_width = int(capture.get(cv2.CAP_PROP_FRAME_WIDTH))
-    frame_height = int(capture.get(cv2.CAP_PROP_FRAME_HEIGHT))
-    video = np.zeros((frame_count, frame_height, frame_width, 3), np.uint8)
-    for count in range(frame_count):
-        ret, frame = capture.read()
-        if not ret:
-            raise ValueError("Failed to load frame #{} of {}.".format(count, path))
-        video[count, :, :] = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
-    return video.transpose((3, 0, 1, 2)).astype(np.float32)
-
-
-def preprocess(video, height, width):
-    """Trilinear (align_corners=True) resize to (T, height, width) + zero-one normalisation (:100-106)."""
-    v = torch.Tensor(video).unsqueeze(0)
-    v = F.interpolate(v, size=(v.shape[2], height, width), mode="trilinear", align_corners=True)
-    return zeroone_normalizer(v.squeeze(0).numpy())
 
 
 def main(argv=None):

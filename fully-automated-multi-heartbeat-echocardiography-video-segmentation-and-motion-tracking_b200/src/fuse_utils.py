@@ -293,68 +293,94 @@ def segment_videos_with_fusion(videos, model, step=1, batch_clips=192, edge_hops
 
 
 # ------------------------------------------------------------------------------------------- EF (host)
+# Ejection fraction from the fused masks (reference src/fuse_utils.py:105-147 with get2dPucks, src/utils/echo_utils.py:259-334):
+# the LV area trace picks end-diastolic / end-systolic frames, each LV mask becomes a stack of disks along its long axis
+# (Simpson, single plane), EF = (EDV - ESV) / EDV.  Same results as the reference functions (oracle/ef_ref.py restates them
+# line by line; tests compare the two on the same masks), organised around the device-side by-product of fusion: both
+# fusion kernels already return the per-frame LV area, so the (T,H,W) mask is only touched for the few ED / ES frames.
 def _find_boundaries_thick(binary):
-    """skimage.segmentation.find_boundaries(label_img, mode='thick') for a 2-D label image:
-    (grey dilation != grey erosion) with the 4-connected cross."""
+    """Pixels where the 4-neighbourhood (plus the pixel) is not constant: skimage.segmentation.find_boundaries(mode="thick")
+    for a 2-D label image; neighbours outside the image do not count."""
     from scipy import ndimage as ndi
-    img = binary.astype(np.uint8)
-    fp = ndi.generate_binary_structure(2, 1)
-    return ndi.grey_dilation(img, footprint=fp, mode="nearest") != ndi.grey_erosion(img, footprint=fp, mode="nearest")
+    img = np.asarray(binary).astype(np.uint8)
+    cross = ndi.generate_binary_structure(2, 1)
+    return ndi.maximum_filter(img, footprint=cross, mode="nearest") != ndi.minimum_filter(img, footprint=cross, mode="nearest")
+
+
+def _long_axis_frame(points):
+    """Principal axes (columns, long axis first) of 2 x N pixel coordinates, oriented so that the long axis points to +row and
+    the short axis to +column - the reference's sign convention."""
+    weights, axes = np.linalg.eig(np.cov(points, rowvar=True))
+    axes = axes[:, np.argsort(weights)[::-1]]
+    for k in (0, 1):
+        if axes[k, k] < 0:
+            axes[:, k] = -axes[:, k]
+    return axes
 
 
 def get2dPucks(abin, apix, npucks=10):
-    """Reference ``src/utils/echo_utils.py:259-334``: long-axis extent (PCA) and ``npucks`` disk radii."""
-    if not np.any(abin):
+    """(long-axis length, ``npucks`` disk radii) of a binary LV mask with pixel spacing ``apix`` (reference
+    src/utils/echo_utils.py:259-334): boundary pixels are projected on the mask's principal axes, the long-axis extent of the
+    boundary is cut into ``npucks`` equal slabs and a slab's radius is the median distance of its boundary pixels from the
+    long axis (nan for a slab without boundary pixels).  An empty mask gives (1.0, zeros)."""
+    filled = np.asarray(abin) > 0
+    if not filled.any():
         return 1.0, np.zeros((npucks,))
-    x, y = np.where(abin > 0)
-    X = np.stack([x, y]).astype(np.float64) * np.array(apix)[:, None]
+    spacing = np.asarray(apix, dtype=np.float64).reshape(2, 1)
+    inside = np.vstack(np.nonzero(filled)) * spacing
     try:
-        val, vec = np.linalg.eig(np.cov(X, rowvar=True))
+        axes = _long_axis_frame(inside)
     except Exception:
         return 0.0, np.zeros((npucks,))
-    order = np.argsort(val)[-1::-1]
-    vec = vec[:, order]
-    if vec[0, 0] < 0:
-        vec[:, 0] = -1.0 * vec[:, 0]
-    if vec[1, 1] < 0:
-        vec[:, 1] = -1.0 * vec[:, 1]
-    mu = np.expand_dims(np.mean(X, axis=1), axis=1)
-    Xb = np.stack(np.where(_find_boundaries_thick(abin))).astype(np.float64) * np.array(apix)[:, None]
-    proj = np.dot((Xb - mu).T, vec)
-    l_min, l_max = np.min(proj, axis=0), np.max(proj, axis=0)
-    length = l_max - l_min
-    part = np.linspace(l_min[0], l_max[0], npucks + 1)
-    radii = []
-    for i in range(len(part) - 1):
-        which = np.logical_and(proj[:, 0] >= part[i], proj[:, 0] < part[i + 1])
-        radii.append(np.median(np.abs(proj[:, 1][which])) if np.any(which) else np.nan)
-    return length[0], np.array(radii)
+    centre = inside.mean(axis=1, keepdims=True)
+    edge = np.vstack(np.nonzero(_find_boundaries_thick(filled))) * spacing
+    along, across = np.dot((edge - centre).T, axes).T
+    lo, hi = along.min(), along.max()
+    cuts = np.linspace(lo, hi, npucks + 1)
+    radii = np.full((npucks,), np.nan)
+    for k in range(npucks):
+        slab = (along >= cuts[k]) & (along < cuts[k + 1])
+        if slab.any():
+            radii[k] = np.median(np.abs(across[slab]))
+    return hi - lo, radii
 
 
-def compute_ef_using_putative_clips(fused_segmentations, test_pat_index, return_edes=False):
+def _disk_volume(mask):
+    length, radii = get2dPucks((mask == 1).astype("int"), (1.0, 1.0))
+    return np.sum(np.pi * radii * radii * length / len(radii))
+
+
+def find_ed_es_frames(area):
+    """[(ED frame, ES frame)] from the per-frame LV area: peaks / troughs at least 20 frames apart whose prominence is half
+    the 5-95 percentile range; diastoles must reach the 85th percentile; frame 0 counts as a diastole when the video starts
+    near one (reference src/fuse_utils.py:106-122)."""
     from scipy.signal import find_peaks
-    size = np.sum(fused_segmentations, axis=(1, 2)).ravel()
-    _05cut, _85cut, _95cut = np.percentile(size, [5, 85, 95])
-    trim_range = _95cut - _05cut
-    systole = find_peaks(-size, distance=20, prominence=(0.50 * trim_range))[0]
-    diastole = find_peaks(size, distance=20, prominence=(0.50 * trim_range))[0]
-    diastole = [x for x in diastole if size[x] >= _85cut]
-    if np.mean(size[:3]) >= _85cut:
-        diastole = [0] + diastole
-    diastole = np.array(diastole)
-    clip_pairs = EDESpairs(diastole, systole)
+    area = np.asarray(area).ravel()
+    p05, p85, p95 = np.percentile(area, [5, 85, 95])
+    prominence = 0.5 * (p95 - p05)
+    troughs = find_peaks(-area, distance=20, prominence=prominence)[0]
+    peaks = [f for f in find_peaks(area, distance=20, prominence=prominence)[0] if area[f] >= p85]
+    if np.mean(area[:3]) >= p85:
+        peaks = [0] + peaks
+    return EDESpairs(np.array(peaks), troughs)
+
+
+def compute_ef_using_putative_clips(fused_segmentations, test_pat_index, return_edes=False, area=None):
+    """Ejection fraction (%) at every identified heartbeat of a fused (T,H,W) mask video.  ``area``: the per-frame LV pixel
+    count when the caller already has it (``return_details`` of segment_a_video_with_fusion: a by-product of the fusion
+    kernel); otherwise the masks are summed here as the reference does."""
     frames = fused_segmentations.reshape((-1,) + tuple(fused_segmentations.shape[-2:]))
+    if area is None:
+        area = np.sum(fused_segmentations, axis=(1, 2)).ravel()
+    clip_pairs = find_ed_es_frames(area)
     predicted_efs = []
     for ed, es in clip_pairs:
-        length_ed, radius_ed = get2dPucks((frames[ed] == 1).astype('int'), (1.0, 1.0))
-        length_es, radius_es = get2dPucks((frames[es] == 1).astype('int'), (1.0, 1.0))
-        edv = np.sum(((np.pi * radius_ed * radius_ed) * length_ed / len(radius_ed)))
-        esv = np.sum(((np.pi * radius_es * radius_es) * length_es / len(radius_es)))
-        ef_predicted = (edv - esv) / edv * 100
-        if ef_predicted < 0:
+        edv, esv = _disk_volume(frames[ed]), _disk_volume(frames[es])
+        ef = (edv - esv) / edv * 100
+        if ef < 0:
             print("Negative EF at patient: " + str(test_pat_index))
             continue
-        predicted_efs.append(ef_predicted)
+        predicted_efs.append(ef)
     if return_edes:
         return predicted_efs, clip_pairs
     return predicted_efs

@@ -45,11 +45,15 @@ class R2plus1D_18_MotionNet(nn.Module):
         self.segmentation_head = nn.Conv3d(64, 2, 1)
         self.precision = precision
         self._engines = {}          # device index -> (Engine, signature)
+        self._packed_from = None    # set on DataParallel replicas: the module whose parameters the cache key follows
 
     # ------------------------------------------------------------------ engine management
     def _signature(self):
+        # a DataParallel replica receives freshly broadcast parameter tensors on every forward: its cache key is the SOURCE
+        # module's (whose tensors persist), otherwise every call would repack and re-upload the whole network
+        src = getattr(self, "_packed_from", None) or self
         sig = [self.precision]
-        for t in list(self.parameters()) + list(self.buffers()):
+        for t in list(src.parameters()) + list(src.buffers()):
             sig.append((t.data_ptr(), t._version))
         return tuple(sig)
 
@@ -73,11 +77,13 @@ class R2plus1D_18_MotionNet(nn.Module):
     def __getstate__(self):             # engines hold C handles: never pickle / replicate them
         state = self.__dict__.copy()
         state["_engines"] = {}
+        state["_packed_from"] = None
         return state
 
     def _replicate_for_data_parallel(self):
         replica = super()._replicate_for_data_parallel()
         replica._engines = self._engines
+        replica._packed_from = getattr(self, "_packed_from", None) or self
         return replica
 
     # ------------------------------------------------------------------ forward

@@ -34,6 +34,20 @@ def stub_model(x):
     return seg, torch.zeros(x.shape[0], 4, *x.shape[2:])
 
 
+def write_ef_golden(ref):
+    from oracle import ef_ref
+    out = {}
+    for tag, (frames, period, seed) in {"a": (150, 47.0, 0), "b": (200, 61.0, 1), "c": (90, 33.0, 2)}.items():
+        masks = ef_ref.beating_masks(frames, 112, period, seed)
+        efs, pairs = ref.fuse_utils.compute_ef_using_putative_clips(masks, test_pat_index=tag, return_edes=True)
+        out[f"args_{tag}"] = np.array([frames, period, seed], dtype=np.float64)
+        out[f"efs_{tag}"] = np.array(efs, dtype=np.float64)
+        out[f"pairs_{tag}"] = np.array(pairs, dtype=np.int64).reshape(-1, 2)
+        length, radii = ref.echo_utils.get2dPucks((masks[5] == 1).astype("int"), (1.0, 1.0))
+        out[f"pucks_{tag}"] = np.concatenate([[length], radii])
+    np.savez_compressed(os.path.join(OUT, "ef.npz"), **out)
+
+
 def main():
     ref = ref_import.import_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -109,6 +123,10 @@ def main():
     norm = ref.echonet_dataset.zeroone_normalizer(v.copy())
     pairs = ref.echonet_dataset.EDESpairs([0, 31, 62, 95], [14, 47, 49, 80, 120])
     np.savez_compressed(os.path.join(OUT, "host_helpers.npz"), v=v, norm=norm, pairs=np.array(pairs))
+
+    # 6. ejection fraction: the reference's compute_ef_using_putative_clips + get2dPucks (find_boundaries bound to the oracle's
+    # restatement, the only substitution) on seeded synthetic multi-heartbeat masks
+    write_ef_golden(ref)
     print("golden vectors written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-24s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

@@ -60,6 +60,11 @@ def install_stubs(voter=None):
     if isinstance(lf, _Stub):
         vote = voter or fuse_ref.majority_vote
         lf.fuse_images = lambda images, method="simple", class_list=None: vote(images)
+    seg = sys.modules["skimage.segmentation"]
+    if isinstance(seg, _Stub):
+        # the one skimage function on the EF path (get2dPucks, src/utils/echo_utils.py:301): bound to the oracle's restatement
+        from oracle import ef_ref
+        seg.find_boundaries = lambda label_img, mode="thick", **kw: ef_ref.find_boundaries_thick(label_img)
 
 
 def import_reference():
@@ -74,9 +79,10 @@ def import_reference():
         warnings.simplefilter("ignore")
         from src.model.R2plus1D_18_MotionNet import R2plus1D_18_MotionNet
         from src import fuse_utils, transform_utils, echonet_dataset, clasfv_losses
+        from src.utils import echo_utils
     return types.SimpleNamespace(
         R2plus1D_18_MotionNet=R2plus1D_18_MotionNet, fuse_utils=fuse_utils, transform_utils=transform_utils,
-        echonet_dataset=echonet_dataset, clasfv_losses=clasfv_losses)
+        echonet_dataset=echonet_dataset, clasfv_losses=clasfv_losses, echo_utils=echo_utils)
 
 
 @contextlib.contextmanager

@@ -668,6 +668,27 @@ def test_fusion_error_behaviour(net_fp32, capsys):
     assert "Video is too short" in capsys.readouterr().out and out.shape == (20, 16, 16)
 
 
+def test_ejection_fraction_from_the_device_area_trace(eng):
+    """compute_ef_using_putative_clips fed by the LV area trace the fusion kernel returns, against the
+    oracle (oracle/ef_ref.py, pinned to the reference functions) run on the same fused masks."""
+    from oracle import ef_ref
+    beats = ef_ref.beating_masks(150, 112, 47.0, 3)
+    t = beats.shape[0]
+    starts = list(range(0, t - 32 + 1, 8))
+    lv = torch.from_numpy(beats).float() * 0.8 + 0.1                               # LV probability 0.9 inside, 0.1 outside
+    prob = torch.stack([lv[s0:s0 + 32] for s0 in starts]).unsqueeze(1).contiguous()     # (n,1,32,H,W)
+    mot = torch.zeros(len(starts), 4, 32, 112, 112)
+    r = eng.warp_fuse(prob.cuda(), mot.cuda(), starts, t)
+    masks = r["mask"].cpu().numpy().astype(np.int64)
+    area = r["area"].cpu().numpy()
+    assert np.array_equal(area, masks.reshape(t, -1).sum(1))
+    want, want_pairs = ef_ref.compute_ef_using_putative_clips(masks, "t", return_edes=True)
+    got, pairs = fuse_utils.compute_ef_using_putative_clips(masks, "t", return_edes=True, area=area)
+    assert len(want) >= 2 and all(45 < ef < 90 for ef in want)
+    assert [tuple(map(int, p)) for p in pairs] == [tuple(map(int, p)) for p in want_pairs]
+    np.testing.assert_allclose(np.array(got), np.array(want), rtol=1e-12)
+
+
 # ------------------------------------------------------------------------------------------ CLI
 def test_motion_segment_cli_config0(tmp_path, sd):
     video = synthetic.synthetic_echo_video(128, 112, 112, seed=0)
@@ -684,6 +705,38 @@ def test_motion_segment_cli_config0(tmp_path, sd):
     import pickle
     seg = pickle.load(open(out / "synthetic_echo_whole_video_segmentation.pkl", "rb"))
     assert seg.shape == (128, 112, 112) and seg.dtype == np.int64 and set(np.unique(seg)) <= {0, 1}
+    # mask equality with the oracle's reference-exact fusion of the same decoded video (the reference's host pipeline:
+    # cv2 decode, float, trilinear pre-resize, zero-one normalisation; motion_segment.py:80-106)
+    import cv2
+    from clasfv_b200.src.echonet_dataset import zeroone_normalizer
+    cap = cv2.VideoCapture(str(avi))
+    frames = []
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        frames.append(cv2.cvtColor(fr, cv2.COLOR_BGR2RGB))
+    v = torch.Tensor(np.stack(frames).transpose((3, 0, 1, 2)).astype(np.float32)).unsqueeze(0)
+    v = F.interpolate(v, size=(v.shape[2], 112, 112), mode="trilinear", align_corners=True)
+    host_video = zeroone_normalizer(v.squeeze(0).numpy())
+    ref = fuse_ref.segment_a_video_with_fusion(host_video, lambda x: model_ref.forward(sd, x), interpolate_last=True, step=1, num_clips=1)
+    assert float((seg == ref).mean()) >= 0.999
+    # ED / ES pickles: one pair of files per heartbeat the EF post-processing identifies on these masks, holding those frames
+    from oracle import ef_ref
+    _efs, pairs = ef_ref.compute_ef_using_putative_clips(seg, "cli", return_edes=True)
+    written = sorted(p.name for p in out.iterdir())
+    for ed, es in pairs:
+        for tag, f in (("ED", int(ed)), ("ES", int(es))):
+            name = f"synthetic_echo_{tag}_Frame_{f}_segmentation.pkl"
+            assert name in written
+            assert np.array_equal(pickle.load(open(out / name, "rb")), seg[f])
+    assert len([n for n in written if "_Frame_" in n]) == 2 * len(pairs)
+    assert f"Identified {len(_efs)} systoles" in r.stdout
+    # -c gif: written when the optional presentation dependency is there, skipped with a message otherwise
+    r3 = subprocess.run([sys.executable, cli, "-p", str(avi), "-m", str(ckpt), "-d", "cuda", "-f", "1", "-c", "gif", "-o", str(out)],
+                        capture_output=True, text=True, timeout=600)
+    assert r3.returncode == 0, r3.stderr[-2000:]
+    assert (out / "synthetic_echo_annotated.gif").exists() or "skipping the annotated gif" in r3.stdout
     r2 = subprocess.run([sys.executable, cli, "-p", str(avi), "-m", str(ckpt), "-d", "cpu"], capture_output=True, text=True, timeout=120)
     assert r2.returncode != 0 and "no CPU path" in (r2.stderr + r2.stdout)
 

@@ -143,3 +143,29 @@ def test_warp_fuse_oracle_properties():
     _, cnt_e, _ = fuse_ref.warp_fuse(prob, motion, starts, 32 + n + 3, edge_hops=True)
     _, cnt_s, _ = fuse_ref.warp_fuse(prob, motion, starts, 32 + n + 3, edge_hops=False)
     assert int(cnt_e.sum() - cnt_s.sum()) == 2 * n - 1          # clip 0's backward hop from t=0 lands on frame -1: dropped
+
+
+def test_ejection_fraction_matches_reference_golden(golden_dir):
+    """tests/golden/ef.npz: outputs of the UNMODIFIED reference compute_ef_using_putative_clips / get2dPucks (find_boundaries
+    bound to oracle/ef_ref.find_boundaries_thick, skimage being absent: that one function is unpinned).  Both the oracle's
+    line-by-line restatement and the product's re-organised host code must reproduce them."""
+    from clasfv_b200.src import fuse_utils
+    from oracle import ef_ref
+    g = _load(golden_dir, "ef.npz")
+    for tag in ("a", "b", "c"):
+        frames, period, seed = g[f"args_{tag}"]
+        masks = ef_ref.beating_masks(int(frames), 112, float(period), int(seed))
+        assert len(g[f"efs_{tag}"]) >= 2                                   # not vacuous: several heartbeats found
+        for impl in (ef_ref.compute_ef_using_putative_clips, fuse_utils.compute_ef_using_putative_clips):
+            efs, pairs = impl(masks, tag, return_edes=True)
+            np.testing.assert_allclose(np.array(efs), g[f"efs_{tag}"], rtol=1e-10)
+            assert np.array_equal(np.array(pairs, dtype=np.int64).reshape(-1, 2), g[f"pairs_{tag}"])
+        for pucks in (ef_ref.get_2d_pucks, fuse_utils.get2dPucks):
+            length, radii = pucks((masks[5] == 1).astype("int"), (1.0, 1.0))
+            np.testing.assert_allclose(np.concatenate([[length], radii]), g[f"pucks_{tag}"], rtol=1e-10)
+        # the LV area trace handed in (what the fusion kernels return) instead of summed from the masks
+        efs2 = fuse_utils.compute_ef_using_putative_clips(masks, tag, area=masks.reshape(len(masks), -1).sum(1))
+        np.testing.assert_allclose(np.array(efs2), g[f"efs_{tag}"], rtol=1e-10)
+    # degenerate inputs behave like the reference: empty mask -> (1.0, zeros)
+    length, radii = fuse_utils.get2dPucks(np.zeros((112, 112), dtype=int), (1.0, 1.0))
+    assert length == 1.0 and not radii.any()

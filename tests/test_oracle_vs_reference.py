@@ -69,3 +69,25 @@ def test_apply_sequence_deformation_matches_reference_function(ref, mode, forwar
         want = ref_vis.apply_sequence_deformation(src, motion, a, b, grid_mode=mode, forward=forward)
     got = fuse_ref.apply_sequence_deformation(src, motion, a, b, grid_mode=mode, forward=forward)
     assert torch.equal(want, got)
+
+
+def test_ef_matches_reference_functions(ref):
+    """oracle/ef_ref.py and the product's host EF code against the reference's compute_ef_using_putative_clips, EDESpairs and
+    get2dPucks run unmodified (find_boundaries bound to the restatement on both sides - skimage is absent)."""
+    from clasfv_b200.src import fuse_utils
+    from oracle import ef_ref
+    for frames, period, seed in ((130, 41.0, 7), (180, 52.0, 8)):
+        masks = ef_ref.beating_masks(frames, 112, period, seed)
+        want, want_pairs = ref.fuse_utils.compute_ef_using_putative_clips(masks, test_pat_index="t", return_edes=True)
+        assert len(want) >= 2
+        for impl in (ef_ref.compute_ef_using_putative_clips, fuse_utils.compute_ef_using_putative_clips):
+            got, pairs = impl(masks, "t", return_edes=True)
+            assert [tuple(map(int, p)) for p in pairs] == [tuple(map(int, p)) for p in want_pairs]
+            np.testing.assert_allclose(np.array(got), np.array(want), rtol=1e-12)
+        for f in (0, 11, 60):
+            lw, rw = ref.echo_utils.get2dPucks((masks[f] == 1).astype("int"), (1.0, 1.0))
+            for pucks in (ef_ref.get_2d_pucks, fuse_utils.get2dPucks):
+                lg, rg = pucks((masks[f] == 1).astype("int"), (1.0, 1.0))
+                np.testing.assert_allclose(np.concatenate([[lg], rg]), np.concatenate([[lw], rw]), rtol=1e-12)
+    d, s_ = [5, 40, 90, 91], [20, 22, 60, 130, 3]
+    assert fuse_utils.EDESpairs(d, s_) == ref.echonet_dataset.EDESpairs(d, s_) == ef_ref.edes_pairs(d, s_)
