@@ -25,6 +25,7 @@
 #include "umma_ptx.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -129,6 +130,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // the next kernel of the stream may be scheduled from here on (it parks in its own griddep_wait until this grid is done)
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -149,6 +152,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
             tma_load_3d(b_base + (uint32_t)((tap * kslabs + ks) * b_slab_bytes), &p.tmap_b, wres_bar, ks * SLAB_K,
                         (int)(blockIdx.x % (unsigned)tiles_n) * bn, p.tap_widx[tap]);
       }
+      griddep_wait();                             // weights are constants; activations are the preceding kernels' output
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % tiles_n;
@@ -253,6 +257,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
+    griddep_wait();                               // before the first residual load and the first store (write-after-read)
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;             // the two warps of a quarter take alternate 16-column chunks
     const int row = q * 32 + lane;
@@ -284,27 +289,33 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
                                  : (int64_t)ob * p.res_b_bstride + (int64_t)(ot + p.res_b_toff) * frame_elems + pix;
       const void* res_base = res_a ? p.residual : p.residual_b;
 
-      // the residual of the first chunk is requested before the accumulator is even complete
-      uint4 res_bf[2]; float4 res_f[4];
-      auto fetch_res = [&](int cc) {
+      // The residuals of this warp's first TWO chunks are requested before the accumulator is even complete, and chunk i + 2
+      // as soon as chunk i has been consumed: with a single chunk in flight the 64-column layers (two chunks per warp) exposed a
+      // whole L2 / DRAM latency per tile (ncu source view, profiles/r02_summary.md: 973 of 3 400 epilogue samples on that load).
+      uint4 res_bf[2][2]; float4 res_f[2][4];
+      auto fetch_res = [&](int cc, int buf) {
         if (!has_res) return;
         if (p.out_type == CLASFV_F32) {
           const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(res_base) + roff + cc);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) res_f[i] = __ldg(rp + i);
+          for (int i = 0; i < 4; ++i) res_f[buf][i] = __ldg(rp + i);
         } else {
           const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(res_base) + roff + cc);
-          res_bf[0] = __ldg(rp); res_bf[1] = __ldg(rp + 1);
+          res_bf[buf][0] = __ldg(rp); res_bf[buf][1] = __ldg(rp + 1);
         }
       };
       const int cc0 = half * 16;
-      if (cc0 < ncols) fetch_res(cc0);
+      if (cc0 < ncols) fetch_res(cc0, 0);
+      if (cc0 + 32 < ncols) fetch_res(cc0 + 32, 1);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.bn);
       uint32_t acc[16];
       if (cc0 < ncols) tc_ld16(taddr + (uint32_t)cc0, acc);
-      for (int cc = cc0; cc < ncols; cc += 32) {
+      // two chunks per trip, so that each residual buffer is named at compile time (registers, not local memory)
+      auto chunk = [&](int cc, auto rbuf) {
+        constexpr int RB = decltype(rbuf)::value;
+
         tc_wait_ld();
         float v[16];
 #pragma unroll
@@ -317,23 +328,23 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
         if (has_res) {
           if (p.out_type == CLASFV_F32) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { v[4 * i] += res_f[i].x; v[4 * i + 1] += res_f[i].y; v[4 * i + 2] += res_f[i].z; v[4 * i + 3] += res_f[i].w; }
+            for (int i = 0; i < 4; ++i) { v[4 * i] += res_f[RB][i].x; v[4 * i + 1] += res_f[RB][i].y; v[4 * i + 2] += res_f[RB][i].z; v[4 * i + 3] += res_f[RB][i].w; }
           } else if (p.out_type == CLASFV_F16) {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              const __half2* hh = reinterpret_cast<const __half2*>(&res_bf[i]);
+              const __half2* hh = reinterpret_cast<const __half2*>(&res_bf[RB][i]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(hh[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&res_bf[i]);
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&res_bf[RB][i]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hh[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
             }
           }
-          if (cc + 32 < ncols) fetch_res(cc + 32);
+          if (cc + 64 < ncols) fetch_res(cc + 64, RB);
         }
         if (p.relu) {
 #pragma unroll
@@ -369,6 +380,10 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
             }
           }
         }
+            };
+      for (int cc = cc0; cc < ncols; cc += 64) {
+        chunk(cc, std::integral_constant<int, 0>());
+        if (cc + 32 < ncols) chunk(cc + 32, std::integral_constant<int, 1>());
       }
       tc_fence_before();
       __syncwarp();
@@ -700,8 +715,7 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_b * p.tiles_n;
   int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (p.resident && p.tiles_n > 1) grid = std::max(grid / p.tiles_n, 1) * p.tiles_n;     // a CTA keeps one N tile: tile % tiles_n == blockIdx.x % tiles_n
-  conv_umma_kernel<<<grid, UMMA_THREADS, smem, stream>>>(p);
-  CLASFV_CUDA(cudaGetLastError());
+  CLASFV_CUDA(launch_pdl(conv_umma_kernel, dim3((unsigned)grid), dim3(UMMA_THREADS), smem, stream, p));
   return CLASFV_OK;
 }
 

@@ -289,9 +289,14 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   __syncthreads();
   tc_fence_after();
 
+  // Programmatic dependent launch: everything above touched only constants (weights, biases) and this CTA's own shared /
+  // tensor memory.  The lateral maps (producer) and the output planes (epilogue 2; the fusion kernel of the previous video
+  // may still be reading them) are the preceding kernels' business until griddep_wait() returns.
+  griddep_launch_dependents();
   if (warp == 0) {
     // ================================================================ producer
     if (elect_one()) {
+      griddep_wait();
       const int nb = g.nb, ntile = g.ntile, tiles_w = g.tiles_w;
       const uint32_t tx = (uint32_t)g.b_tx_bytes, stage_bytes = (uint32_t)g.b_stage_bytes;
       const uint32_t koff1 = (uint32_t)g.koff[1] * 128u, koff2 = (uint32_t)g.koff[2] * 128u, koff3 = (uint32_t)g.koff[3] * 128u;
@@ -452,6 +457,7 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int64_t plane = (int64_t)a.h * a.w;
     const int ntile = g.ntile, tiles_w = g.tiles_w;
+    griddep_wait();
     const bool lv_only = a.out_kind == CLASFV_OUT_LVPROB, prob_out = a.out_kind == CLASFV_OUT_PROB || lv_only;
     float bias[6];
 #pragma unroll
@@ -598,7 +604,7 @@ static int launch_head_typed(const HeadArgs& a, const HeadGeom& g, const HeadMap
 #define CLASFV_HEAD_LAUNCH(F16, KS)                                                               \
   do {                                                                                            \
     CLASFV_CUDA(allow_max_dynamic_smem(head_umma_kernel<OutT, F16, KS>));                         \
-    head_umma_kernel<OutT, F16, KS><<<grid, HU_THREADS, smem, stream>>>(a, g, maps, tab);         \
+    CLASFV_CUDA(launch_pdl(head_umma_kernel<OutT, F16, KS>, dim3((unsigned)grid), dim3(HU_THREADS), smem, stream, a, g, maps, tab)); \
   } while (0)
   if (a.tail_f16) {
     if (g.ksteps == 7) CLASFV_HEAD_LAUNCH(true, 7); else CLASFV_HEAD_LAUNCH(true, 8);

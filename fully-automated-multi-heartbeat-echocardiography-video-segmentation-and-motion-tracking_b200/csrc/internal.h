@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <utility>
 
 #include "../../include/clasfv_b200.h"
 
@@ -37,6 +38,22 @@ cudaError_t allow_max_dynamic_smem_impl(const void* kernel);     // api.cu: once
 template <typename Kernel>
 inline cudaError_t allow_max_dynamic_smem(Kernel kernel) { return allow_max_dynamic_smem_impl(reinterpret_cast<const void*>(kernel)); }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Launch with programmatic stream serialisation: the kernel may begin before its predecessor in the stream has finished
+// and MUST execute griddepcontrol.wait (ptx::griddep_wait) before it touches anything a predecessor reads or writes.
+// Off unless CLASFV_PDL=1 (it measured no gain, see pdl_enabled in api.cu); without the attribute the griddepcontrol
+// instructions in the kernels are no-ops.
+bool pdl_enabled();                                                  // api.cu
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---------------------------------------------------------------------------------------------
 constexpr int CLASFV_MAX_FSEL = 64;      // longest virtual clip of a frame-selected convolution

@@ -11,6 +11,12 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Programmatic dependent launch (kernels launched with launch_pdl, internal.h): the next kernel of the stream may start its
+// prologue - tensor-memory allocation, barrier set-up, constant weights - while this one drains; griddep_wait() is the point
+// after which everything the preceding kernels wrote is visible and everything they read may be overwritten.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }

@@ -181,12 +181,15 @@ def segment_a_video_with_fusion(video, model, interpolate_last=True, step=1, num
 
 
 class _VideoPipeline:
-    """State of segment_videos_with_fusion: two pinned staging slots and two device video slots per (shape), one copy
-    stream; prob / motion planes of the video in flight are reused when consecutive videos have the same shape."""
+    """State of segment_videos_with_fusion: two pinned staging slots and two device video slots, one copy stream per
+    direction; prob / motion planes of the video in flight are reused when consecutive videos have the same shape."""
 
     def __init__(self, eng):
         self.eng = eng
-        self.copy_stream = torch.cuda.Stream(device=eng.device)
+        # one stream per direction: on a single in-order copy stream the upload of video i+1 would queue behind the mask
+        # download of video i, which waits for video i's compute - and the GPU would idle for an upload per video
+        self.copy_stream = torch.cuda.Stream(device=eng.device)          # host -> device
+        self.back_stream = torch.cuda.Stream(device=eng.device)          # device -> host
         self.stage = [None, None]
         self.dev_video = [None, None]
         self.uploaded = [None, None]         # event: the slot's last host->device copy (its pinned buffer is reusable after it)
@@ -259,13 +262,13 @@ def segment_videos_with_fusion(videos, model, step=1, batch_clips=192, edge_hops
         pipe.consumed[slot] = done
         host = torch.empty(wide.shape, dtype=torch.int64, pin_memory=True)
         area = torch.empty(res["area"].shape, dtype=torch.int32, pin_memory=True) if return_details else None
-        with torch.cuda.stream(pipe.copy_stream):
-            pipe.copy_stream.wait_event(done)
+        with torch.cuda.stream(pipe.back_stream):
+            pipe.back_stream.wait_event(done)
             host.copy_(wide, non_blocking=True)
             if area is not None:
                 area.copy_(res["area"], non_blocking=True)
-            wide.record_stream(pipe.copy_stream)
-            res["area"].record_stream(pipe.copy_stream)
+            wide.record_stream(pipe.back_stream)
+            res["area"].record_stream(pipe.back_stream)
             back = torch.cuda.Event(); back.record()
         return host, area, back
 

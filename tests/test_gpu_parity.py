@@ -509,6 +509,27 @@ def test_warp_fuse_properties_at_config3_size(eng):
     assert int(rz["mask"].sum().item()) == 0                                             # ties go to background
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_warp_fuse_at_config3_size_against_the_oracle_on_sampled_frames(eng, dtype):
+    """BASELINE config 3 (256 stride-1 clips x 32 x 112 x 112, flows of a few pixels): the fused class sums, vote counts and
+    masks of sampled output frames - first, last, interior, one next to each end - against the CPU oracle, which is run
+    on just the clips that can vote on each sampled frame (the whole operator is 8 minutes of CPU)."""
+    n, h, w = 256, 112, 112
+    g = torch.Generator(device="cuda").manual_seed(5)
+    prob = torch.sigmoid(2 * torch.randn(n, 1, 32, h, w, generator=g, device="cuda")).to(dtype)
+    mot = torch.tanh(torch.randn(n, 4, 32, h, w, generator=g, device="cuda") * (3.0 / 56.0)).to(dtype)
+    starts, t_out = list(range(n)), n + 31
+    r = eng.warp_fuse(prob, mot, starts, t_out)
+    for frame in (0, 1, 143, 285, 286):
+        clips = [c for c in range(n) if frame - 32 <= starts[c] <= frame + 1]
+        acc, cnt, mask = fuse_ref.warp_fuse(prob[clips].float().cpu(), mot[clips].float().cpu(), [starts[c] for c in clips], t_out)
+        assert int(r["cnt"][frame]) == int(cnt[frame])
+        got = r["acc"][frame].cpu()
+        assert float((got - acc[frame].float()).abs().max()) <= 1e-5 * float(cnt[frame])          # fp32 sums of <= 94 votes
+        margin = (acc[frame, 1] - acc[frame, 0]).abs()
+        assert torch.equal(r["mask"][frame].cpu()[margin > 1e-4], mask[frame][margin > 1e-4])
+
+
 # ------------------------------------------------------------------------------------------ pipelines
 def test_reference_exact_fusion_matches_oracle(net_fp32, sd):
     video = synthetic.synthetic_echo_video(75, 32, 48, seed=3)
