@@ -262,6 +262,14 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
     const int half = (warp - 2) >> 2;             // the two warps of a quarter take alternate 16-column chunks
     const int row = q * 32 + lane;
     const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
+    // Position of this thread's row inside the output box: the same for every tile, so the divisions by the box extents
+    // are done once.  For the short-K layers (everything with 64 output columns: a tile is 27-36 MMAs) the epilogue is the
+    // critical path, and a third of its instructions were this index arithmetic repeated per tile (ncu source view).
+    int r = row;
+    const int iw = r % p.bw; r /= p.bw;
+    const int ih = r % p.bh; r /= p.bh;
+    const int itt = r % p.bt; r /= p.bt;
+    const int ib = r;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1; const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -271,11 +279,6 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
       const int h0 = (mt % p.tiles_h) * p.bh; mt /= p.tiles_h;
       const int t0 = (mt % p.tiles_t) * p.bt; mt /= p.tiles_t;
       const int b0 = mt * p.bb;
-      int r = row;
-      const int iw = r % p.bw; r /= p.bw;
-      const int ih = r % p.bh; r /= p.bh;
-      const int itt = r % p.bt; r /= p.bt;
-      const int ib = r;
       const int ow = w0 + iw, oh = h0 + ih, ot = t0 + itt, ob = b0 + ib;
       const bool valid = ib < p.bb && ow < p.wo && oh < p.ho && ot < p.to && ob < p.n;
       const int c0 = n_tile * p.bn;
@@ -317,67 +320,62 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
         constexpr int RB = decltype(rbuf)::value;
 
         tc_wait_ld();
-        float v[16];
+        // 16 accumulator columns as 8 pairs: packed fp32 adds (FADD2) for the bias and the residual, ReLU folded into the
+        // 16-bit conversion (cvt.rn.relu) - for the 64-column layers the epilogue is the critical path
+        float2 v[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + cc + 4 * i);
-          v[4 * i] = __uint_as_float(acc[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b4.y;
-          v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4.w;
+          v[2 * i] = __fadd2_rn(make_float2(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1])), make_float2(b4.x, b4.y));
+          v[2 * i + 1] = __fadd2_rn(make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])), make_float2(b4.z, b4.w));
         }
         if (cc + 32 < ncols) tc_ld16(taddr + (uint32_t)(cc + 32), acc);      // next chunk's accumulators in flight
         if (has_res) {
           if (p.out_type == CLASFV_F32) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { v[4 * i] += res_f[RB][i].x; v[4 * i + 1] += res_f[RB][i].y; v[4 * i + 2] += res_f[RB][i].z; v[4 * i + 3] += res_f[RB][i].w; }
+            for (int i = 0; i < 4; ++i) {
+              v[2 * i] = __fadd2_rn(v[2 * i], make_float2(res_f[RB][i].x, res_f[RB][i].y));
+              v[2 * i + 1] = __fadd2_rn(v[2 * i + 1], make_float2(res_f[RB][i].z, res_f[RB][i].w));
+            }
           } else if (p.out_type == CLASFV_F16) {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const __half2* hh = reinterpret_cast<const __half2*>(&res_bf[RB][i]);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(hh[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+              for (int j = 0; j < 4; ++j) v[4 * i + j] = __fadd2_rn(v[4 * i + j], __half22float2(hh[j]));
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&res_bf[RB][i]);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hh[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+              for (int j = 0; j < 4; ++j) v[4 * i + j] = __fadd2_rn(v[4 * i + j], __bfloat1622float2(hh[j]));
             }
           }
           if (cc + 64 < ncols) fetch_res(cc + 64, RB);
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (valid) {
           if (p.out_type == CLASFV_F32) {
             float* o = static_cast<float*>(p.out) + off + cc;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else if (p.out_type == CLASFV_F16) {
-            // saturating conversion: a value beyond +-65504 stores the largest finite fp16, never an infinity
-            __half* o = static_cast<__half*>(p.out) + off + cc;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              uint4 w4;
-              w4.x = cvt_f16x2_sat(v[8 * i + 0], v[8 * i + 1]); w4.y = cvt_f16x2_sat(v[8 * i + 2], v[8 * i + 3]);
-              w4.z = cvt_f16x2_sat(v[8 * i + 4], v[8 * i + 5]); w4.w = cvt_f16x2_sat(v[8 * i + 6], v[8 * i + 7]);
-              reinterpret_cast<uint4*>(o)[i] = w4;
+            for (int i = 0; i < 4; ++i) {
+              float4 w4 = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y);
+              if (p.relu) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
+              reinterpret_cast<float4*>(o)[i] = w4;
             }
           } else {
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + off + cc;
+            // fp16: saturating conversion (a value beyond +-65504 stores the largest finite fp16, never an infinity)
+            uint32_t pk[8];
+            if (p.out_type == CLASFV_F16) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              uint4 w4;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-              w4.x = *reinterpret_cast<uint32_t*>(&h0); w4.y = *reinterpret_cast<uint32_t*>(&h1);
-              w4.z = *reinterpret_cast<uint32_t*>(&h2); w4.w = *reinterpret_cast<uint32_t*>(&h3);
-              reinterpret_cast<uint4*>(o)[i] = w4;
+              for (int i = 0; i < 8; ++i) pk[i] = p.relu ? cvt_relu_16x2<true>(v[i].x, v[i].y) : cvt_f16x2_sat(v[i].x, v[i].y);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[i] = p.relu ? cvt_relu_16x2<false>(v[i].x, v[i].y) : cvt_bf16x2(v[i].x, v[i].y);
             }
+            uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + off + cc);
+            o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
             };

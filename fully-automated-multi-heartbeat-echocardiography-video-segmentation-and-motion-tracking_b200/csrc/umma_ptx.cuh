@@ -101,6 +101,19 @@ __device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {
   return d;
 }
 
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+// {low half = relu(a), high half = relu(b)} in fp16 (saturating) or bf16: ReLU and the conversion are one instruction
+template <bool F16> __device__ __forceinline__ uint32_t cvt_relu_16x2(float a, float b) {
+  uint32_t d;
+  if (F16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+
 // instruction descriptor: D=f32, A=B=bf16, both K-major (cute::UMMA::InstrDescriptor)
 __host__ __device__ inline uint32_t idesc_bf16_f32(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
