@@ -156,6 +156,7 @@ def run_reference_arm(args, rank):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(),
+        "value_is": "EXTRAPOLATED: seconds per clip of the sample x 169 clips (a whole video is 2 CPU-minutes per step)",
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": vals[0]["threads"], "kind": "port",
                          "sample": f"{sample} of {N_CLIPS} stride-1 clips per step (reference network on PyTorch CPU + oracle warp-fuse), "
                                    f"scaled to the 169-clip video; {wall:.1f}s of CPU work"},

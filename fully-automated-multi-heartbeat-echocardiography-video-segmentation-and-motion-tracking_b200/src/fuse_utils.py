@@ -221,12 +221,14 @@ class _VideoPipeline:
         return dev, ev, slot
 
     def plane_buffers(self, n, h, w, dtype):
-        key = (n, h, w, dtype)
-        if self.planes is None or self.planes[0] != key:
-            self.planes = None               # release before allocating the next shape
+        """(n,1,32,h,w) LV-probability and (n,4,32,h,w) motion planes as views of two flat buffers that only ever grow:
+        videos of different lengths reuse them instead of sending a new size through the allocator per video."""
+        need = n * CLIP * h * w
+        if self.planes is None or self.planes[0] != dtype or self.planes[1].numel() < need:
+            self.planes = None               # release before allocating the larger buffers
             dev = self.eng.device
-            self.planes = (key, torch.empty((n, 1, CLIP, h, w), dtype=dtype, device=dev), torch.empty((n, 4, CLIP, h, w), dtype=dtype, device=dev))
-        return self.planes[1], self.planes[2]
+            self.planes = (dtype, torch.empty(need, dtype=dtype, device=dev), torch.empty(4 * need, dtype=dtype, device=dev))
+        return self.planes[1][:need].view(n, 1, CLIP, h, w), self.planes[2][:4 * need].view(n, 4, CLIP, h, w)
 
 
 def segment_videos_with_fusion(videos, model, step=1, batch_clips=192, edge_hops=False, return_details=False):
