@@ -17,8 +17,9 @@
 // TMA box load per level lands them in shared memory as MN-major SWIZZLE_128B rows - and its A operand is the patch's
 // constant interpolation matrix A[v, k] = fp16(wH(v, y) * wW(v, x)) (four non-zeros per level and voxel).  A depends only
 // on the patch position, not on (clip, frame): the matrices of all patches of the frame geometry are built once
-// (head_table_kernel, cached per geometry by the handle) and a CTA keeps one in shared memory while it sweeps the frames
-// of a clip.  There is no CUDA-core interpolation stage at all: round 1's row-at-a-time kernel spent its time there
+// (head_table_kernel, cached per geometry by the handle) and a CTA keeps one in TENSOR memory while it sweeps the frames
+// of a clip (bulk copy -> shared memory -> tcgen05.cp; an SS-mode 128x64x16 MMA reads 6 KB of shared memory per 32 clocks
+// of math and measured 60 clocks: with A in tensor memory the head went from 2.65 to 2.22 ms per video).  There is no CUDA-core interpolation stage at all: round 1's row-at-a-time kernel spent its time there
 // (VERDICT r1 "what's weak" 3).
 //
 // Warp roles (768 threads, persistent, one CTA per SM); every hand-over is an mbarrier, every buffer at least doubled:
@@ -122,11 +123,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-#ifdef HEAD_TEST_WAIT
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#endif
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (!done) {
@@ -276,6 +273,9 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
   const uint32_t acc0 = tmem_base, acc1 = tmem_base + 128u, acc2 = tmem_base + 256u;   // 2 x 64, 2 x 64, 2 x 16 columns
   // relu(h1): 2 stages x 40 columns (32 of data + 8 for K 64..79 = {1, 1, 0, ...}: the bias columns); relu(h2): 2 x 32
   const uint32_t tmem_a1 = tmem_base + 288u, tmem_a2 = tmem_base + 368u;
+  // the patch's interpolation matrix as a tensor-memory A operand: 128 K columns x 16 bit = 64 columns, copied from the
+  // shared-memory staging buffer by tcgen05.cp at the start of every unit (432 + 64 = 496 of the 512 columns)
+  const uint32_t tmem_wa = tmem_base + 432u;
   if (warp >= 4 && warp < 8) {
     // constant bias columns of both relu(h1) stages: K 64 and 65 = 1.0, K 66..79 = 0
     const uint32_t ones = TAIL_F16 ? 0x3C003C00u : 0x3F803F80u;
@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
     // kernel (ncu source view of the first version: ~150 instructions of predicate and R2UR plumbing per tile, 70 % busy),
     // so the loop body is kept to the waits, a handful of 32-bit adds and the MMAs: the descriptors' high words are
     // constants, the low words advance by compile-time offsets, the step count is a template parameter.
-    // A = fp16 interpolation weights (K-major, shared memory), B = the raw fp16 lateral pixels, MN-major
+    // A = fp16 interpolation weights (tensor memory, staged through a K-major shared-memory buffer), B = the raw fp16
+    // lateral pixels, MN-major
     const uint32_t idesc0 = idesc_f16_f32(128, 64) | (1u << 16);
     const uint64_t desc0 = smem_desc_sw128(0);
     const uint32_t desc_hi = (uint32_t)(desc0 >> 32);
@@ -356,17 +357,21 @@ __global__ void __launch_bounds__(HU_THREADS, 1) head_umma_kernel(const HeadArgs
       const uint32_t a_lo = a_lo0 + ab * (A_BYTES >> 4), b_lo = b_lo0 + (uint32_t)bstage * (uint32_t)(B_STAGE_BYTES >> 4);
       const uint32_t d0 = acc0 + s * 64u;
       if (elect_one()) {
+        if (tin == 0) {
+          // new unit: its interpolation matrix from shared memory to tensor memory, 16 K columns (32 bytes of every row) per
+          // copy.  tcgen05.cp and tcgen05.mma execute in issue order, so the copy runs after the previous unit's last MMA 0
+          // has read the old matrix and before this unit's first; the staging buffer is free once the copies have completed.
 #pragma unroll
-#ifdef HEAD_EXPERIMENT_K0
-        for (int kk = 0; kk < HEAD_EXPERIMENT_K0; ++kk)
-#else
+          for (int kk = 0; kk < KSTEPS; ++kk)
+            asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_wa + (uint32_t)(kk * 8)),
+                         "l"(((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)((kk >> 2) * 1024 + (kk & 3) * 2))) : "memory");
+          tc_commit(bar(A_EMPTY, ab));
+        }
+#pragma unroll
         for (int kk = 0; kk < KSTEPS; ++kk)
-#endif
-          tc_mma_bf16(d0, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)((kk >> 2) * 1024 + (kk & 3) * 2)),
-                      ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)(kk * 128)), idesc0, kk ? 1u : 0u);
+          tc_mma_ts_f16(d0, tmem_wa + (uint32_t)(kk * 8), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)(kk * 128)), idesc0, kk ? 1u : 0u);
         tc_commit(bar(B_EMPTY, bstage));
         tc_commit(bar(ACC0_FULL, s));
-        if (tin == T - 1) tc_commit(bar(A_EMPTY, ab));
       }
       __syncwarp();
       if (++bstage == nb) { bstage = 0; bphase ^= 1u; }

@@ -42,3 +42,16 @@ def test_sixteen_bit_storage_noise_is_ordered():
     # the bf16 floor is a property of the number format on these weights, not of any implementation
     w = _metrics(*model_emul.forward(sd, x, Config(head="patch", **{**FP32, "wtrunk": "bf16"})), seg_ref, mot_ref, 64)
     assert w[0] > 3 * h[0]
+
+
+def test_bf16_weight_rounding_alone_breaks_the_gates_at_the_production_shape():
+    """on the parity fixture, rounding ONLY the trunk's (BatchNorm-folded) weights to bf16 - activations,
+    lateral maps, the whole head in fp32 - already violates the north-star's 16-bit gates (softmax max-abs <= 2e-2, argmax
+    agreement >= 99.9 %), so no implementation with bf16 operands can meet them on these weights; fp16 weights do not."""
+    sd = fixtures.calibrated_state_dict(0)
+    x = fixtures.synthetic_clip(32, 112, 112, seed=13, batch=1)
+    seg_ref, mot_ref = model_ref.forward(sd, x)
+    wb = _metrics(*model_emul.forward(sd, x, Config(head="patch", **{**FP32, "wtrunk": "bf16"})), seg_ref, mot_ref, 112)
+    wh = _metrics(*model_emul.forward(sd, x, Config(head="patch", **{**FP32, "wtrunk": "f16"})), seg_ref, mot_ref, 112)
+    assert wb[0] > 2e-2 and wb[1] < 0.999, wb                 # bf16 weights: 0.098 / 99.34 % measured
+    assert wh[0] <= 2e-2 and wh[1] >= 0.999, wh               # fp16 weights: 0.011 / 99.92 %
