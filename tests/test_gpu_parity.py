@@ -305,7 +305,7 @@ def test_forward_bf16_against_oracle_and_autocast_yardstick(net_bf16, sd):
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])
-@pytest.mark.parametrize("t,h,w", [(8, 112, 112), (4, 224, 224), (8, 48, 144), (8, 32, 32)])
+@pytest.mark.parametrize("t,h,w", [(8, 112, 112), (4, 224, 224), (8, 48, 144), (8, 32, 32), (8, 16, 16), (2, 16, 512), (2, 512, 16)])
 def test_decoder_head_alone_matches_its_emulation(sd, net_bf16, net_fp16, precision, t, h, w):
     """The fused tensor-core head (csrc/decoder_umma.cu) on caller-supplied fp16 lateral maps against the emulation of
     its arithmetic on the SAME maps (oracle/model_emul.py:head): interpolation weights fp16(wH*wW), fp32 accumulation,
@@ -428,7 +428,9 @@ def test_tensor_core_head_geometries_against_fp32_path(net_bf16, net_fp32, t, h,
     (43, 32, 32, 32, 1, 5),        # 12 windows, ragged last batch
     (40, 16, 48, 32, 2, 16),       # stride-2 windows, shortest clip the schedule accepts, one batch
     (52, 32, 112, 112, 1, 8),      # the benchmark geometry (56x56 layer-1 maps)
-    (22, 16, 224, 224, 1, 4),      # config-5 geometry: 112x112 layer-1 maps, head with two 128-voxel w tiles
+    (22, 16, 224, 224, 1, 4),      # config-5 geometry: 112x112 layer-1 maps
+    (70, 64, 32, 32, 1, 8),        # the longest clip the frame-selected inputs take (64 frames)
+    (45, 40, 16, 16, 1, 3),        # smallest frame: the deepest maps are 1 x 1
 ])
 def test_dense_video_schedule_is_bit_identical_to_per_clip(net_bf16, tv, clip_len, h, w, step, sub_batch):
     """Sharing the stem and layer1 between overlapping windows (csrc/api.cu, Forward::run_dense) must not change a
