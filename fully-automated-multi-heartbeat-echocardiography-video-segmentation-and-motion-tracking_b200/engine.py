@@ -34,6 +34,7 @@ class Engine:
     """One packed CLAS-FV network on one CUDA device."""
 
     MAX_RUN = 1024        # windows per clasfv_forward call of forward_windows
+    WORKSPACE_BUDGET = 64e9   # bytes of activation workspace forward_windows lets an internal batch take
 
     def __init__(self, device):
         self.lib = _lib.lib()
@@ -127,6 +128,10 @@ class Engine:
         """All windows [s, s+clip_len) of a resident video (3,Tv,H,W) in as few calls as possible: every maximal run
         of equally spaced starts is ONE clasfv_forward call, so the library can share the stem and layer1 between
         the overlapping windows (dense-video schedule) and batches internally (``batch_clips`` per batch)."""
+        # the library's workspace grows with the internal batch: about 130 MB per 32 x 112 x 112 clip in a 16-bit mode (twice
+        # that in fp32), proportional to the clip's voxels - keep it under WORKSPACE_BUDGET whatever the frame size
+        per_clip = 130e6 * (clip_len / 32.0) * (video.shape[2] * video.shape[3]) / (112.0 * 112.0) * (2 if self.precision == F32 else 1)
+        batch_clips = max(1, min(int(batch_clips), int(self.WORKSPACE_BUDGET // per_clip)))
         self.set_option("sub_batch", batch_clips)
         starts = [int(s) for s in clip_starts]
         i, n = 0, len(starts)

@@ -106,7 +106,7 @@ def test_forward_windows_groups_equally_spaced_runs_into_single_calls():
 
     class Recorder(Engine):
         def __init__(self):
-            self.calls, self.options = [], {}
+            self.calls, self.options, self.precision = [], {}, 1
 
         def set_option(self, name, value):
             self.options[name] = value
