@@ -33,10 +33,13 @@ __device__ __forceinline__ float linspace_pm1(int idx, int steps) {
 // Every kernel in this file evaluates the sampling arithmetic through the helpers below with explicit rounding intrinsics.
 // Left to the compiler, `a*b + c*d` may be contracted into fma(a, b, rn(c*d)) or fma(c, d, rn(a*b)) - it chose differently
 // in different kernels, which made the direct-gather and the staged warp-fuse kernels disagree in the last bit.
-// grid_sample's unnormalise for align_corners=False: ((g + 1) * size - 1) / 2
-__device__ __forceinline__ float unnormalize(float g, float size) {
-  return __fmul_rn(__fmaf_rn(__fadd_rn(g, 1.f), size, -1.f), 0.5f);
+// grid_sample's unnormalise for align_corners=False: ((g + 1) * size - 1) / 2.  ATen rounds rn(rn(g + 1) * size - 1) (one fused
+// multiply-add) and halves it; halving is exact, so rn(x) / 2 == rn(x / 2) and the halving folds into the constants:
+// rn(rn(g + 1) * (size / 2) - 1/2) is the same fp32 number with one instruction fewer (size / 2 is exact).
+__device__ __forceinline__ float unnormalize_half(float g, float half_size) {
+  return __fmaf_rn(__fadd_rn(g, 1.f), half_size, -0.5f);
 }
+__device__ __forceinline__ float unnormalize(float g, float size) { return unnormalize_half(g, size * 0.5f); }
 // nw*a + ne*b + sw*c + se*d, accumulated left to right, one rounding per step
 __device__ __forceinline__ float tap_sum(float a, float nw, float b, float ne, float c, float sw, float d, float se) {
   return __fmaf_rn(d, se, __fmaf_rn(c, sw, __fmaf_rn(b, ne, __fmul_rn(a, nw))));
@@ -279,9 +282,11 @@ constexpr int WS_PP = 2;
 
 template <typename T> struct Item;
 template <> struct Item<float> {
-  static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) {
-    const float2 o = __ldg(reinterpret_cast<const float2*>(p)); v[0] = o.x; v[1] = o.y;
-  }
+  using Raw = float2;
+  static __device__ __forceinline__ Raw ld_raw(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ void unpack(const Raw& o, float (&v)[2]) { v[0] = o.x; v[1] = o.y; }
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) { unpack(ld_raw(p), v); }
+  static __device__ __forceinline__ void lds(const float* p, float (&v)[2]) { unpack(*reinterpret_cast<const float2*>(p), v); }
   static __device__ __forceinline__ void ld_acc(const float* p, float (&v)[2]) {
     const float2 o = *reinterpret_cast<const float2*>(p); v[0] = o.x; v[1] = o.y;
   }
@@ -291,10 +296,13 @@ template <> struct Item<float> {
   }
 };
 template <> struct Item<__nv_bfloat16> {
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[2]) {
-    const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(p));
+  using Raw = uint32_t;
+  static __device__ __forceinline__ Raw ld_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[2]) {
     v[0] = __uint_as_float(r << 16); v[1] = __uint_as_float(r & 0xffff0000u);
   }
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[2]) { unpack(ld_raw(p), v); }
+  static __device__ __forceinline__ void lds(const __nv_bfloat16* p, float (&v)[2]) { unpack(*reinterpret_cast<const uint32_t*>(p), v); }
   static __device__ __forceinline__ void ld_acc(const float* p, float (&v)[2]) {
     const float2 o = *reinterpret_cast<const float2*>(p); v[0] = o.x; v[1] = o.y;
   }
@@ -304,10 +312,13 @@ template <> struct Item<__nv_bfloat16> {
   }
 };
 template <> struct Item<__half> {
-  static __device__ __forceinline__ void ld(const __half* p, float (&v)[2]) {
-    const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(p));
+  using Raw = uint32_t;
+  static __device__ __forceinline__ Raw ld_raw(const __half* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[2]) {
     const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r)); v[0] = f.x; v[1] = f.y;
   }
+  static __device__ __forceinline__ void ld(const __half* p, float (&v)[2]) { unpack(ld_raw(p), v); }
+  static __device__ __forceinline__ void lds(const __half* p, float (&v)[2]) { unpack(*reinterpret_cast<const uint32_t*>(p), v); }
   static __device__ __forceinline__ void ld_acc(const float* p, float (&v)[2]) {
     const float2 o = *reinterpret_cast<const float2*>(p); v[0] = o.x; v[1] = o.y;
   }
@@ -332,17 +343,22 @@ template <> __device__ __forceinline__ float lds_val<__nv_bfloat16>(const __nv_b
 // is exact, so both are one rounding of the same real number.
 struct Taps { int p; float nw, ne, sw, se; };
 struct TapGeom {                      // loop invariants of taps_setup, converted once per thread
-  float wf, hf, wm1, hm1, wm2, hm2;
+  float wf, whalf, hhalf, wm1, hm1, wm2, hm2;
   __device__ __forceinline__ TapGeom(int h, int w)
-      : wf((float)w), hf((float)h), wm1((float)(w - 1)), hm1((float)(h - 1)), wm2((float)(w - 2)), hm2((float)(h - 2)) {}
+      : wf((float)w), whalf(0.5f * (float)w), hhalf(0.5f * (float)h), wm1((float)(w - 1)), hm1((float)(h - 1)), wm2((float)(w - 2)), hm2((float)(h - 2)) {}
 };
+// CLAMP_NW = false: the plane is followed by W + 2 zero elements (flow-staged ring units), so the north-west corner may sit
+// on the last row / column as grid_sample has it - the corners past the plane have weight exactly 0 and read zeros or
+// the next row's first pixel (a finite probability): the same sum again, two instructions fewer per tap set.
+template <bool CLAMP_NW>
 __device__ __forceinline__ Taps taps_setup(float bx, float by, float fx, float fy, const TapGeom& g) {
   const float gx = bx + fx, gy = by + fy;
-  float ix = unnormalize(gx, g.wf);
-  float iy = unnormalize(gy, g.hf);
+  float ix = unnormalize_half(gx, g.whalf);
+  float iy = unnormalize_half(gy, g.hhalf);
   ix = fminf(g.wm1, fmaxf(ix, 0.f));
   iy = fminf(g.hm1, fmaxf(iy, 0.f));
-  const float fx0 = fminf(floorf(ix), g.wm2), fy0 = fminf(floorf(iy), g.hm2);
+  float fx0 = floorf(ix), fy0 = floorf(iy);
+  if (CLAMP_NW) { fx0 = fminf(fx0, g.wm2); fy0 = fminf(fy0, g.hm2); }
   const float wx1 = ix - fx0, wy1 = iy - fy0;
   const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
   Taps t;
@@ -359,16 +375,24 @@ __device__ __forceinline__ float taps_fetch(const T* plane, const Taps& t, int w
   return tap_sum(lds_val<T>(p), t.nw, lds_val<T>(p + 1), t.ne, lds_val<T>(p + w), t.sw, lds_val<T>(p + w + 1), t.se);
 }
 
-template <typename T, int WS_THREADS, int ITEMS>
-__global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const WarpFuseArgs a, int n_units, int slice_pix) {
+// FLOWS = true (round 2, the default whenever two such units fit): a ring unit also carries the CTA's pixel slice of the hop's
+// two flow planes, [LV plane][W + 2 zeros][flow x slice][flow y slice], all three filled by the producer's bulk copies.  With
+// the flows read from global memory by the consumers, 47 % of a warp's latency per instruction was the wait on those loads
+// (ncu, profiles/r02_wf_ncu.csv: long scoreboard 3.3 of 7.0 cycles per issue; every warp of the CTA issued them at the
+// same point - right after being released by the same barrier); now DRAM latency is hidden by the depth of the ring, the
+// consumers' flow reads are conflict-free LDS, the 28 registers that held a hop's flows are gone, and the only global loads left
+// to the consumers - the direct votes - are requested one clip ahead.
+template <typename T, int WS_THREADS, int ITEMS, bool FLOWS>
+__global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const WarpFuseArgs a, int n_units, int slice_pix, uint32_t unit_bytes,
+                                                                          uint32_t pad_bytes, uint32_t slice_stride) {
   extern __shared__ __align__(128) uint8_t ws_smem[];
   using namespace ptx;
+  using Raw = typename Item<T>::Raw;
   constexpr int PP = WS_PP, WS_CONSUMERS = WS_THREADS - 32;   // warp 0 = producer
   const int g = blockIdx.y;
   const int hw = a.h * a.w;
   const int L = a.clip_len;
   const uint32_t plane_bytes = (uint32_t)hw * (uint32_t)sizeof(T);
-  const uint32_t unit_bytes = plane_bytes;                  // one ring unit = the LV plane of one hop's source frame
   const uint32_t sbase = smem_u32(ws_smem);
   const uint32_t bar0 = sbase + (uint32_t)n_units * unit_bytes;         // full[u] at bar0 + 8u, empty[u] at bar0 + 8(n_units + u)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -376,30 +400,47 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
   const T* __restrict__ mot = static_cast<const T*>(a.motion);
   const int64_t clip_elems = (int64_t)a.prob_planes * L * hw;
   const int lo = __ldg(a.frame_lo + g), hi = __ldg(a.frame_hi + g);
+  const int pix0 = blockIdx.x * slice_pix;
+  const int pix_end = min(hw, pix0 + slice_pix);
 
   if (threadIdx.x == 0) {
     for (int u = 0; u < n_units; ++u) { mbar_init(bar0 + 8u * u, 1); mbar_init(bar0 + 8u * (n_units + u), WS_CONSUMERS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (FLOWS) {          // the zero elements behind every unit's plane (never written by a bulk copy)
+    const int words = (int)(pad_bytes >> 2);
+    for (int i = threadIdx.x; i < n_units * words; i += WS_THREADS)
+      *reinterpret_cast<uint32_t*>(ws_smem + (size_t)(i / words) * unit_bytes + plane_bytes + 4u * (uint32_t)(i % words)) = 0u;
+  }
   __syncthreads();
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- producer: one bulk copy per class plane of every hop
+    // ---------------------------------------------------------------- producer: the bulk copies of every hop
     if (lane == 0) {
+      const uint32_t slice_bytes = (uint32_t)(pix_end - pix0) * (uint32_t)sizeof(T);
+      const uint32_t tx = plane_bytes + (FLOWS ? 2u * slice_bytes : 0u);
       int item = 0;
       for (int c = lo; c < hi; ++c) {
         const int t = g - __ldg(a.clip_start + c);
         const T* pc = prob + (int64_t)c * clip_elems;
+        const T* mc = mot + (int64_t)c * 4 * L * hw + pix0;
         for (int hop = 0; hop < 2; ++hop) {
           const int ts = hop == 0 ? t - 1 : t + 1;
           const bool on = ts >= 0 && ts < L && (a.edge_hops || (hop == 0 ? ts + 1 < L : ts >= 1));
           if (!on) continue;
           const int u = item % n_units; const uint32_t ph = (uint32_t)(item / n_units) & 1u;
           mbar_wait(bar0 + 8u * (n_units + u), ph ^ 1u);
-          mbar_arrive_expect_tx(bar0 + 8u * u, unit_bytes);
+          mbar_arrive_expect_tx(bar0 + 8u * u, tx);
           const uint32_t dst = sbase + (uint32_t)u * unit_bytes;
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                        ::"r"(dst), "l"(pc + (int64_t)ts * hw), "r"(plane_bytes), "r"(bar0 + 8u * u) : "memory");
+          if (FLOWS) {
+            const uint32_t fdst = dst + plane_bytes + pad_bytes;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(fdst), "l"(mc + (int64_t)((hop == 0 ? 0 : 2 * L) + ts) * hw), "r"(slice_bytes), "r"(bar0 + 8u * u) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(fdst + slice_stride), "l"(mc + (int64_t)((hop == 0 ? L : 3 * L) + ts) * hw), "r"(slice_bytes), "r"(bar0 + 8u * u) : "memory");
+          }
           ++item;
         }
       }
@@ -418,10 +459,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
       a.cnt[g] = (a.accumulate ? a.cnt[g] : 0) + votes;
     }
   } else {
-    // ---------------------------------------------------------------- consumers: fixed items (pixels / pixel pairs), sums in registers
+    // ---------------------------------------------------------------- consumers: fixed items (pixel pairs), sums in registers
     const int ctid = threadIdx.x - 32;
-    const int pix0 = blockIdx.x * slice_pix;
-    const int pix_end = min(hw, pix0 + slice_pix);
     const int p0 = pix0 + PP * ctid;                       // item k of this thread starts at pixel p0 + k * PP * WS_CONSUMERS
     constexpr int ITEM_STEP = PP * WS_CONSUMERS;
     // items past the slice end are simply not there: n_items is the same for all but the last lanes of a slice
@@ -441,44 +480,72 @@ __global__ void __launch_bounds__(WS_THREADS, 1) warp_fuse_staged_kernel(const W
     int votes = 0;
     const TapGeom geom(a.h, a.w);
     int item = 0;
+    // direct votes of clip c: requested while clip c - 1 is being processed (FLOWS), consumed first thing in clip c's turn
+    Raw dv[ITEMS];
+    auto request_direct = [&](int c) {
+      const int t = g - __ldg(a.clip_start + c);
+      if (t < 0 || t >= L) return;
+      const T* d1 = prob + (int64_t)c * clip_elems + (int64_t)t * hw + p0;
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k)
+        if (k < n_items) dv[k] = Item<T>::ld_raw(d1 + k * ITEM_STEP);
+    };
+    if (FLOWS && lo < hi) request_direct(lo);
     for (int c = lo; c < hi; ++c) {
       const int t = g - __ldg(a.clip_start + c);
-      const T* pc = prob + (int64_t)c * clip_elems + p0;
-      const T* mc = mot + (int64_t)c * 4 * L * hw + p0;
       if (t >= 0 && t < L) {                                   // direct vote
-        const T* d1 = pc + (int64_t)t * hw;
         ++votes;
+        if (!FLOWS) request_direct(c);
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
           if (k >= n_items) break;
           float v1[PP];
-          Item<T>::ld(d1 + k * ITEM_STEP, v1);
+          Item<T>::unpack(dv[k], v1);
 #pragma unroll
           for (int q = 0; q < PP; ++q) s1[k][q] += v1[q];
         }
       }
+      if (FLOWS && c + 1 < hi) request_direct(c + 1);
+      const T* mc = mot + (int64_t)c * 4 * L * hw + p0;
 #pragma unroll
       for (int hop = 0; hop < 2; ++hop) {
         const int ts = hop == 0 ? t - 1 : t + 1;
         const bool on = ts >= 0 && ts < L && (a.edge_hops || (hop == 0 ? ts + 1 < L : ts >= 1));
         if (!on) continue;
         ++votes;
-        const T* fxp = mc + (int64_t)((hop == 0 ? 0 : 2 * L) + ts) * hw;
-        const T* fyp = mc + (int64_t)((hop == 0 ? L : 3 * L) + ts) * hw;
-        float fx[ITEMS][PP], fy[ITEMS][PP];
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k)
-          if (k < n_items) { Item<T>::ld(fxp + k * ITEM_STEP, fx[k]); Item<T>::ld(fyp + k * ITEM_STEP, fy[k]); }
         const int u = item % n_units; const uint32_t ph = (uint32_t)(item / n_units) & 1u;
-        mbar_wait(bar0 + 8u * u, ph);
         const T* u1 = reinterpret_cast<const T*>(ws_smem + (size_t)u * unit_bytes);
+        if (FLOWS) {
+          const T* ufx = reinterpret_cast<const T*>(ws_smem + (size_t)u * unit_bytes + plane_bytes + pad_bytes) + PP * ctid;
+          const T* ufy = reinterpret_cast<const T*>(reinterpret_cast<const uint8_t*>(ufx) + slice_stride);
+          mbar_wait(bar0 + 8u * u, ph);
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-          if (k >= n_items) break;
+          for (int k = 0; k < ITEMS; ++k) {
+            if (k >= n_items) break;
+            float fx[PP], fy[PP];
+            Item<T>::lds(ufx + k * ITEM_STEP, fx); Item<T>::lds(ufy + k * ITEM_STEP, fy);
 #pragma unroll
-          for (int q = 0; q < PP; ++q) {
-            const Taps ta = taps_setup(bx[k][q], by[k], fx[k][q], fy[k][q], geom);
-            s1[k][q] += taps_fetch<T>(u1, ta, a.w);
+            for (int q = 0; q < PP; ++q) {
+              const Taps ta = taps_setup<false>(bx[k][q], by[k], fx[q], fy[q], geom);
+              s1[k][q] += taps_fetch<T>(u1, ta, a.w);
+            }
+          }
+        } else {
+          const T* fxp = mc + (int64_t)((hop == 0 ? 0 : 2 * L) + ts) * hw;
+          const T* fyp = mc + (int64_t)((hop == 0 ? L : 3 * L) + ts) * hw;
+          float fx[ITEMS][PP], fy[ITEMS][PP];
+#pragma unroll
+          for (int k = 0; k < ITEMS; ++k)
+            if (k < n_items) { Item<T>::ld(fxp + k * ITEM_STEP, fx[k]); Item<T>::ld(fyp + k * ITEM_STEP, fy[k]); }
+          mbar_wait(bar0 + 8u * u, ph);
+#pragma unroll
+          for (int k = 0; k < ITEMS; ++k) {
+            if (k >= n_items) break;
+#pragma unroll
+            for (int q = 0; q < PP; ++q) {
+              const Taps ta = taps_setup<true>(bx[k][q], by[k], fx[k][q], fy[k][q], geom);
+              s1[k][q] += taps_fetch<T>(u1, ta, a.w);
+            }
           }
         }
         __syncwarp();
@@ -643,40 +710,69 @@ int launch_motion_field(const float* flow, float* grid_out, int n, int h, int w,
   return CLASFV_OK;
 }
 
-template <typename T, int THREADS, int ITEMS>
-static cudaError_t launch_staged(const WarpFuseArgs& a, int units, size_t smem, cudaStream_t s) {
-  const int64_t hw = (int64_t)a.h * a.w;
-  const int per_cta = (THREADS - 32) * WS_PP * ITEMS;
-  const int slices = (int)cdiv(hw, per_cta);
-  int slice_pix = (int)cdiv(hw, slices);
-  slice_pix += slice_pix & 1;                           // even: pixel pairs
-  cudaError_t e = allow_max_dynamic_smem(warp_fuse_staged_kernel<T, THREADS, ITEMS>);
+struct StagedPlan { int units, slices, slice_pix; uint32_t unit_bytes, pad_bytes, slice_stride; size_t smem; };
+
+template <typename T, int THREADS, int ITEMS, bool FLOWS>
+static cudaError_t launch_staged(const WarpFuseArgs& a, const StagedPlan& pl, cudaStream_t s) {
+  cudaError_t e = allow_max_dynamic_smem(warp_fuse_staged_kernel<T, THREADS, ITEMS, FLOWS>);
   if (e != cudaSuccess) return e;
-  warp_fuse_staged_kernel<T, THREADS, ITEMS><<<dim3((unsigned)slices, (unsigned)a.t_out), THREADS, smem, s>>>(a, units, slice_pix);
+  warp_fuse_staged_kernel<T, THREADS, ITEMS, FLOWS><<<dim3((unsigned)pl.slices, (unsigned)a.t_out), THREADS, pl.smem, s>>>(
+      a, pl.units, pl.slice_pix, pl.unit_bytes, pl.pad_bytes, pl.slice_stride);
   return cudaSuccess;
+}
+template <int THREADS, int ITEMS, bool FLOWS>
+static cudaError_t launch_staged_typed(const WarpFuseArgs& a, const StagedPlan& pl, cudaStream_t s) {
+  return a.dtype == CLASFV_F32   ? launch_staged<float, THREADS, ITEMS, FLOWS>(a, pl, s)
+         : a.dtype == CLASFV_F16 ? launch_staged<__half, THREADS, ITEMS, FLOWS>(a, pl, s)
+                                 : launch_staged<__nv_bfloat16, THREADS, ITEMS, FLOWS>(a, pl, s);
+}
+
+// Ring geometry of the staged kernel for a CTA of `threads` threads x `items` pixel pairs.  `flows`: the units also carry the
+// slice's flow planes (and W + 2 zeros behind the LV plane).  Slices are multiples of 8 pixels, so that every bulk copy starts
+// and ends on 16 bytes.  Returns false when fewer than two units fit.
+static bool plan_staged(const WarpFuseArgs& a, int threads, int items, bool flows, StagedPlan* pl) {
+  const int64_t hw = (int64_t)a.h * a.w;
+  const size_t es = a.dtype == CLASFV_F32 ? 4 : 2;
+  const size_t budget = 227 * 1024 - 256;
+  const int per_cta = (threads - 32) * WS_PP * items;
+  pl->slices = (int)cdiv(hw, per_cta);
+  pl->slice_pix = (int)(cdiv(cdiv(hw, pl->slices), 8) * 8);
+  if (pl->slice_pix > per_cta) { pl->slices += 1; pl->slice_pix = (int)(cdiv(cdiv(hw, pl->slices), 8) * 8); }
+  if (pl->slice_pix > per_cta) return false;
+  pl->slices = (int)cdiv(hw, pl->slice_pix);
+  pl->pad_bytes = flows ? (uint32_t)(cdiv((a.w + 2) * es, 16) * 16) : 0u;
+  pl->slice_stride = flows ? (uint32_t)(pl->slice_pix * es) : 0u;
+  pl->unit_bytes = (uint32_t)(hw * es) + pl->pad_bytes + 2u * pl->slice_stride;
+  pl->units = (int)std::min<size_t>((budget - 16 * WS_MAX_UNITS) / pl->unit_bytes, (size_t)WS_MAX_UNITS);
+  pl->smem = (size_t)pl->units * pl->unit_bytes + 16 * (size_t)pl->units;
+  return pl->units >= 2;
 }
 
 int launch_warp_fuse(const WarpFuseArgs& a, cudaStream_t s) {
   if (a.area) CLASFV_CUDA(cudaMemsetAsync(a.area, 0, sizeof(int32_t) * a.t_out, s));
-  // staged kernel: needs at least two ring units of two class planes in shared memory, an even width (pixel pairs)
-  // and 16-byte aligned planes (bulk copies); otherwise the direct-gather kernel runs
+  // staged kernel: needs at least two ring units in shared memory, an even width (pixel pairs) and 16-byte aligned planes
+  // (bulk copies); otherwise the direct-gather kernel runs.  Units that also carry the flows are preferred (112 x 112: four
+  // 49 KB units in a 16-bit type, two 99 KB units in fp32); a 16-bit 224 x 224 plane leaves room for LV-only units.
   {
     const int64_t hw = (int64_t)a.h * a.w;
     const size_t es = a.dtype == CLASFV_F32 ? 4 : 2;
-    const size_t unit = (size_t)hw * es;
-    const size_t budget = 225 * 1024;
-    int units = (int)std::min<size_t>((budget - 16 * WS_MAX_UNITS) / unit, (size_t)WS_MAX_UNITS);
     static const bool no_staged = getenv("CLASFV_WARP_FUSE_DIRECT") != nullptr;
-    const bool aligned = (hw * es) % 16 == 0 && a.w % 2 == 0 && ((uintptr_t)a.prob % 16) == 0 && ((uintptr_t)a.acc % 8) == 0 &&
-                         (!a.mask || ((uintptr_t)a.mask % 2) == 0);
-    if (units >= 2 && aligned && a.h >= 2 && !no_staged) {        // (w >= 2 follows from the even width)
-      const size_t smem = (size_t)units * unit + 16 * (size_t)units;
-      const cudaError_t e = a.dtype == CLASFV_F32   ? launch_staged<float, WS_THREADS_PER_CTA, WS_ITEMS>(a, units, smem, s)
-                            : a.dtype == CLASFV_F16 ? launch_staged<__half, WS_THREADS_PER_CTA, WS_ITEMS>(a, units, smem, s)
-                                                    : launch_staged<__nv_bfloat16, WS_THREADS_PER_CTA, WS_ITEMS>(a, units, smem, s);
-      CLASFV_CUDA(e);
-      CLASFV_CUDA(cudaGetLastError());
-      return CLASFV_OK;
+    static const bool no_flows = getenv("CLASFV_WARP_FUSE_NO_FLOW_STAGING") != nullptr;
+    const bool aligned = (hw * es) % 16 == 0 && a.w % 2 == 0 && ((uintptr_t)a.prob % 16) == 0 && ((uintptr_t)a.motion % 16) == 0 &&
+                         ((uintptr_t)a.acc % 8) == 0 && (!a.mask || ((uintptr_t)a.mask % 2) == 0);
+    if (aligned && a.h >= 2 && !no_staged) {        // (w >= 2 follows from the even width)
+      StagedPlan pl;
+      cudaError_t e = cudaErrorInvalidValue; bool launched = false;
+      // (measured on config 3, ms at 0 / 4 px flow, profiles/r02w_warp_fuse_variants.jsonl: 512 x 7 with the fewest slices
+      // 0.43 / 0.50 fp32, 0.45 / 0.49 bf16; 1 024 threads x 4 pairs 0.46 / 0.51, 0.49 / 0.51; three slices 0.45 / 0.50, 0.47 / 0.50;
+      // four slices 0.50 / 0.55, 0.51 / 0.54; flows from global memory, same build: 0.56 / 0.59, 0.57 / 0.59)
+      if (!no_flows && plan_staged(a, WS_THREADS_PER_CTA, WS_ITEMS, true, &pl)) { e = launch_staged_typed<WS_THREADS_PER_CTA, WS_ITEMS, true>(a, pl, s); launched = true; }
+      else if (plan_staged(a, WS_THREADS_PER_CTA, WS_ITEMS, false, &pl)) { e = launch_staged_typed<WS_THREADS_PER_CTA, WS_ITEMS, false>(a, pl, s); launched = true; }
+      if (launched) {
+        CLASFV_CUDA(e);
+        CLASFV_CUDA(cudaGetLastError());
+        return CLASFV_OK;
+      }
     }
   }
   dim3 grid((unsigned)cdiv((int64_t)a.h * a.w, WF_THREADS), (unsigned)a.t_out);

@@ -835,15 +835,26 @@ import sys, numpy as np, torch
 sys.path.insert(0, {root!r})
 from clasfv_b200.engine import Engine
 dtype = torch.float32 if sys.argv[1] == "fp32" else torch.bfloat16
-g = torch.Generator().manual_seed(11)
-n, h, w = 40, 48, 64
-prob = torch.softmax(2 * torch.randn(n, 2, 32, h, w, generator=g), 1).to(dtype)
-mot = torch.tanh(0.15 * torch.randn(n, 4, 32, h, w, generator=g))
-mot[:, :, :, :, :3] = -0.9; mot[:, :, :, :, -3:] = 0.9; mot[:, :, :, :2, :] = -0.9; mot[:, :, :, -2:, :] = 0.9   # taps clamped at every border
-mot = mot.to(dtype)
-r = Engine("cuda:0").warp_fuse(prob.cuda(), mot.cuda(), list(range(n)), n + 31, edge_hops=(sys.argv[2] == "1"))
-np.savez(sys.argv[3], acc=r["acc"].cpu().numpy(), cnt=r["cnt"].cpu().numpy(), mask=r["mask"].cpu().numpy(), area=r["area"].cpu().numpy())
+# the inputs are generated ONCE by the parent and read from a file: both kernels must see the same bytes (two processes that
+# each evaluate torch's CPU randn / tanh / softmax are not guaranteed to - this comparison is about the kernels)
+z = np.load(sys.argv[4])
+prob = torch.from_numpy(z["prob"]).to(dtype); mot = torch.from_numpy(z["mot"]).to(dtype)
+n = prob.shape[0]
+pd, md = prob.cuda(), mot.cuda()
+bits = torch.int32 if dtype == torch.float32 else torch.int16
+chk = np.array([int(pd.view(bits).long().sum()), int(md.view(bits).long().sum())])      # what the kernel reads, as uploaded
+r = Engine("cuda:0").warp_fuse(pd, md, list(range(n)), n + 31, edge_hops=(sys.argv[2] == "1"))
+np.savez(sys.argv[3], acc=r["acc"].cpu().numpy(), cnt=r["cnt"].cpu().numpy(), mask=r["mask"].cpu().numpy(), area=r["area"].cpu().numpy(), chk=chk)
 """
+
+
+def _wf_inputs(path):
+    g = torch.Generator().manual_seed(11)
+    n, h, w = 40, 48, 64
+    prob = torch.softmax(2 * torch.randn(n, 2, 32, h, w, generator=g), 1)
+    mot = torch.tanh(0.15 * torch.randn(n, 4, 32, h, w, generator=g))
+    mot[:, :, :, :, :3] = -0.9; mot[:, :, :, :, -3:] = 0.9; mot[:, :, :, :2, :] = -0.9; mot[:, :, :, -2:, :] = 0.9   # taps clamped at every border
+    np.savez(path, prob=prob.numpy(), mot=mot.numpy())
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
@@ -854,13 +865,18 @@ def test_staged_warp_fuse_is_bit_identical_to_the_direct_gather_kernel(tmp_path,
     (CLASFV_WARP_FUSE_DIRECT), hence two subprocesses."""
     script = tmp_path / "wf.py"
     script.write_text(_WF_SCRIPT.format(root=ROOT))
+    inputs = str(tmp_path / "inputs.npz")
+    _wf_inputs(inputs)
     out = {}
-    for name, env in (("staged", {}), ("direct", {"CLASFV_WARP_FUSE_DIRECT": "1"})):
+    for name, env in (("staged", {}), ("direct", {"CLASFV_WARP_FUSE_DIRECT": "1"}), ("staged_again", {})):
         path = str(tmp_path / f"{name}.npz")
         e = dict(os.environ); e.pop("CLASFV_WARP_FUSE_DIRECT", None); e.update(env)
-        subprocess.run([sys.executable, str(script), dtype, "1" if dtype == "fp32" else "0", path], check=True, env=e, timeout=300)
+        subprocess.run([sys.executable, str(script), dtype, "1" if dtype == "fp32" else "0", path, inputs], check=True, env=e, timeout=300)
         out[name] = np.load(path)
     a, b = out["staged"], out["direct"]
+    assert np.array_equal(a["chk"], b["chk"]) and np.array_equal(a["chk"], out["staged_again"]["chk"]), "the device inputs differ between processes"
+    # run-to-run determinism of the staged kernel across processes (ADVICE r1: a race in the ring would show here)
+    assert np.array_equal(a["acc"].view(np.uint32), out["staged_again"]["acc"].view(np.uint32)), "staged kernel differs from itself across processes"
     differing = int((a["acc"].view(np.uint32) != b["acc"].view(np.uint32)).sum())
     worst = float(np.abs(a["acc"] - b["acc"]).max())
     print(f"\n[staged vs direct, {dtype}] class sums differing in any bit: {differing} of {a['acc'].size}, max abs difference {worst:.3g}")

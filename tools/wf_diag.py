@@ -15,6 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = open(os.path.join(ROOT, "tests", "test_gpu_parity.py")).read()
 body = src[src.index('_WF_SCRIPT = r"""') + len('_WF_SCRIPT = r"""'):]
 open("/tmp/wf.py", "w").write(body[:body.index('"""')].format(root=ROOT))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import test_gpu_parity  # noqa: E402  (the inputs are generated once, here, and shared by every process)
+test_gpu_parity._wf_inputs("/tmp/wf_inputs.npz")
 repeats = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 
 
@@ -24,7 +28,7 @@ def run(name, dtype, edge, tag):
     if name == "direct":
         e["CLASFV_WARP_FUSE_DIRECT"] = "1"
     path = f"/tmp/wf_{name}_{tag}.npz"
-    subprocess.run([sys.executable, "/tmp/wf.py", dtype, edge, path], check=True, env=e)
+    subprocess.run([sys.executable, "/tmp/wf.py", dtype, edge, path, "/tmp/wf_inputs.npz"], check=True, env=e)
     return np.load(path)["acc"]
 
 
@@ -33,7 +37,7 @@ def diff(a, b):
     idx = np.argwhere(d)
     s = f"{int(d.sum())} of {d.size} differ, max abs {float(np.abs(a - b).max()):.3g}"
     if len(idx):
-        s += f"; frames {np.unique(idx[:, 0])[:8]} rows {np.unique(idx[:, 2])[:8]} cols {np.unique(idx[:, 3])[:8]}"
+        s += f"; frames {np.unique(idx[:, 0])[:12]} (n={len(np.unique(idx[:, 0]))}) rows {np.unique(idx[:, 2])[:60]} cols {np.unique(idx[:, 3])[:70]}"
     return s
 
 
