@@ -130,6 +130,7 @@ struct clasfv_handle {
   // options (clasfv_set_option)
   int sub_batch = 32;          // clips per internal batch of clasfv_forward
   bool dense_video = true;     // share layer-1 work between overlapping windows of one video (bf16 tensor-core path)
+  bool umma_pair = true;       // CTA pairs (cta_group::2) for the convolutions with >= 128 output columns
 };
 
 namespace {
@@ -255,7 +256,9 @@ int run_conv(clasfv_handle* h, const ConvArgs& a, cudaStream_t stream) {
   ++h->launches;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (trace) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(stream); cudaEventRecord(e0, stream); }
-  const int rc = (a.act_dtype != CLASFV_F32 && !h->force_simt) ? launch_conv_umma(a, h->num_sms, stream) : launch_conv_simt(a, stream);
+  ConvArgs ap = a;
+  ap.no_pair = h->umma_pair ? 0 : 1;
+  const int rc = (a.act_dtype != CLASFV_F32 && !h->force_simt) ? launch_conv_umma(ap, h->num_sms, stream) : launch_conv_simt(a, stream);
   if (trace) {
     cudaEventRecord(e1, stream); cudaEventSynchronize(e1);
     float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
@@ -849,6 +852,7 @@ int clasfv_set_option(clasfv_handle* h, const char* name, int value) {
   const std::string k(name);
   if (k == "sub_batch") { CLASFV_REQUIRE(value >= 1 && value <= 4096, "clasfv_set_option: sub_batch out of range"); h->sub_batch = value; }
   else if (k == "dense_video") { h->dense_video = value != 0; }
+  else if (k == "umma_pair") { h->umma_pair = value != 0; }
   else { set_error("clasfv_set_option: unknown option '%s'", name); return CLASFV_EINVAL; }
   return CLASFV_OK;
 }
@@ -1074,6 +1078,7 @@ int clasfv_conv3d(clasfv_handle* h, const void* x_dev, int dtype, int n, int t, 
   pc.kt = kt; pc.kh = kh; pc.kw = kw; pc.st = st; pc.sh = sh; pc.sw = sw; pc.pt = pt; pc.ph = ph; pc.pw = pw;
   pc.w = w_dev; pc.bias = b_dev;
   ConvArgs a = make_conv(pc, n, t, height, width, x_dev, out_dev, residual_dev, relu, dtype, out_f32);
+  a.no_pair = h->umma_pair ? 0 : 1;
   int rc = engine == 1 ? launch_conv_umma(a, h->num_sms, stream) : launch_conv_simt(a, stream);
   cudaError_t e = cudaStreamSynchronize(stream);
   cudaFree(w_dev);

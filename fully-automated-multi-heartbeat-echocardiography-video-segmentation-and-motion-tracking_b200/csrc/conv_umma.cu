@@ -21,6 +21,15 @@
 //                                    + residual, ReLU, convert, store channels-last
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
+//
+// CTA pairs (template parameter CTAS == 2; layers with >= 128 output columns): a cluster of two CTAs on the two SMs of one TPC
+// runs ONE tcgen05.mma.cta_group::2 of M = 256.  Each CTA loads the A slab of its own 128-row tile and HALF the rows of the
+// filter slab, keeps its own accumulator and runs its own epilogue; only the leader (cluster rank 0) issues MMAs.  An MMA then
+// reads 4 KB of A + 16 x BN bytes of B per CTA instead of 32 x BN: the 128-column layers are no longer bound by shared-memory
+// bandwidth, a filter bank twice as large stays resident (layer2's temporal convolutions without the N split, which read
+// their activations twice), and streamed filters cost half the L2 traffic per CTA.  Barrier protocol: every TMA load of both
+// CTAs reports to the LEADER's full barrier (which expects both CTAs' bytes); tcgen05.commit multicasts to the empty /
+// accumulator-full barriers of both CTAs; the peer's epilogue warps arrive remotely on the leader's accumulator-empty barrier.
 #include "internal.h"
 #include "umma_ptx.cuh"
 
@@ -53,10 +62,15 @@ constexpr int SMEM_BUDGET = 222 * 1024;
 //   3x1x1 temporal, stride 1 : 1 group of 3 taps, halo of 2 frames            (box bw x bh x (bt+2), bb = 1)
 //   1x3x3 spatial,  stride 1 : 3 groups (kw) of 3 taps (kh), halo of 2 rows   (box bw x (bh+2), bt = bb = 1, bw % 8 == 0)
 //   anything else            : every tap its own group, no halo
+// The ORDER in which K is traversed does not depend on whether a layout could be shared: a stride-1 3x1x1 / 1x3x3 convolution
+// whose tiling (or shared-memory budget) rules sharing out still walks "logical group -> 64-channel slab -> tap" (span = 3
+// single-tap groups per logical group), exactly the sequence of the shared layout.  The tiling depends on the batch size and
+// the frame geometry; the sums, and hence the output bits, must not (dense-video vs per-clip schedule, CTA pairs vs single CTAs).
 struct UmmaParams {
   CUtensorMap tmap_a[MAX_MAPS];
   CUtensorMap tmap_b;
   int ngroups, ntaps, kslabs, k16_last;
+  int span;                                 // groups per logical group (1, or 3 for an unshared stride-1 3-tap family): K order is logical group -> slab -> group
   int8_t grp_view[MAX_TAPS], grp_dw[MAX_TAPS], grp_dh[MAX_TAPS], grp_dt[MAX_TAPS];
   int8_t grp_first[MAX_TAPS + 1];           // taps of group g: [grp_first[g], grp_first[g+1])
   int8_t tap_widx[MAX_TAPS];                // index of the tap in the packed weight tensor
@@ -87,6 +101,7 @@ struct UmmaParams {
 };
 
 // ------------------------------------------------------------------------------------ the kernel
+template <int CTAS>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A slabs][B stage slabs | resident weights][barriers][tmem ptr]; base re-aligned to 1024
@@ -105,14 +120,19 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work units: (M tile, N tile) for one CTA; (pair of consecutive M tiles, N tile) for a CTA pair - the CTA of rank r owns M tile
+  // 2 * pair + r (a pair's second tile may lie past the end: its loads are zero-filled by TMA and nothing is stored)
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_b;
-  const int total_tiles = m_tiles * p.tiles_n;
+  const int total_tiles = (int)((m_tiles + CTAS - 1) / CTAS) * p.tiles_n;
+  const int unit0 = (int)blockIdx.x / CTAS, unit_step = (int)gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     for (int v = 0; v < (p.fsel_on ? MAX_MAPS : MAX_VIEWS); ++v) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a[v]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
     for (int s = 0; s < p.nstages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS * CTAS); }
     mbar_init(wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -123,11 +143,17 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
     for (int i = threadIdx.x; i < p.cout; i += UMMA_THREADS) bias_s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {          // the same warp of both CTAs allocates the pair's columns
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();        // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // the next kernel of the stream may be scheduled from here on (it parks in its own griddep_wait until this grid is done)
@@ -138,25 +164,34 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
     // One elected thread.  Every kernel parameter it needs is copied into registers first: the asm statements below
     // carry "memory" clobbers, after which the compiler would otherwise re-read the parameter (constant) bank each time.
     if (elect_one()) {
-      const int nst = p.nstages, kslabs = p.kslabs, ngroups = p.ngroups, tpg = p.tpg, resident = p.resident, tiles_n = p.tiles_n;
+      const int nst = p.nstages, kslabs = p.kslabs, ngroups = p.ngroups, tpg = p.tpg, resident = p.resident, tiles_n = p.tiles_n, span = p.span;
       const int tw = p.tiles_w, th = p.tiles_h, tt = p.tiles_t, bw = p.bw, bh = p.bh, bt = p.bt, bb = p.bb, bn = p.bn;
       const int a_slab_bytes = p.a_slab_bytes, b_slab_bytes = p.b_slab_bytes, b_stage_slabs = p.b_stage_slabs, frame_bytes = p.frame_bytes;
       const int framewise = p.framewise, fw_split = p.fw_split, fw_a_toff = p.fw_a_toff, fw_b_toff = p.fw_b_toff;
       const int fsel_on = p.fsel_on, fsel_st = p.fsel_st;
-      const uint32_t tx = (uint32_t)p.a_tx_bytes + (resident ? 0u : (uint32_t)(tpg * b_slab_bytes));
+      // CTA pair: the bytes of both CTAs are expected by the leader's barrier, which every load of the pair reports to
+      const uint32_t tx = (uint32_t)CTAS * ((uint32_t)p.a_tx_bytes + (resident ? 0u : (uint32_t)(tpg * b_slab_bytes)));
+      const int brow = (int)rank * (bn / CTAS);   // this CTA's rows of the filter slab
+      auto load_a = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+        if (CTAS == 2) tma_load_5d_pair(dst, map, bar, c0, c1, c2, c3, c4); else tma_load_5d(dst, map, bar, c0, c1, c2, c3, c4);
+      };
+      auto load_b = [&](uint32_t dst, uint32_t bar, int c0, int c1, int c2) {
+        if (CTAS == 2) tma_load_3d_pair(dst, &p.tmap_b, bar, c0, c1, c2); else tma_load_3d(dst, &p.tmap_b, bar, c0, c1, c2);
+      };
       if (resident) {
         // the whole filter bank of this (single) N tile stays in shared memory for the life of the CTA
-        mbar_arrive_expect_tx(wres_bar, (uint32_t)(p.ntaps * kslabs * b_slab_bytes));
+        if (leader) mbar_arrive_expect_tx(wres_bar, (uint32_t)CTAS * (uint32_t)(p.ntaps * kslabs * b_slab_bytes));
+        const uint32_t wbar = CTAS == 2 ? map_to_cta(wres_bar, 0) : wres_bar;
         for (int tap = 0; tap < p.ntaps; ++tap)
           for (int ks = 0; ks < kslabs; ++ks)
-            tma_load_3d(b_base + (uint32_t)((tap * kslabs + ks) * b_slab_bytes), &p.tmap_b, wres_bar, ks * SLAB_K,
-                        (int)(blockIdx.x % (unsigned)tiles_n) * bn, p.tap_widx[tap]);
+            load_b(b_base + (uint32_t)((tap * kslabs + ks) * b_slab_bytes), wbar, ks * SLAB_K,
+                   (unit0 % tiles_n) * bn + brow, p.tap_widx[tap]);
       }
       griddep_wait();                             // weights are constants; activations are the preceding kernels' output
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         const int n_tile = tile % tiles_n;
-        int mt = tile / tiles_n;
+        int mt = (tile / tiles_n) * CTAS + (int)rank;
         const int w0 = (mt % tw) * bw; mt /= tw;
         const int h0 = (mt % th) * bh; mt /= th;
         const int t0 = (mt % tt) * bt; mt /= tt;
@@ -164,35 +199,45 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
         // frame-selected input: this (single-frame) tile's input frame picks the source map and the frame coordinate
         int fsel_map = 0, fsel_ct = 0;
         if (fsel_on) { const int f = t0 * fsel_st; fsel_map = p.fsel_src[f] ? MAX_VIEWS : 0; fsel_ct = p.fsel_idx[f]; }
-        for (int g = 0; g < ngroups; ++g) {
+        for (int lg = 0; lg < ngroups; lg += span)
+        for (int ks = 0; ks < kslabs; ++ks)
+        for (int g = lg; g < lg + span; ++g) {
           const bool sel = fsel_on && p.grp_fsel[g];
           const CUtensorMap* map = &p.tmap_a[p.grp_view[g] + (sel ? fsel_map : 0)];
           const int cw = w0 + p.grp_dw[g], ch = h0 + p.grp_dh[g], ct = sel ? fsel_ct : t0 + p.grp_dt[g];
           int widx[3];
 #pragma unroll
           for (int j = 0; j < 3; ++j) widx[j] = (!resident && j < tpg) ? p.tap_widx[g * tpg + j] : 0;
-          for (int ks = 0; ks < kslabs; ++ks) {
+          {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(stage), tx);
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), tx);
+            const uint32_t fbar = CTAS == 2 ? map_to_cta(full_bar(stage), 0) : full_bar(stage);
             const uint32_t a_dst = a_base + (uint32_t)(stage * a_slab_bytes);
             if (framewise) {
               // the tile spans the whole virtual clip (bt == to, ct == -1): frames [-1, split) come from source A and
               // [split, to] from source B, each contiguous in its source, so two box loads (map 0: split+1 frames,
               // map 1: the rest) fill the slab; a frame outside its source's extent is zero-filled by TMA
               const int na = fw_split - ct;
-              tma_load_5d(a_dst, &p.tmap_a[0], full_bar(stage), ks * SLAB_K, cw, ch, ct + fw_a_toff, b0);
-              tma_load_5d(a_dst + (uint32_t)(na * frame_bytes), &p.tmap_a[1], full_bar(stage), ks * SLAB_K, cw, ch, ct + na + fw_b_toff, b0);
+              load_a(a_dst, &p.tmap_a[0], fbar, ks * SLAB_K, cw, ch, ct + fw_a_toff, b0);
+              load_a(a_dst + (uint32_t)(na * frame_bytes), &p.tmap_a[1], fbar, ks * SLAB_K, cw, ch, ct + na + fw_b_toff, b0);
             } else {
-              tma_load_5d(a_dst, map, full_bar(stage), ks * SLAB_K, cw, ch, ct, b0);
+              load_a(a_dst, map, fbar, ks * SLAB_K, cw, ch, ct, b0);
             }
             if (!resident) {
               const uint32_t b_dst = b_base + (uint32_t)(stage * b_stage_slabs * b_slab_bytes);
 #pragma unroll
               for (int j = 0; j < 3; ++j)
-                if (j < tpg) tma_load_3d(b_dst + (uint32_t)(j * b_slab_bytes), &p.tmap_b, full_bar(stage), ks * SLAB_K, n_tile * bn, widx[j]);
+                if (j < tpg) load_b(b_dst + (uint32_t)(j * b_slab_bytes), fbar, ks * SLAB_K, n_tile * bn + brow, widx[j]);
             }
             if (++stage == nst) { stage = 0; phase ^= 1u; }
           }
+        }
+      }
+      if (CTAS == 2) {
+        // tail: every multicast release of the leader's MMA warp has landed in THIS CTA's barriers before it may leave
+        for (int i = 0; i < nst; ++i) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -201,9 +246,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
     // One elected thread; for the 64-column layers this thread's instruction stream IS the critical path (ncu:
     // profiles/r01w), so the loop body is a handful of 32-bit adds per tcgen05.mma: parameters in registers, descriptor
     // low words strength-reduced (the high word of a SWIZZLE_128B K-major descriptor is a constant).
-    if (elect_one()) {
+    if (leader && elect_one()) {
       if (p.resident) { mbar_wait(wres_bar, 0); tc_fence_after(); }
-      const int nst = p.nstages, kslabs = p.kslabs, ngroups = p.ngroups, tpg = p.tpg, resident = p.resident, bn = p.bn;
+      const int nst = p.nstages, kslabs = p.kslabs, ngroups = p.ngroups, tpg = p.tpg, resident = p.resident, bn = p.bn, span = p.span;
       const uint32_t k16_last = (uint32_t)p.k16_last, idesc = p.idesc;
       const uint32_t desc_hi = (uint32_t)(smem_desc_sw128(0) >> 32);
       const uint32_t a_lo0 = (uint32_t)smem_desc_sw128(a_base), b_lo0 = (uint32_t)smem_desc_sw128(b_base);
@@ -212,15 +257,20 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
       auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+        if (CTAS == 2) tc_mma_bf16_pair(d, da, db, idesc, acc); else tc_mma_bf16(d, da, db, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) { if (CTAS == 2) tc_commit_pair(bar); else tc_commit(bar); };
+      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
         const int as = it & 1; const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * bn);
         uint32_t accumulate = 0;
-        uint32_t b_res = b_lo0;                  // resident weights: slot (tap * kslabs + ks), visited in exactly this order
-        for (int g = 0; g < ngroups; ++g) {
-          for (int ks = 0; ks < kslabs; ++ks) {
+        for (int lg = 0; lg < ngroups; lg += span)
+        for (int ks = 0; ks < kslabs; ++ks) {
+          for (int g = lg; g < lg + span; ++g) {
+            const uint32_t b_res = b_lo0 + (uint32_t)(g * tpg * kslabs) * bs16;     // resident weights: slot (tap * kslabs + ks)
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_st16;
@@ -235,24 +285,23 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
                 const uint32_t db = b_lo + (uint32_t)j * (resident ? (uint32_t)kslabs * bs16 : bs16);
                 // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field.
                 // Only the first instruction of a tile overwrites the accumulator; a full slab is four unpredicated issues.
-                tc_mma_bf16(tmem_d, desc(da), desc(db), idesc, accumulate);
+                mma(tmem_d, desc(da), desc(db), accumulate);
                 accumulate = 1;
                 if (nk == 4) {
-                  tc_mma_bf16(tmem_d, desc(da + 2u), desc(db + 2u), idesc, 1u);
-                  tc_mma_bf16(tmem_d, desc(da + 4u), desc(db + 4u), idesc, 1u);
-                  tc_mma_bf16(tmem_d, desc(da + 6u), desc(db + 6u), idesc, 1u);
+                  mma(tmem_d, desc(da + 2u), desc(db + 2u), 1u);
+                  mma(tmem_d, desc(da + 4u), desc(db + 4u), 1u);
+                  mma(tmem_d, desc(da + 6u), desc(db + 6u), 1u);
                 } else {
-                  if (nk > 1) tc_mma_bf16(tmem_d, desc(da + 2u), desc(db + 2u), idesc, 1u);
-                  if (nk > 2) tc_mma_bf16(tmem_d, desc(da + 4u), desc(db + 4u), idesc, 1u);
+                  if (nk > 1) mma(tmem_d, desc(da + 2u), desc(db + 2u), 1u);
+                  if (nk > 2) mma(tmem_d, desc(da + 4u), desc(db + 4u), 1u);
                 }
               }
             }
-            tc_commit(empty_bar(stage));          // slab reusable once these MMAs have read it
+            commit(empty_bar(stage));             // slab reusable (in both CTAs of a pair) once these MMAs have read it
             if (++stage == nst) { stage = 0; phase ^= 1u; }
           }
-          b_res += (uint32_t)(tpg * kslabs) * bs16;
         }
-        tc_commit(tfull_bar(as));                 // accumulator complete
+        commit(tfull_bar(as));                    // accumulator complete (each CTA of a pair holds its own 128 rows)
       }
     }
   } else {
@@ -271,10 +320,11 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
     const int itt = r % p.bt; r /= p.bt;
     const int ib = r;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const uint32_t tempty_leader[2] = {CTAS == 2 ? map_to_cta(tempty_bar(0), 0) : 0u, CTAS == 2 ? map_to_cta(tempty_bar(1), 0) : 0u};
+    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
       const int as = it & 1; const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const int n_tile = tile % p.tiles_n;
-      int mt = tile / p.tiles_n;
+      int mt = (tile / p.tiles_n) * CTAS + (int)rank;
       const int w0 = (mt % p.tiles_w) * p.bw; mt /= p.tiles_w;
       const int h0 = (mt % p.tiles_h) * p.bh; mt /= p.tiles_h;
       const int t0 = (mt % p.tiles_t) * p.bt; mt /= p.tiles_t;
@@ -385,15 +435,18 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));   // 8 arrivals (one per epilogue warp) free the accumulator
+      // 8 arrivals (one per epilogue warp; 16 for a pair, on the leader's barrier) free the accumulator stage
+      if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(tempty_leader[as]); else mbar_arrive(tempty_bar(as)); }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();          // neither CTA leaves (or frees tensor memory) while the pair's MMAs / remote arrivals are in flight
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -507,10 +560,13 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   if (!bn) bn = round_up((int)cdiv(s.cout, min_tiles), 16);
   CLASFV_REQUIRE(bn >= 16 && bn <= 256, "conv_umma: N tile overflow");
   p.bn = bn; p.tiles_n = (int)cdiv(s.cout, bn);
-  p.b_slab_bytes = bn * SLAB_K * 2;
+  // CTA pairs for the wide layers (layers 2-4; see the header): each CTA stages half the rows of a filter slab
+  static const bool no_pair = getenv("CLASFV_UMMA_NO_PAIR") != nullptr;
+  const int ctas = (!no_pair && !a.no_pair && bn >= 128 && !a.seg.on && num_sms >= 2) ? 2 : 1;
+  p.b_slab_bytes = (bn / ctas) * SLAB_K * 2;
   p.n = s.n; p.to = s.to; p.ho = s.ho; p.wo = s.wo; p.cout = s.cout;
   // ---- K
-  p.ntaps = ntaps;
+  p.ntaps = ntaps; p.span = 1;
   p.kslabs = (int)cdiv(s.cin, SLAB_K);
   p.k16_last = (s.cin - (p.kslabs - 1) * SLAB_K) / UMMA_K;
 
@@ -564,7 +620,7 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   // multiple of the N tiling, so a persistent CTA only ever sees one N tile).  The weights are then read once per CTA instead
   // of once per 128-row tile (192 KB per tile against 72 KB of activations); the A slabs are read twice.
   static const bool no_split = getenv("CLASFV_UMMA_NO_NSPLIT") != nullptr;
-  if (!p.resident && p.tiles_n == 1 && ntaps <= 3 && s.cout % 32 == 0 && !no_split) {
+  if (ctas == 1 && !p.resident && p.tiles_n == 1 && ntaps <= 3 && s.cout % 32 == 0 && !no_split) {
     const int bn2 = s.cout / 2, b_slab2 = bn2 * SLAB_K * 2, res2 = ntaps * p.kslabs * b_slab2;
     if (res2 + 4 * p.a_slab_bytes + bar_bytes + 1024 <= SMEM_BUDGET) {
       bn = bn2; p.bn = bn2; p.tiles_n = 2; p.b_slab_bytes = b_slab2; p.resident = 1;
@@ -599,7 +655,12 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
       ++ng;
     }
   } else {
-    for (int tap = 0; tap < ntaps; ++tap) {
+    // the 3-tap families walk K in the order of their shared layouts (see UmmaParams): 1x3x3 by kw then kh, 3x1x1 by kt
+    const bool family_h = unit_stride && s.kt == 1 && s.kh == 3 && s.kw == 3 && s.ph == 1 && s.pw == 1;
+    const bool family_t = unit_stride && s.kt == 3 && s.kh == 1 && s.kw == 1 && s.pt == 1;
+    if (family_h || family_t) p.span = 3;
+    for (int e = 0; e < ntaps; ++e) {
+      const int tap = family_h ? (e % 3) * 3 + e / 3 : e;        // entry e = (kw, kh) of a 1x3x3 filter is tap kh * 3 + kw
       const int src = tap / sp_taps, sp = tap % sp_taps;
       const int kw = sp % s.kw, kh = (sp / s.kw) % s.kh, kt = sp / (s.kw * s.kh);
       int qt, rt, qh, rh, qw, rw;
@@ -685,14 +746,14 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   {
     const uint64_t dims[3] = {(uint64_t)s.cin, (uint64_t)s.cout, (uint64_t)ntaps};
     const uint64_t strides[2] = {(uint64_t)s.cin * 2, (uint64_t)s.cout * s.cin * 2};
-    const uint32_t box[3] = {(uint32_t)SLAB_K, (uint32_t)bn, 1};
+    const uint32_t box[3] = {(uint32_t)SLAB_K, (uint32_t)(bn / ctas), 1};
     int rc = encode_map(&p.tmap_b, const_cast<void*>(a.weight), 3, dims, strides, box, fp16);
     if (rc) return rc;
   }
   int cols = 32;
   while (cols < 2 * bn) cols *= 2;
   p.tmem_cols = cols;
-  p.idesc = idesc_16bit_f32(TILE_M, bn, fp16);
+  p.idesc = idesc_16bit_f32(TILE_M * ctas, bn, fp16);
   p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.relu = a.relu;
   p.out_type = a.out_f32 ? CLASFV_F32 : a.out_f16 ? CLASFV_F16 : a.act_dtype;
   const int64_t out_frame = (int64_t)s.ho * s.wo * s.cout;
@@ -709,11 +770,18 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)p.nstages * p.a_slab_bytes +
                       (p.resident ? (size_t)ntaps * p.kslabs * p.b_slab_bytes : (size_t)p.nstages * p.b_stage_slabs * p.b_slab_bytes) + bar_bytes;
   CLASFV_REQUIRE(smem <= 227 * 1024, "conv_umma: shared memory overflow (%zu bytes)", smem);
-  CLASFV_CUDA(allow_max_dynamic_smem(conv_umma_kernel));
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_b * p.tiles_n;
-  int grid = total_tiles < num_sms ? total_tiles : num_sms;
-  if (p.resident && p.tiles_n > 1) grid = std::max(grid / p.tiles_n, 1) * p.tiles_n;     // a CTA keeps one N tile: tile % tiles_n == blockIdx.x % tiles_n
-  CLASFV_CUDA(launch_pdl(conv_umma_kernel, dim3((unsigned)grid), dim3(UMMA_THREADS), smem, stream, p));
+  // work units: (M tile, N tile), or (pair of M tiles, N tile) for a CTA pair; one CTA / one pair per unit, persistent
+  const int64_t m_tiles = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_b;
+  const int64_t total_units = cdiv(m_tiles, ctas) * p.tiles_n;
+  int units = (int)std::min<int64_t>(total_units, num_sms / ctas);
+  if (p.resident && p.tiles_n > 1) units = std::max(units / p.tiles_n, 1) * p.tiles_n;   // a CTA keeps one N tile: unit % tiles_n is constant
+  if (ctas == 2) {
+    CLASFV_CUDA(allow_max_dynamic_smem(conv_umma_kernel<2>));
+    CLASFV_CUDA(launch_pdl(conv_umma_kernel<2>, dim3((unsigned)(2 * units)), dim3(UMMA_THREADS), smem, stream, 2, p));
+  } else {
+    CLASFV_CUDA(allow_max_dynamic_smem(conv_umma_kernel<1>));
+    CLASFV_CUDA(launch_pdl(conv_umma_kernel<1>, dim3((unsigned)units), dim3(UMMA_THREADS), smem, stream, 1, p));
+  }
   return CLASFV_OK;
 }
 

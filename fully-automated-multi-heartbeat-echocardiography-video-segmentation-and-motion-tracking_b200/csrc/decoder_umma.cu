@@ -609,7 +609,7 @@ static int launch_head_typed(const HeadArgs& a, const HeadGeom& g, const HeadMap
 #define CLASFV_HEAD_LAUNCH(F16, KS)                                                               \
   do {                                                                                            \
     CLASFV_CUDA(allow_max_dynamic_smem(head_umma_kernel<OutT, F16, KS>));                         \
-    CLASFV_CUDA(launch_pdl(head_umma_kernel<OutT, F16, KS>, dim3((unsigned)grid), dim3(HU_THREADS), smem, stream, a, g, maps, tab)); \
+    CLASFV_CUDA(launch_pdl(head_umma_kernel<OutT, F16, KS>, dim3((unsigned)grid), dim3(HU_THREADS), smem, stream, 1, a, g, maps, tab)); \
   } while (0)
   if (a.tail_f16) {
     if (g.ksteps == 7) CLASFV_HEAD_LAUNCH(true, 7); else CLASFV_HEAD_LAUNCH(true, 8);

@@ -44,14 +44,24 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // Off unless CLASFV_PDL=1 (it measured no gain, see pdl_enabled in api.cu); without the attribute the griddepcontrol
 // instructions in the kernels are no-ops.
 bool pdl_enabled();                                                  // api.cu
+// `cluster` > 1 launches thread-block clusters of that many CTAs along x (the grid must be a multiple of it).
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -82,6 +92,7 @@ struct ConvArgs {
   double macs_per_pos;    // true (unpadded) MACs per output position, for the profiler's performed-FLOP count
   // ---- optional, tcgen05 path only (zero-initialised by make_conv): ragged clip geometry of the dense-video trunk
   int64_t out_batch_stride;   // elements between consecutive clips of `out` (0 = dense To*Ho*Wo*Cout)
+  int no_pair;                // 1: never run this convolution on CTA pairs (cta_group::2); option "umma_pair" of the handle
   // Time-segmented input of a 3x1x1 stride-1 pad-1 convolution (seg.on): the clip the convolution sees is VIRTUAL.
   // Its input frame v (v = -1 .. to, the convolution's own zero padding included) is frame v + a_toff of source A
   // (`in`, a_t frames per clip, in_batch_stride) when v < split, else frame v + b_toff of source B (b, b_t frames per

@@ -236,6 +236,30 @@ def test_conv_tcgen05_bf16(eng, case):
     assert float(((out - out2).abs() / (ref.abs() + 1.0)).max()) <= 2 * tol      # summation order may move a value across one rounding boundary
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[5] >= 128])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_conv_cta_pair_is_bit_identical_to_single_cta(eng, case, dtype):
+    """Layers with >= 128 output columns run on CTA pairs (tcgen05.mma.cta_group::2, M = 256, half of the filter rows per
+    CTA, csrc/conv_umma.cu).  Every output element is accumulated over the same K steps in the same order as by the
+    single-CTA kernel wherever both use the same slab layout, so there the option must not change a bit - odd tile counts (a
+    pair whose second tile is empty), ragged last N tiles, strided and residual cases included."""
+    try:
+        eng.set_option("umma_pair", 1)
+        pair, ref = _conv_case(eng, case, dtype, "umma")
+        eng.set_option("umma_pair", 0)
+        single, _ = _conv_case(eng, case, dtype, "umma")
+    finally:
+        eng.set_option("umma_pair", 1)
+    assert torch.isfinite(pair).all()
+    assert float(((pair - ref).abs() / (ref.abs() + 1.0)).max()) <= (2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11)
+    ndiff = int((pair != single).sum())
+    print(f"\n[pair vs single, {case[4]}->{case[5]} k={case[6]} {dtype}] differing outputs: {ndiff} of {pair.numel()}, max abs {float((pair - single).abs().max()):.3g}, "
+          f"max err vs fp32 reference: pair {float((pair - ref).abs().max()):.4g} single {float((single - ref).abs().max()):.4g}")
+    # The order in which K is walked does not depend on the tiling or on whether a tap family shares its slab (conv_umma.cu,
+    # UmmaParams::span), so the halved filter stage of a pair - which lets the 256-column layers keep the shared layout - moves no bit.
+    assert ndiff == 0
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_tcgen05_fp16(eng, case):
     out, ref = _conv_case(eng, case, torch.float16, "umma")
