@@ -562,7 +562,10 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   p.bn = bn; p.tiles_n = (int)cdiv(s.cout, bn);
   // CTA pairs for the wide layers (layers 2-4; see the header): each CTA stages half the rows of a filter slab
   static const bool no_pair = getenv("CLASFV_UMMA_NO_PAIR") != nullptr;
-  const int ctas = (!no_pair && !a.no_pair && bn >= 128 && !a.seg.on && num_sms >= 2) ? 2 : 1;
+  // (measured per layer, profiles/r02r_conv_trace_{pair,nopair}.txt: layers 2-4 gain - layer2 spatial 1 136 -> 1 250 TFLOP/s,
+  // layer2 temporal 695 -> 812, strided temporal 350 -> 548, layer3 temporal 796 -> 1 006; the short-K 64 -> 144 convolutions of
+  // layer1 (36 MMAs per tile: the pair's cross-CTA hand-shakes are not amortised) and the single-tap downsample projections lose)
+  const int ctas = (!no_pair && !a.no_pair && bn >= 128 && s.cin >= 128 && sp_taps > 1 && !a.seg.on && num_sms >= 2) ? 2 : 1;
   p.b_slab_bytes = (bn / ctas) * SLAB_K * 2;
   p.n = s.n; p.to = s.to; p.ho = s.ho; p.wo = s.wo; p.cout = s.cout;
   // ---- K
