@@ -93,7 +93,11 @@ int clasfv_forward(clasfv_handle* h, const float* x_dev, const int64_t* clip_off
  *                  resident video, bf16 tensor-core mode, N >= 4, T >= 16: the stem and layer1 are evaluated once over
  *                  the union of the frames, and per clip only the <= 5 frames next to each clip edge (the ones the
  *                  clip's zero padding reaches through 5 temporal convolutions) are recomputed.  Outputs are
- *                  bit-identical to the per-clip schedule; pass every window of the video in ONE call to benefit. */
+ *                  bit-identical to the per-clip schedule; pass every window of the video in ONE call to benefit.
+ *   "umma_pair"    0/1 (default 1).  Convolutions with >= 128 input and output channels and more than one filter tap run on
+ *                  CTA pairs (tcgen05.mma.cta_group::2: two SMs of a TPC share one M = 256 MMA, each staging half of the
+ *                  filter rows).  Outputs are bit-identical either way (the K order does not depend on the tiling);
+ *                  the switch exists for measurements and tests. */
 int clasfv_set_option(clasfv_handle* h, const char* name, int value);
 
 /* Stage timing of clasfv_forward with CUDA events recorded on the caller's stream (measurement support,

@@ -23,11 +23,14 @@ def main():
     ap.add_argument("--dtypes", nargs="*", default=["fp32", "bf16", "fp16"])
     ap.add_argument("--size", type=int, default=112)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--flow-kinds", nargs="*", default=["white", "smooth"],
+                    help="white: independent flow per pixel (the worst gather pattern: neighbouring pixels sample unrelated places); "
+                         "smooth: a 14x14 field upsampled bilinearly, like the decoder's (neighbouring pixels sample neighbouring places)")
     ap.add_argument("--once", action="store_true", help="one point per dtype (256 clips, 4 px), 1 warm-up + 1 launch: for ncu captures")
     args = ap.parse_args()
     warm = 3
     if args.once:
-        args.clips, args.flow_px, args.iters, warm = [256], [4.0], 1, 1
+        args.clips, args.flow_px, args.iters, warm, args.flow_kinds = [256], [4.0], 1, 1, ["white"]
     try:
         peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
@@ -39,9 +42,16 @@ def main():
         dtype = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[dt]
         for n in args.clips:
             prob = torch.sigmoid(torch.randn(n, 1, 32, h, w, generator=g, device="cuda")).to(dtype)      # the LV probability
-            for px in args.flow_px:
+            for px, kind in [(px, kind) for px in args.flow_px for kind in (args.flow_kinds if px > 0 else args.flow_kinds[:1])]:
                 # tanh(N(0, sigma)) with sigma chosen so that the rms displacement is `px` pixels
-                mot = torch.tanh(torch.randn(n, 4, 32, h, w, generator=g, device="cuda") * (px / 56.0)).to(dtype)
+                if kind == "white":
+                    mot = torch.tanh(torch.randn(n, 4, 32, h, w, generator=g, device="cuda") * (px / (h / 2.0))).to(dtype)
+                else:
+                    low = torch.randn(n * 4, 32, 14, 14, generator=g, device="cuda")
+                    up = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=True).view(n, 4, 32, h, w)
+                    up = up / up.std()
+                    mot = torch.tanh(up * (px / (h / 2.0))).to(dtype)
+                    del low, up
                 starts = list(range(n))
                 t_out = n + 31
                 for _ in range(warm):
@@ -56,7 +66,7 @@ def main():
                 ms = e0.elapsed_time(e1) / args.iters
                 nbytes = n * 32 * h * w * 5 * prob.element_size() + t_out * h * w * 9 + t_out * 8
                 nbytes6 = nbytes + n * 32 * h * w * prob.element_size()
-                print(json.dumps({"kernel": "warp_fuse", "dtype": dt, "size": h, "clips": n, "flow_px_rms": px, "ms": round(ms, 4),
+                print(json.dumps({"kernel": "warp_fuse", "dtype": dt, "size": h, "clips": n, "flow_px_rms": px, "flow_kind": kind if px > 0 else "zero", "ms": round(ms, 4),
                                   "algorithmic_bytes": nbytes, "GBps": round(nbytes / ms / 1e6, 1), "frac_of_measured_hbm": round(nbytes / ms / 1e6 / peak, 4),
                                   "GBps_6plane": round(nbytes6 / ms / 1e6, 1),
                                   "note": "inputs of 16 clips (39-77 MB) fit the 126 MB L2" if n <= 16 else ""}), flush=True)

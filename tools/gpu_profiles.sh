@@ -21,9 +21,11 @@ echo "conv full $L exit $?"
 done
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:head_umma -s 1 -c 1 -o gpurun_out/prof_head_$TAG -f python tools/profile_forward.py 64 2 > gpurun_out/pf_ncu_head.log 2>&1
 echo "head full exit $?"
-timeout 300 python tools/bench_warp_fuse.py --once --dtypes bf16 > gpurun_out/wf_plain.log 2>&1 &&
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:warp_fuse -s 1 -c 1 -o gpurun_out/prof_wf_$TAG -f python tools/bench_warp_fuse.py --once --dtypes bf16 > gpurun_out/pf_ncu_wf.log 2>&1
-echo "wf full exit $?"
+for DT in bf16 fp32; do
+timeout 300 python tools/bench_warp_fuse.py --once --dtypes $DT > gpurun_out/wf_plain_$DT.log 2>&1 &&
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:warp_fuse -s 1 -c 1 -o gpurun_out/prof_wf_${DT}_$TAG -f python tools/bench_warp_fuse.py --once --dtypes $DT > gpurun_out/pf_ncu_wf_$DT.log 2>&1
+echo "wf full $DT exit $?"
+done
 timeout 300 python tools/bench_warp_fuse.py --clips 16 64 256 > gpurun_out/warp_fuse_sweep_$TAG.jsonl 2>&1
 timeout 300 python tools/bench_warp_fuse.py --clips 64 --size 224 --flow-px 0 4 >> gpurun_out/warp_fuse_sweep_$TAG.jsonl 2>&1
 timeout 200 python tools/conv_trace.py 200 bf16 > gpurun_out/conv_trace_$TAG.txt 2>&1
