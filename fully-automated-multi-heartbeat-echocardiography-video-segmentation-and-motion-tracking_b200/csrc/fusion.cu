@@ -276,7 +276,8 @@ constexpr int WS_MAX_UNITS = 8;
 //   bf16   512x7 0.82 / 0.92    768x5 1.10 / 1.17    1024x4 1.14 / 1.22 (64-register cap: spills and constant reloads)
 // Also measured and rejected for fp32: single pixels per item, so that the lanes' taps are one word apart instead of two
 // (no 2-way bank conflict under a smooth flow): twice the global load instructions cost more than the conflicts
-// (1.05-1.18 ms).
+// (1.05-1.18 ms in round 1; again on the flow-staged kernel, 14 single-pixel items per thread: 0.50-0.58 ms against 0.43-0.51,
+// profiles/r02u_warp_fuse_fp32_items.jsonl - twice the LDS / FADD instructions for the flows and the sums).
 constexpr int WS_THREADS_PER_CTA = 512, WS_ITEMS = 7;
 constexpr int WS_PP = 2;
 
