@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
     const int itt = r % p.bt; r /= p.bt;
     const int ib = r;
     int it = 0;
-    const uint32_t tempty_leader[2] = {CTAS == 2 ? map_to_cta(tempty_bar(0), 0) : 0u, CTAS == 2 ? map_to_cta(tempty_bar(1), 0) : 0u};
+    const uint32_t tempty_leader0 = CTAS == 2 ? map_to_cta(tempty_bar(0), 0) : 0u, tempty_leader1 = CTAS == 2 ? map_to_cta(tempty_bar(1), 0) : 0u;
     for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
       const int as = it & 1; const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const int n_tile = tile % p.tiles_n;
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) conv_umma_kernel(const __grid
       tc_fence_before();
       __syncwarp();
       // 8 arrivals (one per epilogue warp; 16 for a pair, on the leader's barrier) free the accumulator stage
-      if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(tempty_leader[as]); else mbar_arrive(tempty_bar(as)); }
+      if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(as ? tempty_leader1 : tempty_leader0); else mbar_arrive(tempty_bar(as)); }
     }
   }
 

@@ -77,8 +77,12 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
   uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
 }
+// Arrive on a barrier of another CTA of the cluster (address from map_to_cta).  Default semantics (.release.cta) as in
+// cutlass::arch::ClusterBarrier::arrive: what the arrival has to order is this warp's tensor-memory reads (tcgen05.fence::
+// before_thread_sync precedes it), not its global stores - `.release.cluster` compiled to MEMBAR.ALL.GPU + ERRBAR + MEMBAR.ALL.CTA
+// per arrival and those three were the most sampled instructions of the pair kernel (ncu source view, profiles/r02_summary.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
