@@ -163,8 +163,9 @@ class Engine:
         return out
 
     def set_option(self, name, value):
-        """``sub_batch`` (clips per internal batch of a forward call, default 16) or ``dense_video`` (0/1: share
-        the stem and layer1 between overlapping windows of one resident video, default on)."""
+        """``sub_batch`` (clips per internal batch of a forward call, default 16), ``dense_video`` (0/1: share
+        the stem and layer1 between overlapping windows of one resident video, default on) or ``umma_pair`` (0/1: the
+        convolutions of layers 2-4 on CTA pairs, default on; the outputs are the same bits either way)."""
         check(self.lib.clasfv_set_option(self._h, name.encode(), int(value)), f"clasfv_set_option({name})")
 
     def profile_begin(self):
