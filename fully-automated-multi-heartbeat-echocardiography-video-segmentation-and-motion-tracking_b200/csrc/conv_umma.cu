@@ -607,9 +607,12 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t stream) {
   // CTA pairs for the wide layers (layers 2-4; see the header): each CTA stages half the rows of a filter slab
   static const bool no_pair = getenv("CLASFV_UMMA_NO_PAIR") != nullptr;
   // (measured per layer, profiles/r02r_conv_trace_{pair,nopair}.txt: layers 2-4 gain - layer2 spatial 1 136 -> 1 250 TFLOP/s,
-  // layer2 temporal 695 -> 812, strided temporal 350 -> 548, layer3 temporal 796 -> 1 006; the short-K 64 -> 144 convolutions of
-  // layer1 (36 MMAs per tile: the pair's cross-CTA hand-shakes are not amortised) and the single-tap downsample projections lose)
-  const int ctas = (!no_pair && !a.no_pair && bn >= 128 && s.cin >= 128 && sp_taps > 1 && !a.seg.on && num_sms >= 2) ? 2 : 1;
+  // layer2 temporal 695 -> 812, strided temporal 350 -> 548, layer3 temporal 796 -> 1 006; the single-tap downsample projections
+  // lose and stay single-CTA.  The short-K 64 -> 144 / 64 -> 240 convolutions lost too (1 000 -> 756) while the peer's
+  // accumulator-empty arrive carried a GPU-scope fence (umma_ptx.cuh, mbar_arrive_cluster); without it they gain:
+  // 993 -> 1 032, 918 -> 1 037, profiles/r02h_conv_trace_pair_min_cin_{64,128}.txt.  CLASFV_UMMA_PAIR_MIN_CIN restores the narrower rule.)
+  static const int pair_min_cin = getenv("CLASFV_UMMA_PAIR_MIN_CIN") ? atoi(getenv("CLASFV_UMMA_PAIR_MIN_CIN")) : 0;
+  const int ctas = (!no_pair && !a.no_pair && bn >= 128 && s.cin >= pair_min_cin && sp_taps > 1 && !a.seg.on && num_sms >= 2) ? 2 : 1;
   p.b_slab_bytes = (bn / ctas) * SLAB_K * 2;
   p.n = s.n; p.to = s.to; p.ho = s.ho; p.wo = s.wo; p.cout = s.cout;
   // ---- K
